@@ -1,0 +1,214 @@
+/*
+ * qrmsa_b200.h -- C ABI of the B200-native batched QRMSA environment step.
+ *
+ * The reference (LEA-UFPA/optical-networking-gym) has no C ABI: its native boundary for this path
+ * is the Cython extension module `optical_networking_gym.envs.qrmsa`, reached through Python
+ * attribute access on a `QRMSAEnv` instance.  Each entry point below names the reference
+ * interface it stands in for (file:line under /root/reference).  The Python host layer
+ * (optical_networking_gym_b200/) binds these with ctypes and re-creates the QRMSAEnv
+ * reset/step/action-mask surface on top; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: plain C types only; every function returns a qrmsa_status (0 = OK) unless noted;
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream); pointers named d_* are
+ * device pointers on the context's device, h_* are host pointers (pinned or pageable).  One
+ * context per device; contexts share no global state, so eight can coexist in one process.
+ * There is NO CPU fallback: without a CUDA device qrmsa_create fails with QRMSA_ERR_NO_DEVICE.
+ */
+#ifndef QRMSA_B200_H
+#define QRMSA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qrmsa_ctx qrmsa_ctx;
+typedef struct qrmsa_tracegen qrmsa_tracegen;
+
+typedef enum qrmsa_status {
+    QRMSA_OK = 0,
+    QRMSA_ERR_ARG = 1,         /* bad argument                                             */
+    QRMSA_ERR_CUDA = 2,        /* CUDA runtime error; see qrmsa_last_error                 */
+    QRMSA_ERR_UNSUPPORTED = 3, /* configuration outside what the kernels implement         */
+    QRMSA_ERR_STATE = 4,       /* call order (e.g. step before a trace is loaded)          */
+    QRMSA_ERR_NO_DEVICE = 5,   /* no usable CUDA device: the product has no CPU path       */
+    QRMSA_ERR_ENV = 6          /* an environment raised: the reference would have thrown   */
+} qrmsa_status;
+
+/*
+ * Static description of one network + traffic classes, exported from the reference `topology`
+ * graph (reference topology.pyx:244-369: graph["ksp"], ["modulations"], ["node_indices"], edge
+ * attrs "index"/"link") and the QRMSAEnv constructor arguments (envs/qrmsa.pyx:206-237).
+ * Path p of the ordered pair (src,dst) has index (src*n_nodes + dst)*k_paths + p.
+ */
+typedef struct qrmsa_static_tables {
+    int32_t n_nodes, n_links, k_paths, n_mods, mods_to_consider, n_rates, n_slots, max_hops;
+    const uint8_t *path_hops;      /* [n_nodes*n_nodes*k_paths]            hops, 0 = no such path     */
+    const uint8_t *path_links;     /* [n_nodes*n_nodes*k_paths*max_hops]   link indices               */
+    const int32_t *link_n_spans;   /* [n_links]  spans per link (all spans of a link identical)        */
+    const double *link_span_len_m; /* [n_links]  span length, metres                                   */
+    const double *link_alpha;      /* [n_links]  Span.attenuation_normalized, 1/m (topology.pyx:21)    */
+    const double *link_nf;         /* [n_links]  Span.noise_figure_normalized (topology.pyx:23)        */
+    const int32_t *mod_se;         /* [n_mods]   Modulation.spectral_efficiency                        */
+    const double *mod_min_osnr;    /* [n_mods]   Modulation.minimum_osnr, dB                           */
+    const double *bit_rates;       /* [n_rates]  bit-rate classes (Gb/s)                               */
+    const uint8_t *slots_needed;   /* [n_rates*n_mods] QRMSAEnv.get_number_slots (qrmsa.pyx:1198-1205) */
+    double frequency_start;        /* Hz  (qrmsa.pyx:226)  */
+    double slot_bandwidth_hz;      /* Hz  (qrmsa.pyx:227)  */
+    double launch_power_w;         /* W   (qrmsa.pyx:288)  */
+    double margin_db;              /* dB  (qrmsa.pyx:228)  */
+} qrmsa_static_tables;
+
+/* Counter slots returned by qrmsa_counters (per env group), all int64. */
+enum {
+    QRMSA_CNT_DECIDED = 0,        /* requests decided (= env.step calls that consumed a request)     */
+    QRMSA_CNT_ACCEPTED = 1,       /* services_accepted            (qrmsa.pyx:1316-1317)              */
+    QRMSA_CNT_REJECTED = 2,       /* bl_reject                    (qrmsa.pyx:861-865)                */
+    QRMSA_CNT_RATE_REQUESTED = 3, /* sum of requested bit rates   (qrmsa.pyx:1106-1107)              */
+    QRMSA_CNT_RATE_PROVISIONED = 4, /* sum of provisioned rates   (qrmsa.pyx:1318-1321)              */
+    QRMSA_CNT_HOPS_ACCEPTED = 5,  /* sum of hops of accepted paths (h of SURVEY 8d)                  */
+    QRMSA_CNT_LINKS_READ = 6,     /* link bitmap rows read while deciding (Lr)                       */
+    QRMSA_CNT_RECORDS_READ = 7,   /* channel records on links of paths that had a QoT check (Nq)     */
+    QRMSA_CNT_GN_TERMS = 8,       /* (link, neighbour) terms summed by the GN model                  */
+    QRMSA_CNT_GN_EVALS = 9,       /* GSNR evaluations                                                */
+    QRMSA_CNT_RELEASES = 10,      /* services released            (qrmsa.pyx:1113-1122)              */
+    QRMSA_CNT_NEAR_THRESHOLD = 11, /* decisions with some |GSNR - threshold| < 1e-3 dB (flagged)     */
+    QRMSA_CNT_BLOCKED_RESOURCES = 12, /* heuristic return flag    (heuristics.py:966)                */
+    QRMSA_CNT_BLOCKED_OSNR = 13,
+    QRMSA_CNT_PATHS_TRIED = 14,
+    QRMSA_CNT_ERRORS = 15,        /* envs that hit an error state (list overflow, ValueError path)   */
+    QRMSA_CNT_MOD_HIST = 16,      /* [16..23] accepted services per modulation index                 */
+    QRMSA_N_COUNTERS = 32
+};
+
+/* Bits OR-ed into the per-request action word above bit 24 (see qrmsa_get_actions). */
+#define QRMSA_ACTION_MASK 0x00ffffffu
+#define QRMSA_FLAG_NEAR_THRESHOLD 0x80000000u /* some evaluated GSNR within 1e-3 dB of its threshold */
+#define QRMSA_FLAG_DECIDED 0x40000000u        /* the request has been decided                        */
+#define QRMSA_FLAG_ACCEPTED 0x20000000u
+
+/* step_action status per env (qrmsa.pyx:838-1065) */
+enum {
+    QRMSA_STEP_ACCEPTED = 0,
+    QRMSA_STEP_REJECT_ACTION = 1, /* action == k*M*S                               (qrmsa.pyx:861-865) */
+    QRMSA_STEP_NOT_FREE = 2,      /* is_path_free false: request NOT consumed      (qrmsa.pyx:886-897) */
+    QRMSA_STEP_LOW_GSNR = 3,      /* reference raises ValueError                   (qrmsa.pyx:925-929) */
+    QRMSA_STEP_IDLE = 4           /* env has no further request in the loaded trace                    */
+};
+
+const char *qrmsa_version(void);
+const char *qrmsa_strerror(int status);
+/* Last CUDA / validation message recorded on this context ("" if none). */
+const char *qrmsa_last_error(const qrmsa_ctx *ctx);
+
+/*
+ * Replaces: QRMSAEnv.__init__ (envs/qrmsa.pyx:206-415) for n_envs independent environments.
+ * Allocates all per-env state in device memory: packed per-link slot bitmaps (uint32 words, 1 =
+ * free; stands in for topology.graph["available_slots"], qrmsa.pyx:302-305), per-link channel
+ * lists (stand in for topology[u][v]["running_services"]), the request/service table and the
+ * release schedule.  max_requests = requests per episode (episode_length), <= 16384.
+ */
+int qrmsa_create(const qrmsa_static_tables *tables, int n_envs, int max_requests, int device, qrmsa_ctx **out);
+void qrmsa_destroy(qrmsa_ctx *ctx);
+
+/* Env groups (contiguous, equal-sized) for per-load-point counters; default 1. */
+int qrmsa_set_groups(qrmsa_ctx *ctx, int n_groups);
+/* Keep a per-request GSNR log (double, [n_envs][max_requests]); off by default. */
+int qrmsa_enable_gsnr_log(qrmsa_ctx *ctx, int enable);
+
+/*
+ * Replaces: QRMSAEnv.reset (envs/qrmsa.pyx:427-504) for every env: all slots free, lists empty,
+ * release queue cleared, episode counters zeroed.  The request stream of the new episode is
+ * attached with qrmsa_load_trace*, whose request 0 becomes the current request (reset's
+ * `_next_service()`, qrmsa.pyx:499-500).
+ */
+int qrmsa_reset(qrmsa_ctx *ctx, void *stream);
+
+/*
+ * Replaces: the per-request draws of QRMSAEnv._next_service/_get_node_pair
+ * (envs/qrmsa.pyx:1079-1099, :1134-1148) by replaying a recorded stream, and the release heap of
+ * _add_release (qrmsa.pyx:1327-1330) by a per-env release schedule sorted on the same key
+ * (float32(arrival + holding), service_id).  Arrays are [n_requests][n_envs] (request-major);
+ * n_requests <= max_requests.
+ */
+int qrmsa_load_trace(qrmsa_ctx *ctx, const uint8_t *d_src, const uint8_t *d_dst, const uint8_t *d_rate,
+                     const float *d_arrival, const float *d_holding, int n_requests, void *stream);
+int qrmsa_load_trace_host(qrmsa_ctx *ctx, const uint8_t *h_src, const uint8_t *h_dst, const uint8_t *h_rate,
+                          const float *h_arrival, const float *h_holding, int n_requests, void *stream);
+
+/*
+ * Replaces: n_steps iterations of the benchmark loop
+ *     action, _, _ = heuristic_shortest_available_path_first_fit_best_modulation(env)
+ *     env.step(action)
+ * (heuristics/heuristics.py:923-966, envs/qrmsa.pyx:838-1065, examples/JOCN_Benchmark_2024/
+ * graph_load.py:161-163) for every env, fused in one kernel launch: availability AND
+ * (qrmsa.pyx:1482-1512), first-fit with guard band (utils.pyx:44-58, qrmsa.pyx:515-541), GN-model
+ * GSNR (core/osnr.pyx:21-142), commit (qrmsa.pyx:1288-1330), next request + releases
+ * (qrmsa.pyx:1067-1122, :1332-1350).  Steps past the end of the loaded trace are not executed.
+ */
+int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream);
+
+/*
+ * Replaces: QRMSAEnv.step(action) (envs/qrmsa.pyx:838-1065) with one externally chosen action per
+ * env (RL path).  d_action int64[n_envs]; outputs (nullable) d_reward float[n_envs]
+ * (qrmsa.pyx:992-995, :1266-1285), d_status uint8[n_envs] (QRMSA_STEP_*), d_gsnr double[n_envs],
+ * d_terminated uint8[n_envs] (episode_services_processed == episode_length, qrmsa.pyx:1056).
+ */
+int qrmsa_step_action(qrmsa_ctx *ctx, const int64_t *d_action, float *d_reward, uint8_t *d_status, double *d_gsnr,
+                      uint8_t *d_terminated, void *stream);
+
+/*
+ * Decisions of requests [first, first+count) as int32 action words, [count][n_envs] request-major:
+ * low 24 bits = the reference's action index p*M*S + (max_mod_idx - m)*S + slot, reject = k*M*S
+ * (heuristics.py:36-54, qrmsa.pyx:319-321), high bits = QRMSA_FLAG_*.
+ */
+int qrmsa_get_actions(qrmsa_ctx *ctx, int first, int count, int32_t *d_out, void *stream);
+int qrmsa_get_actions_host(qrmsa_ctx *ctx, int first, int count, int32_t *h_out, void *stream);
+/* GSNR (dB) of the accepted candidate per request (0.0 on reject), needs qrmsa_enable_gsnr_log. */
+int qrmsa_get_gsnr_host(qrmsa_ctx *ctx, int first, int count, double *h_out, void *stream);
+
+/* Per-group counters, int64 [n_groups][QRMSA_N_COUNTERS]; synchronises the stream. */
+int qrmsa_counters(qrmsa_ctx *ctx, int64_t *h_out, void *stream);
+/* Same, left on the device (for the episode-end NCCL all-reduce): int64 [n_groups][QRMSA_N_COUNTERS]. */
+int qrmsa_counters_device(qrmsa_ctx *ctx, int64_t **d_out);
+/* Per-env progress: int32 [n_envs][4] = {current request index, accepted, rejected, error code}. */
+int qrmsa_env_state_host(qrmsa_ctx *ctx, int32_t *h_out, void *stream);
+
+/*
+ * Replaces: reading topology.graph["available_slots"] (int32 [E][S], 1 = free; qrmsa.pyx:302-305)
+ * of one env -- parity / debugging / the single-env view used by the Python heuristics.
+ */
+int qrmsa_export_slots(qrmsa_ctx *ctx, int env, int32_t *h_available_slots);
+/* Packed bitmaps of envs [first, first+count): uint32 [count][E][W], W = ceil(S/32). */
+int qrmsa_export_bitmaps(qrmsa_ctx *ctx, int first, int count, uint32_t *h_out);
+/* Channel list of one link (stand-in for topology[u][v]["running_services"]): int32 [cap][3] =
+ * (initial_slot, number_slots, modulation index); returns the count in *n. */
+int qrmsa_export_link_list(qrmsa_ctx *ctx, int env, int link, int32_t *h_out3, int cap, int *n);
+/*
+ * Replaces: core.osnr.calculate_osnr(env, service) (core/osnr.pyx:21-142) for a hypothetical
+ * service on path p of (src,dst) at (initial_slot, number_slots) against env's current state.
+ */
+int qrmsa_probe_gsnr(qrmsa_ctx *ctx, int env, int src, int dst, int p, int initial_slot, int number_slots,
+                     double *h_gsnr_db);
+
+/*
+ * Host-side request generator reproducing CPython 3.12 `random.Random(seed)` draw for draw
+ * (MT19937, expovariate, choices) in the order of QRMSAEnv._next_service (qrmsa.pyx:1079-1089)
+ * and _get_node_pair (qrmsa.pyx:1134-1148): env i is seeded with base_seed + i.
+ * h_load[n_envs] = offered load per env; h_src_cum[n_nodes] / h_dst_cum[n_nodes*n_nodes] /
+ * h_rate_cum[n_rates] are the cumulative weight tables `choices` bisects (built by the caller
+ * exactly as the reference builds its weights).  Pure host code, no GPU needed.
+ */
+int qrmsa_tracegen_create(int n_envs, uint64_t base_seed, int n_nodes, int n_rates, const double *h_load,
+                          double mean_holding_time, const double *h_src_cum, const double *h_dst_cum,
+                          const double *h_rate_cum, qrmsa_tracegen **out);
+/* Next n_requests of every env, arrays [n_requests][n_envs]; the clock persists across calls. */
+int qrmsa_tracegen_next(qrmsa_tracegen *gen, int n_requests, uint8_t *h_src, uint8_t *h_dst, uint8_t *h_rate,
+                        float *h_arrival, float *h_holding, int n_threads);
+void qrmsa_tracegen_destroy(qrmsa_tracegen *gen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRMSA_B200_H */

@@ -1,0 +1,205 @@
+"""ctypes binding of oracle/qrmsa_oracle.c.   TEST INFRASTRUCTURE ONLY.
+
+The oracle is the checker for the CUDA path (tests/, __graft_entry__.smoke(),
+bench.py's cpu_baseline leg).  The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "qrmsa_oracle.c")
+BUILD_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(BUILD_DIR, "libqrmsa_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        # no -ffast-math, no -march=native: must run unchanged on the GPU box's host CPU
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"], check=True)
+    return LIB
+
+
+class _Tables(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("n_nodes", "n_links", "k_paths", "n_mods", "mods_to_consider", "n_rates", "n_slots", "max_hops")] + [
+        ("path_hops", C.c_void_p), ("path_links", C.c_void_p), ("link_n_spans", C.c_void_p),
+        ("link_span_len_m", C.c_void_p), ("link_alpha", C.c_void_p), ("link_nf", C.c_void_p),
+        ("mod_se", C.c_void_p), ("mod_min_osnr", C.c_void_p), ("bit_rates", C.c_void_p),
+        ("slots_needed", C.c_void_p),
+        ("frequency_start", C.c_double), ("slot_bw", C.c_double), ("launch_power_w", C.c_double),
+        ("margin_db", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_create.restype = C.c_void_p
+        _lib.orc_create.argtypes = [C.POINTER(_Tables), C.c_int]
+        _lib.orc_destroy.argtypes = [C.c_void_p]
+        _lib.orc_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int]
+        _lib.orc_run_first_fit.restype = C.c_int
+        _lib.orc_run_first_fit.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+        _lib.orc_step_action.restype = C.c_int
+        _lib.orc_step_action.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int), C.c_int]
+        _lib.orc_get_slots.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_get_link_list.restype = C.c_int
+        _lib.orc_get_link_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.orc_probe_gsnr.restype = C.c_double
+        _lib.orc_probe_gsnr.argtypes = [C.c_void_p] + [C.c_int] * 5
+        _lib.orc_get_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_current_request.restype = C.c_int
+        _lib.orc_current_request.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+COUNTER_NAMES = ("processed", "accepted", "ep_processed", "ep_accepted", "bl_reject", "n_gn", "n_gn_terms",
+                 "n_links_read", "n_release", "hops_accepted", "heur_blk_res", "heur_blk_osnr")
+
+
+class OracleEnv:
+    """One scalar FP64 env.  `tables` is any object with the StaticTables attribute names."""
+
+    def __init__(self, tables, max_requests: int = 1):
+        L = lib()
+        self.tables = tables
+        self._keep = dict(
+            path_hops=np.ascontiguousarray(tables.path_hops, np.uint8),
+            path_links=np.ascontiguousarray(tables.path_links, np.uint8),
+            link_n_spans=np.ascontiguousarray(tables.link_n_spans, np.int32),
+            link_span_len_m=np.ascontiguousarray(tables.link_span_len_m, np.float64),
+            link_alpha=np.ascontiguousarray(tables.link_alpha, np.float64),
+            link_nf=np.ascontiguousarray(tables.link_nf, np.float64),
+            mod_se=np.ascontiguousarray(tables.mod_se, np.int32),
+            mod_min_osnr=np.ascontiguousarray(tables.mod_min_osnr, np.float64),
+            bit_rates=np.ascontiguousarray(tables.bit_rates, np.float64),
+            slots_needed=np.ascontiguousarray(tables.slots_needed, np.uint8),
+        )
+        t = _Tables()
+        for n in ("n_nodes", "n_links", "k_paths", "n_mods", "mods_to_consider", "n_rates", "n_slots", "max_hops"):
+            setattr(t, n, int(getattr(tables, n)))
+        for n, a in self._keep.items():
+            setattr(t, n, a.ctypes.data)
+        t.frequency_start = tables.frequency_start
+        t.slot_bw = tables.slot_bandwidth_hz
+        t.launch_power_w = tables.launch_power_w
+        t.margin_db = tables.margin_db
+        self._h = C.c_void_p(L.orc_create(C.byref(t), int(max_requests)))
+        self._trace = None
+        self.E, self.S = int(tables.n_links), int(tables.n_slots)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def reset(self, src, dst, rate, arrival, holding):
+        """Wipe the network and attach a request trace (request 0 becomes current)."""
+        tr = (np.ascontiguousarray(src, np.uint8), np.ascontiguousarray(dst, np.uint8),
+              np.ascontiguousarray(rate, np.uint8), np.ascontiguousarray(arrival, np.float32),
+              np.ascontiguousarray(holding, np.float32))
+        self._trace = tr
+        lib().orc_reset(self._h, *[_ptr(a) for a in tr], len(tr[0]))
+
+    def run_first_fit(self, n_steps: int, log_qot: bool = True):
+        action = np.zeros(n_steps, np.int32)
+        accepted = np.zeros(n_steps, np.uint8)
+        gsnr = np.zeros(n_steps, np.float64)
+        cap = n_steps * self.tables.k_paths * self.tables.n_mods if log_qot else 0
+        qs = np.zeros(max(cap, 1), np.int32)
+        qg = np.zeros(max(cap, 1), np.float64)
+        qt = np.zeros(max(cap, 1), np.float64)
+        qn = C.c_int(0)
+        rc = lib().orc_run_first_fit(self._h, n_steps, _ptr(action), _ptr(accepted), _ptr(gsnr),
+                                     _ptr(qs) if log_qot else None, _ptr(qg) if log_qot else None,
+                                     _ptr(qt) if log_qot else None, cap, C.byref(qn))
+        if rc != 0:
+            raise RuntimeError("oracle: trace exhausted (a step needs the following request)")
+        out = dict(action=action, accepted=accepted, gsnr=gsnr)
+        if log_qot:
+            out.update(qot_step=qs[: qn.value].copy(), qot_gsnr=qg[: qn.value].copy(), qot_thr=qt[: qn.value].copy())
+        return out
+
+    def step_action(self, action: int, episode_length: int):
+        rw, g, term = C.c_double(0), C.c_double(0), C.c_int(0)
+        st = lib().orc_step_action(self._h, int(action), C.byref(rw), C.byref(g), C.byref(term), int(episode_length))
+        return st, rw.value, g.value, bool(term.value)
+
+    def slots(self) -> np.ndarray:
+        out = np.zeros((self.E, self.S), np.uint8)
+        lib().orc_get_slots(self._h, _ptr(out))
+        return out
+
+    def link_list(self, link: int) -> np.ndarray:
+        out = np.zeros((self.S, 3), np.int32)
+        c = lib().orc_get_link_list(self._h, int(link), _ptr(out))
+        return out[:c].copy()
+
+    def probe_gsnr(self, src, dst, p, start, n) -> float:
+        return lib().orc_probe_gsnr(self._h, int(src), int(dst), int(p), int(start), int(n))
+
+    def counters(self) -> dict:
+        ci = np.zeros(20, np.int64)
+        cd = np.zeros(3, np.float64)
+        lib().orc_get_counters(self._h, _ptr(ci), _ptr(cd))
+        d = {n: int(ci[i]) for i, n in enumerate(COUNTER_NAMES)}
+        d["mod_hist"] = ci[12:20].copy()
+        d["bit_rate_requested"], d["bit_rate_provisioned"], d["now"] = (float(x) for x in cd)
+        return d
+
+    @property
+    def current_request(self) -> int:
+        return lib().orc_current_request(self._h)
+
+
+# ------------------------------------------------------------------------------------------------
+# Request generation restated with CPython's own `random` (exact by construction): the reference
+# draws, per request and in this order (envs/qrmsa.pyx:1079-1089, :1134-1148):
+#   expovariate(1/mean_iat), expovariate(1/mean_holding), choices(nodes, w), choices(nodes, w'),
+#   choices(bit_rates, probs, k=1)
+# ------------------------------------------------------------------------------------------------
+def generate_trace_python(n_nodes: int, n_rates: int, load: float, mean_holding: float, seed: int, n_requests: int,
+                          start_time: float = 0.0, rng=None):
+    import random
+
+    rng = rng if rng is not None else random.Random(seed)
+    mean_holding = float(np.float32(mean_holding))  # set_load takes a C float (qrmsa.pyx:1124)
+    mean_iat = 1 / (load / mean_holding)
+    nodes = list(range(n_nodes))
+    w = np.full((n_nodes,), fill_value=1.0 / n_nodes, dtype=np.float64)
+    probs = [1.0 / n_rates for _ in range(n_rates)]
+    src = np.zeros(n_requests, np.uint8)
+    dst = np.zeros(n_requests, np.uint8)
+    rate = np.zeros(n_requests, np.uint8)
+    arrival = np.zeros(n_requests, np.float32)
+    holding = np.zeros(n_requests, np.float32)
+    now = float(start_time)
+    for i in range(n_requests):
+        at = np.float32(now + rng.expovariate(1 / mean_iat))
+        now = float(at)
+        ht = np.float32(rng.expovariate(1.0 / mean_holding))
+        s = rng.choices(nodes, weights=w)[0]
+        w2 = np.copy(w)
+        w2[s] = 0.0
+        w2 /= np.sum(w2)
+        d = rng.choices(nodes, weights=w2)[0]
+        r = rng.choices(list(range(n_rates)), probs, k=1)[0]
+        src[i], dst[i], rate[i], arrival[i], holding[i] = s, d, r, at, ht
+    return dict(src=src, dst=dst, rate=rate, arrival=arrival, holding=holding), rng, now

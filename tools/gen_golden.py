@@ -1,0 +1,180 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* from the COMPILED reference (oracle/_ref).
+
+Runs only where /root/reference exists (this container); the fixtures it writes
+are committed so the GPU box and later sessions need neither the reference nor
+the 1-minute Cython build.  Everything written here is OUTPUT of the reference
+(request traces, decisions, GSNR values, slot matrices) or tables derived from
+its topology object -- no reference source.
+
+    python oracle/build_ref.py && python tools/gen_golden.py [--only NAME]
+
+Fixtures
+  tables_<topo>_<S>.npz      static tables exported from the reference topology object
+  run_<tag>.npz              one env, first-fit heuristic + step (graph_load.py:161-163 loop):
+                             trace, action/accepted/gsnr per step, every QoT check, slot snapshots
+  multi_<tag>.npz            many short envs (seeds base..base+n-1) for batched parity
+  rl_<tag>.npz               env.step() driven by externally chosen actions (valid, invalid, reject)
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+from optical_networking_gym_b200.tables import StaticTables  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+BIT_RATES = (10, 40, 100, 400, 1000)
+
+SINGLE = [
+    # tag, topology, S, load, seed, steps, snapshot_every
+    ("nobel-eu_320_l300_s50", "nobel-eu", 320, 300.0, 50, 3000, 500),
+    ("nsfnet_320_l300_s50", "nsfnet", 320, 300.0, 50, 10000, 2000),   # BASELINE config 1
+    ("germany50_640_l800_s52", "germany50", 640, 800.0, 52, 1500, 500),
+    ("nobel-eu_320_l500_s7", "nobel-eu", 320, 500.0, 7, 1500, 500),
+    ("ring4_320_l60_s3", "ring4", 320, 60.0, 3, 600, 200),
+]
+MULTI = [
+    # tag, topology, S, load, base_seed, n_envs, steps
+    ("nobel-eu_320_l300_b50", "nobel-eu", 320, 300.0, 50, 64, 400),
+    ("germany50_640_l800_b50", "germany50", 640, 800.0, 50, 8, 300),
+]
+RL = [
+    ("nsfnet_320_l210_s11", "nsfnet", 320, 210.0, 11, 400),
+]
+
+
+def tables_for(topo, S):
+    return StaticTables.from_topology(topo, num_spectrum_resources=S, bit_rates=BIT_RATES, launch_power_dbm=1.0,
+                                      margin=0.0, k_paths=5, modulations_to_consider=6)
+
+
+def gen_rl(topo, tb, S, load, seed, n_steps):
+    """Drive reference env.step() with a mix of first-fit, random-valid, invalid and reject actions."""
+    heur = rh.first_fit_heuristic()
+    env = rh.make_env(topo, seed, n_slots=S, load=load, episode_length=n_steps + 1)
+    node_index = {n: i for i, n in enumerate(topo.graph["node_indices"])}
+    rates = list(env.bit_rates)
+    rng = np.random.default_rng(seed)
+    rec = dict(src=[], dst=[], rate=[], arrival=[], holding=[], action=[], status=[], reward=[], gsnr=[], term=[])
+    snaps = []
+
+    def log_req(svc):
+        rec["src"].append(node_index[svc.source]); rec["dst"].append(node_index[svc.destination])
+        rec["rate"].append(rates.index(int(svc.bit_rate)))
+        rec["arrival"].append(np.float32(svc.arrival_time)); rec["holding"].append(np.float32(svc.holding_time))
+
+    log_req(env.current_service)
+    n_actions = env.action_space.n
+    consumed = 0
+    while consumed < n_steps:
+        kind = rng.integers(10)
+        a_ff, _, _ = heur(env)
+        if kind < 6:
+            a = a_ff
+        elif kind < 7:
+            a = n_actions - 1
+        else:
+            a = int(rng.integers(n_actions - 1))  # arbitrary: usually not free or GSNR too low
+        svc = env.current_service
+        before = svc.service_id
+        try:
+            _, reward, term, _, info = env.step(int(a))
+            if "osnr" not in info:      # early return: path/slot not free, request not consumed (qrmsa.pyx:886-897)
+                status, g = 2, 0.0
+            else:
+                status, g = (1 if a == n_actions - 1 else 0), info["osnr"]
+        except ValueError:
+            # GSNR below threshold: the reference raises (qrmsa.pyx:925-929) and leaves the state untouched
+            status, reward, term, g = 3, 0.0, False, float("nan")
+        rec["action"].append(a); rec["status"].append(status); rec["reward"].append(reward)
+        rec["gsnr"].append(g); rec["term"].append(bool(term))
+        if status in (0, 1):
+            consumed += 1
+            assert env.current_service.service_id == before + 1
+            log_req(env.current_service)
+        else:
+            assert env.current_service.service_id == before
+        snaps.append(np.packbits(np.array(env.topology.graph["available_slots"], np.uint8), axis=1))
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["src"] = out["src"].astype(np.uint8); out["dst"] = out["dst"].astype(np.uint8)
+    out["rate"] = out["rate"].astype(np.uint8)
+    out["arrival"] = out["arrival"].astype(np.float32); out["holding"] = out["holding"].astype(np.float32)
+    out["action"] = out["action"].astype(np.int64); out["status"] = out["status"].astype(np.uint8)
+    out["slots_packed_last"] = snaps[-1]
+    out["slots_packed_every"] = np.array(snaps[::25])
+    out["final_slots"] = np.array(env.topology.graph["available_slots"], np.uint8)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    topo_cache = {}
+
+    def topo_of(name):
+        if name not in topo_cache:
+            topo_cache[name] = rh.make_topology(name)
+        return topo_cache[name]
+
+    for tag, name, S, load, seed, steps, snap in SINGLE:
+        if args.only and args.only not in tag:
+            continue
+        t0 = time.time()
+        topo = topo_of(name)
+        tb = tables_for(topo, S)
+        tb.save(os.path.join(GOLDEN, f"tables_{name}_{S}.npz"))
+        out, _ = rh.run_first_fit(topo, seed, steps, snapshot_every=snap, n_slots=S, load=load)
+        out["snap_slots"] = np.packbits(out["snap_slots"], axis=2)
+        out["meta_load"] = np.float64(load); out["meta_seed"] = np.int64(seed)
+        np.savez_compressed(os.path.join(GOLDEN, f"run_{tag}.npz"), **out)
+        print(f"run_{tag}: {steps} steps, accept {out['accepted'].mean():.3f}, {time.time() - t0:.1f}s")
+
+    for tag, name, S, load, base, n_envs, steps in MULTI:
+        if args.only and args.only not in tag:
+            continue
+        t0 = time.time()
+        topo = topo_of(name)
+        tables_for(topo, S).save(os.path.join(GOLDEN, f"tables_{name}_{S}.npz"))
+        keys = ("src", "dst", "rate", "arrival", "holding", "action", "accepted", "gsnr", "final_slots")
+        acc = {k: [] for k in keys}
+        qn, qg, qt, qs = [], [], [], []
+        for i in range(n_envs):
+            out, _ = rh.run_first_fit(topo, base + i, steps, n_slots=S, load=load)
+            for k in keys:
+                acc[k].append(out[k])
+            qn.append(len(out["qot_gsnr"])); qg.append(out["qot_gsnr"]); qt.append(out["qot_thr"]); qs.append(out["qot_step"])
+        d = {k: np.array(v) for k, v in acc.items()}
+        d["final_slots"] = np.packbits(d["final_slots"], axis=2)
+        d["qot_count"] = np.array(qn, np.int32)
+        d["qot_gsnr"] = np.concatenate(qg); d["qot_thr"] = np.concatenate(qt); d["qot_step"] = np.concatenate(qs)
+        d["meta_load"] = np.float64(load); d["meta_seed"] = np.int64(base)
+        np.savez_compressed(os.path.join(GOLDEN, f"multi_{tag}.npz"), **d)
+        print(f"multi_{tag}: {n_envs} envs x {steps} steps, {time.time() - t0:.1f}s")
+
+    for tag, name, S, load, seed, steps in RL:
+        if args.only and args.only not in tag:
+            continue
+        t0 = time.time()
+        topo = topo_of(name)
+        tb = tables_for(topo, S)
+        tb.save(os.path.join(GOLDEN, f"tables_{name}_{S}.npz"))
+        out = gen_rl(topo, tb, S, load, seed, steps)
+        out["meta_load"] = np.float64(load); out["meta_seed"] = np.int64(seed)
+        np.savez_compressed(os.path.join(GOLDEN, f"rl_{tag}.npz"), **out)
+        st = out["status"]
+        print(f"rl_{tag}: {len(st)} calls, status counts {np.bincount(st, minlength=4)}, {time.time() - t0:.1f}s")
+
+
+if __name__ == "__main__":
+    main()
