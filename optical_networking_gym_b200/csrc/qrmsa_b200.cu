@@ -1,0 +1,509 @@
+// qrmsa_b200.cu -- C ABI (include/qrmsa_b200.h) over the sm_100a kernels of qrmsa_kernels.cuh.
+// Host code: context / memory management, GN-table construction, launches.  No torch types.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "qrmsa_kernels.cuh"
+
+using namespace qrmsa;
+
+struct qrmsa_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int threads = 512;
+    int grid = 0;
+    int n_groups = 1;
+    int max_need = 1;
+    KParams kp{};
+    std::vector<void *> allocs;
+    // staging for host-buffer entry points
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    int64_t *h_counters = nullptr;  // pinned
+    std::vector<uint8_t> need, cls;
+    std::vector<int> cls_n;
+    std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                             \
+            return QRMSA_ERR_CUDA;                                                                     \
+        }                                                                                              \
+    } while (0)
+
+template <class T>
+int dev_alloc(qrmsa_ctx *ctx, T **out, size_t count) {
+    void *p = nullptr;
+    CK(cudaMalloc(&p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+    ctx->allocs.push_back(p);
+    *out = (T *)p;
+    return QRMSA_OK;
+}
+
+template <class T>
+int dev_upload(qrmsa_ctx *ctx, const T **out, const T *host, size_t count) {
+    T *p = nullptr;
+    int rc = dev_alloc(ctx, &p, count);
+    if (rc) return rc;
+    CK(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = p;
+    return QRMSA_OK;
+}
+
+size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+int ensure_stage(qrmsa_ctx *ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return QRMSA_OK;
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    CK(cudaMalloc(&ctx->stage, bytes));
+    ctx->stage_bytes = bytes;
+    return QRMSA_OK;
+}
+
+struct Blob {
+    std::vector<unsigned char> bytes;
+    int add(const void *src, size_t n) {
+        size_t off = round_up(bytes.size(), 16);
+        bytes.resize(off + n);
+        memcpy(bytes.data() + off, src, n);
+        return (int)off;
+    }
+};
+
+const double PHI_MOD[6] = {1.0, 1.0, 2.0 / 3.0, 17.0 / 25.0, 69.0 / 100.0, 13.0 / 21.0};  // osnr.pyx:38-41
+
+}  // namespace
+
+extern "C" const char *qrmsa_version(void) { return "qrmsa_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *qrmsa_strerror(int s) {
+    switch (s) {
+        case QRMSA_OK: return "ok";
+        case QRMSA_ERR_ARG: return "invalid argument";
+        case QRMSA_ERR_CUDA: return "CUDA runtime error";
+        case QRMSA_ERR_UNSUPPORTED: return "unsupported configuration";
+        case QRMSA_ERR_STATE: return "invalid call order";
+        case QRMSA_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case QRMSA_ERR_ENV: return "an environment is in an error state";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char *qrmsa_last_error(const qrmsa_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+extern "C" void qrmsa_destroy(qrmsa_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    delete ctx;
+}
+
+static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs, int max_requests) {
+    KParams &kp = ctx->kp;
+    const int N = t->n_nodes, E = t->n_links, K = t->k_paths, M = t->n_mods, R = t->n_rates, S = t->n_slots;
+    kp.n_envs = n_envs; kp.N = N; kp.E = E; kp.K = K; kp.M = M; kp.Mc = t->mods_to_consider; kp.R = R; kp.S = S;
+    kp.W = (S + 31) / 32;
+    kp.Hmax = t->max_hops;
+    kp.D = 2 * S;
+    kp.CAP = (int)round_up((size_t)(S + 1) / 2, 32);
+    kp.T = max_requests;
+    kp.n_req = 0;
+    kp.group_size = n_envs;
+    kp.f0 = t->frequency_start;
+    kp.sb = t->slot_bandwidth_hz;
+
+    // ---- validation of what the kernels implement
+    if (S < 2 || S > 960) { ctx->err = "n_slots must be in 2..960 (one bitmap word per lane + the virtual slot)"; return QRMSA_ERR_UNSUPPORTED; }
+    if (t->max_hops > 32) { ctx->err = "paths longer than 32 hops"; return QRMSA_ERR_UNSUPPORTED; }
+    if (M > 8 || R > 255 || N > 255 || E > 255 || K > 255) { ctx->err = "table dimension too large"; return QRMSA_ERR_UNSUPPORTED; }
+    if (kp.Mc != M) { ctx->err = "modulations_to_consider must equal the number of modulations"; return QRMSA_ERR_UNSUPPORTED; }
+    if ((long long)K * M * S >= (1 << 24)) { ctx->err = "action space exceeds 24 bits"; return QRMSA_ERR_UNSUPPORTED; }
+    if (max_requests < 2 || max_requests > 16384) { ctx->err = "max_requests must be in 2..16384"; return QRMSA_ERR_UNSUPPORTED; }
+    for (int l = 1; l < E; l++)
+        if (t->link_alpha[l] != t->link_alpha[0]) { ctx->err = "per-link attenuation must be uniform (one G table)"; return QRMSA_ERR_UNSUPPORTED; }
+    for (int m = 0; m < M; m++)
+        if (t->mod_se[m] < 1 || t->mod_se[m] > 6) { ctx->err = "spectral efficiency outside 1..6 (phi table, osnr.pyx:38-41)"; return QRMSA_ERR_UNSUPPORTED; }
+
+    // ---- slot classes
+    ctx->need.assign(t->slots_needed, t->slots_needed + (size_t)R * M);
+    std::vector<int> cls_n;
+    for (uint8_t v : ctx->need) {
+        if (v < 1) { ctx->err = "slots_needed must be >= 1"; return QRMSA_ERR_UNSUPPORTED; }
+        bool seen = false;
+        for (int c : cls_n) seen |= (c == v);
+        if (!seen) cls_n.push_back(v);
+        if (v > ctx->max_need) ctx->max_need = v;
+    }
+    for (size_t i = 0; i < cls_n.size(); i++)
+        for (size_t j = i + 1; j < cls_n.size(); j++)
+            if (cls_n[j] < cls_n[i]) std::swap(cls_n[i], cls_n[j]);
+    const int NC = (int)cls_n.size();
+    if (NC > 32) { ctx->err = "more than 32 distinct slot counts"; return QRMSA_ERR_UNSUPPORTED; }
+    kp.NC = NC;
+    ctx->cls_n = cls_n;
+    ctx->cls.resize((size_t)R * M);
+    for (size_t i = 0; i < ctx->need.size(); i++)
+        for (int c = 0; c < NC; c++)
+            if (cls_n[c] == ctx->need[i]) ctx->cls[i] = (uint8_t)c;
+    if ((S >> 5) + ((ctx->max_need + 1) >> 5) + 2 > 32) { ctx->err = "bitmap + shift distance exceed one warp"; return QRMSA_ERR_UNSUPPORTED; }
+
+    // ---- GN tables (core/osnr.pyx:21-142), FP64, host libm
+    const double beta_2 = -21.3e-27, gamma = 1.3e-3, h_plank = 6.626e-34, pi = M_PI;
+    const double alpha = t->link_alpha[0], sb = t->slot_bandwidth_hz, P = t->launch_power_w;
+    const double l_eff_a = 1.0 / (2.0 * alpha);
+    const int D = kp.D;
+    std::vector<double> G((size_t)NC * D), INV(D), PHIN(256, 0.0), W1(E), W2(E), SELF(NC), CN(NC), ASEC(NC), THR(M);
+    for (int c = 0; c < NC; c++) {
+        const double bw_r = sb * cls_n[c];
+        for (int d = 0; d < D; d++) {
+            const double df = (sb / 2.0) * d;
+            G[(size_t)c * D + d] = asinh(pi * pi * fabs(beta_2) * l_eff_a * bw_r * (df + (bw_r / 2.0))) -
+                                   asinh(pi * pi * fabs(beta_2) * l_eff_a * bw_r * (df - (bw_r / 2.0)));
+        }
+        for (int m = 0; m < M; m++) PHIN[(c << 3) | m] = PHI_MOD[t->mod_se[m] - 1] * bw_r;
+        const double bw = bw_r;
+        SELF[c] = asinh(pi * pi * fabs(beta_2) * (bw * bw) / (4.0 * alpha));
+        CN[c] = pow(P / bw, 3.0) * (8.0 / (27.0 * pi * fabs(beta_2))) * (gamma * gamma) * bw / P;
+        ASEC[c] = bw * h_plank / P;
+    }
+    INV[0] = 0.0;
+    for (int d = 1; d < D; d++) INV[d] = 1.0 / ((sb / 2.0) * d);
+    std::vector<double> leff(E), ex(E);
+    for (int l = 0; l < E; l++) {
+        const double len = t->link_span_len_m[l];
+        leff[l] = (1.0 - exp(-2.0 * alpha * len)) / (2.0 * alpha);
+        ex[l] = (exp(2.0 * alpha * len) - 1.0) * t->link_nf[l];
+        W1[l] = t->link_n_spans[l] * leff[l];
+        W2[l] = t->link_n_spans[l] * leff[l] * (5.0 / 3.0) * (leff[l] / len);
+    }
+    for (int m = 0; m < M; m++) THR[m] = t->mod_min_osnr[m] + t->margin_db;
+    const size_t n_paths = (size_t)N * N * K;
+    std::vector<double2> pgn(n_paths);
+    for (size_t pi_ = 0; pi_ < n_paths; pi_++) {
+        double pa = 0.0, pb = 0.0;
+        const int hops = t->path_hops[pi_];
+        if (hops > t->max_hops) { ctx->err = "path_hops exceeds max_hops"; return QRMSA_ERR_ARG; }
+        for (int h = 0; h < hops; h++) {
+            const int l = t->path_links[pi_ * t->max_hops + h];
+            if (l >= E) { ctx->err = "link index out of range"; return QRMSA_ERR_ARG; }
+            pa += t->link_n_spans[l] * ex[l];
+            pb += W1[l];
+        }
+        pgn[pi_] = make_double2(pa, pb);
+    }
+    std::vector<int32_t> rate_milli(R);
+    for (int r = 0; r < R; r++) rate_milli[r] = (int32_t)llround(t->bit_rates[r] * 1000.0);
+
+    Blob blob;
+    kp.oG = blob.add(G.data(), G.size() * 8);
+    kp.oINV = blob.add(INV.data(), INV.size() * 8);
+    kp.oPHIN = blob.add(PHIN.data(), PHIN.size() * 8);
+    kp.oW1 = blob.add(W1.data(), W1.size() * 8);
+    kp.oW2 = blob.add(W2.data(), W2.size() * 8);
+    kp.oSELF = blob.add(SELF.data(), SELF.size() * 8);
+    kp.oCN = blob.add(CN.data(), CN.size() * 8);
+    kp.oASEC = blob.add(ASEC.data(), ASEC.size() * 8);
+    kp.oTHR = blob.add(THR.data(), THR.size() * 8);
+    kp.oNEED = blob.add(ctx->need.data(), ctx->need.size());
+    kp.oCLS = blob.add(ctx->cls.data(), ctx->cls.size());
+    kp.oRATE = blob.add(rate_milli.data(), rate_milli.size() * 4);
+    blob.bytes.resize(round_up(blob.bytes.size(), 16));
+    kp.blob_bytes = (int)blob.bytes.size();
+
+    // ---- device properties and launch shape
+    CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+    CK(cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    int smem_sm = 0;
+    CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    if (kp.blob_bytes + 64 > ctx->smem_optin) {
+        ctx->err = "GN tables (" + std::to_string(kp.blob_bytes) + " B) exceed shared memory per block";
+        return QRMSA_ERR_UNSUPPORTED;
+    }
+    int ctas_per_sm = 1;
+    ctx->threads = 1024;
+    if (2 * (size_t)(kp.blob_bytes + 1024 + 64) <= (size_t)smem_sm) { ctas_per_sm = 2; ctx->threads = 512; }
+    const int wpc = ctx->threads / 32;
+    const int want = (n_envs + wpc - 1) / wpc;
+    ctx->grid = want < ctx->sm_count * ctas_per_sm ? want : ctx->sm_count * ctas_per_sm;
+    CK(cudaFuncSetAttribute(k_step_first_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_action, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_probe_gsnr, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_build_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+
+    // ---- uploads and state
+    int rc;
+    if ((rc = dev_upload(ctx, &kp.path_hops, t->path_hops, n_paths))) return rc;
+    if ((rc = dev_upload(ctx, &kp.path_links, t->path_links, n_paths * t->max_hops))) return rc;
+    if ((rc = dev_upload(ctx, &kp.path_gn, pgn.data(), n_paths))) return rc;
+    if ((rc = dev_upload(ctx, &kp.blob, blob.bytes.data(), blob.bytes.size()))) return rc;
+    kp.bm_stride = round_up((size_t)E * kp.W, 32);
+    kp.cnt_stride = round_up((size_t)E, 64);
+    if ((rc = dev_alloc(ctx, &kp.bm, (size_t)n_envs * kp.bm_stride))) return rc;
+    if ((rc = dev_alloc(ctx, &kp.cnt, (size_t)n_envs * kp.cnt_stride))) return rc;
+    if ((rc = dev_alloc(ctx, &kp.lists, (size_t)n_envs * E * kp.CAP))) return rc;
+    if ((rc = dev_alloc(ctx, &kp.trace, (size_t)n_envs * kp.T))) return rc;
+    if ((rc = dev_alloc(ctx, &kp.perm, (size_t)n_envs * kp.T))) return rc;
+    if ((rc = dev_alloc(ctx, &kp.estate, (size_t)n_envs))) return rc;
+    if ((rc = dev_alloc(ctx, &kp.counters, (size_t)QRMSA_N_COUNTERS * 1))) return rc;
+    CK(cudaMemset(kp.counters, 0, sizeof(unsigned long long) * QRMSA_N_COUNTERS));
+    CK(cudaMallocHost((void **)&ctx->h_counters, sizeof(int64_t) * QRMSA_N_COUNTERS));
+    kp.gsnr_log = nullptr;
+    k_reset<<<ctx->sm_count * 4, 256>>>(kp);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_create(const qrmsa_static_tables *t, int n_envs, int max_requests, int device, qrmsa_ctx **out) {
+    if (!t || !out || n_envs <= 0) return QRMSA_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return QRMSA_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return QRMSA_ERR_NO_DEVICE;
+    qrmsa_ctx *ctx = new qrmsa_ctx();
+    ctx->device = device;
+    int rc = create_impl(ctx, t, n_envs, max_requests);
+    *out = ctx;  // returned even on failure so that qrmsa_last_error can be read; caller destroys it
+    return rc;
+}
+
+extern "C" int qrmsa_set_groups(qrmsa_ctx *ctx, int n_groups) {
+    if (!ctx || n_groups < 1 || ctx->kp.n_envs % n_groups) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long *c = nullptr;
+    int rc = dev_alloc(ctx, &c, (size_t)QRMSA_N_COUNTERS * n_groups);
+    if (rc) return rc;
+    CK(cudaMemset(c, 0, sizeof(unsigned long long) * QRMSA_N_COUNTERS * n_groups));
+    ctx->kp.counters = c;
+    ctx->n_groups = n_groups;
+    ctx->kp.group_size = ctx->kp.n_envs / n_groups;
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    CK(cudaMallocHost((void **)&ctx->h_counters, sizeof(int64_t) * QRMSA_N_COUNTERS * n_groups));
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_enable_gsnr_log(qrmsa_ctx *ctx, int enable) {
+    if (!ctx) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (enable && !ctx->kp.gsnr_log) {
+        int rc = dev_alloc(ctx, &ctx->kp.gsnr_log, (size_t)ctx->kp.n_envs * ctx->kp.T);
+        if (rc) return rc;
+        CK(cudaMemset(ctx->kp.gsnr_log, 0, sizeof(double) * (size_t)ctx->kp.n_envs * ctx->kp.T));
+    }
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_reset(qrmsa_ctx *ctx, void *stream) {
+    if (!ctx) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->kp.n_req = 0;
+    k_reset<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->kp);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->kp.counters, 0, sizeof(unsigned long long) * QRMSA_N_COUNTERS * ctx->n_groups, st));
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_load_trace(qrmsa_ctx *ctx, const uint8_t *d_src, const uint8_t *d_dst, const uint8_t *d_rate,
+                                const float *d_arrival, const float *d_holding, int n_requests, void *stream) {
+    if (!ctx || !d_src || !d_dst || !d_rate || !d_arrival || !d_holding) return QRMSA_ERR_ARG;
+    if (n_requests < 1 || n_requests > ctx->kp.T) { ctx->err = "n_requests outside 1..max_requests"; return QRMSA_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    KParams &kp = ctx->kp;
+    kp.n_req = n_requests;
+    dim3 grid((kp.n_envs + 31) / 32, (n_requests + 31) / 32);
+    k_ingest_trace<<<grid, 256, 0, st>>>(kp, d_src, d_dst, d_rate, d_arrival, d_holding, n_requests);
+    CK(cudaGetLastError());
+    int n_pad = 2;
+    while (n_pad < n_requests) n_pad <<= 1;
+    int threads = n_pad / 2 < 1024 ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : 1024;
+    int blocks = kp.n_envs < ctx->sm_count * 8 ? kp.n_envs : ctx->sm_count * 8;
+    k_build_schedule<<<blocks, threads, (size_t)n_pad * 8, st>>>(kp, n_requests, n_pad);
+    CK(cudaGetLastError());
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_load_trace_host(qrmsa_ctx *ctx, const uint8_t *h_src, const uint8_t *h_dst, const uint8_t *h_rate,
+                                     const float *h_arrival, const float *h_holding, int n_requests, void *stream) {
+    if (!ctx || !h_src || !h_dst || !h_rate || !h_arrival || !h_holding) return QRMSA_ERR_ARG;
+    if (n_requests < 1 || n_requests > ctx->kp.T) { ctx->err = "n_requests outside 1..max_requests"; return QRMSA_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)n_requests * ctx->kp.n_envs;
+    const size_t nb = round_up(n, 256);
+    int rc = ensure_stage(ctx, nb * 3 + nb * 8);
+    if (rc) return rc;
+    unsigned char *base = (unsigned char *)ctx->stage;
+    float *d_arr = (float *)base, *d_hold = (float *)(base + nb * 4);
+    uint8_t *d_src = base + nb * 8, *d_dst = d_src + nb, *d_rate = d_dst + nb;
+    CK(cudaMemcpyAsync(d_arr, h_arrival, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_hold, h_holding, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_src, h_src, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_dst, h_dst, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_rate, h_rate, n, cudaMemcpyHostToDevice, st));
+    return qrmsa_load_trace(ctx, d_src, d_dst, d_rate, d_arr, d_hold, n_requests, stream);
+}
+
+extern "C" int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream) {
+    if (!ctx || n_steps < 0) return QRMSA_ERR_ARG;
+    if (ctx->kp.n_req < 2) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
+    if (n_steps == 0) return QRMSA_OK;
+    CK(cudaSetDevice(ctx->device));
+    k_step_first_fit<<<ctx->grid, ctx->threads, ctx->kp.blob_bytes, (cudaStream_t)stream>>>(ctx->kp, n_steps);
+    CK(cudaGetLastError());
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_step_action(qrmsa_ctx *ctx, const int64_t *d_action, float *d_reward, uint8_t *d_status,
+                                 double *d_gsnr, uint8_t *d_terminated, void *stream) {
+    if (!ctx || !d_action) return QRMSA_ERR_ARG;
+    if (ctx->kp.n_req < 2) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    k_step_action<<<ctx->grid, ctx->threads, ctx->kp.blob_bytes, (cudaStream_t)stream>>>(
+        ctx->kp, (const long long *)d_action, d_reward, d_status, d_gsnr, d_terminated, ctx->kp.n_req);
+    CK(cudaGetLastError());
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_get_actions(qrmsa_ctx *ctx, int first, int count, int32_t *d_out, void *stream) {
+    if (!ctx || !d_out || first < 0 || count < 0 || first + count > ctx->kp.n_req) return QRMSA_ERR_ARG;
+    if (count == 0) return QRMSA_OK;
+    CK(cudaSetDevice(ctx->device));
+    dim3 grid((ctx->kp.n_envs + 31) / 32, (count + 31) / 32);
+    k_gather_actions<<<grid, 256, 0, (cudaStream_t)stream>>>(ctx->kp, first, count, d_out);
+    CK(cudaGetLastError());
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_get_actions_host(qrmsa_ctx *ctx, int first, int count, int32_t *h_out, void *stream) {
+    if (!ctx || !h_out || first < 0 || count < 0 || first + count > ctx->kp.n_req) return QRMSA_ERR_ARG;
+    if (count == 0) return QRMSA_OK;
+    const size_t bytes = (size_t)count * ctx->kp.n_envs * 4;
+    int rc = ensure_stage(ctx, bytes);
+    if (rc) return rc;
+    rc = qrmsa_get_actions(ctx, first, count, (int32_t *)ctx->stage, stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out, ctx->stage, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_get_gsnr_host(qrmsa_ctx *ctx, int first, int count, double *h_out, void *stream) {
+    if (!ctx || !h_out || first < 0 || count < 0 || first + count > ctx->kp.n_req) return QRMSA_ERR_ARG;
+    if (!ctx->kp.gsnr_log) { ctx->err = "GSNR log not enabled"; return QRMSA_ERR_STATE; }
+    if (count == 0) return QRMSA_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)count * ctx->kp.n_envs * 8;
+    int rc = ensure_stage(ctx, bytes);
+    if (rc) return rc;
+    k_gather_gsnr<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(ctx->kp, first, count, (double *)ctx->stage);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_out, ctx->stage, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_counters(qrmsa_ctx *ctx, int64_t *h_out, void *stream) {
+    if (!ctx || !h_out) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(int64_t) * QRMSA_N_COUNTERS * ctx->n_groups;
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->kp.counters, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    memcpy(h_out, ctx->h_counters, bytes);
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_counters_device(qrmsa_ctx *ctx, int64_t **d_out) {
+    if (!ctx || !d_out) return QRMSA_ERR_ARG;
+    *d_out = (int64_t *)ctx->kp.counters;
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_env_state_host(qrmsa_ctx *ctx, int32_t *h_out, void *stream) {
+    if (!ctx || !h_out) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->kp.n_envs;
+    std::vector<int4> tmp(n);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->kp.estate, sizeof(int4) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < n; i++) {
+        h_out[4 * i + 0] = tmp[i].x;
+        h_out[4 * i + 1] = tmp[i].z;
+        h_out[4 * i + 2] = tmp[i].x - tmp[i].z;
+        h_out[4 * i + 3] = tmp[i].w;
+    }
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_export_bitmaps(qrmsa_ctx *ctx, int first, int count, uint32_t *h_out) {
+    if (!ctx || !h_out || first < 0 || count < 0 || first + count > ctx->kp.n_envs) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    const KParams &kp = ctx->kp;
+    const size_t row = (size_t)kp.E * kp.W;
+    CK(cudaMemcpy2D(h_out, row * 4, kp.bm + (size_t)first * kp.bm_stride, kp.bm_stride * 4, row * 4, count,
+                    cudaMemcpyDeviceToHost));
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_export_slots(qrmsa_ctx *ctx, int env, int32_t *h_slots) {
+    if (!ctx || !h_slots || env < 0 || env >= ctx->kp.n_envs) return QRMSA_ERR_ARG;
+    const KParams &kp = ctx->kp;
+    std::vector<uint32_t> words((size_t)kp.E * kp.W);
+    int rc = qrmsa_export_bitmaps(ctx, env, 1, words.data());
+    if (rc) return rc;
+    for (int l = 0; l < kp.E; l++)
+        for (int s = 0; s < kp.S; s++) h_slots[(size_t)l * kp.S + s] = (words[(size_t)l * kp.W + (s >> 5)] >> (s & 31)) & 1u;
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_export_link_list(qrmsa_ctx *ctx, int env, int link, int32_t *h_out3, int cap, int *n) {
+    if (!ctx || !h_out3 || !n || env < 0 || env >= ctx->kp.n_envs || link < 0 || link >= ctx->kp.E) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    const KParams &kp = ctx->kp;
+    uint16_t c = 0;
+    CK(cudaMemcpy(&c, kp.cnt + (size_t)env * kp.cnt_stride + link, 2, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> recs(kp.CAP);
+    CK(cudaMemcpy(recs.data(), kp.lists + ((size_t)env * kp.E + link) * kp.CAP, (size_t)kp.CAP * 4, cudaMemcpyDeviceToHost));
+    *n = c;
+    for (int i = 0; i < c && i < cap; i++) {
+        const uint32_t r = recs[i];
+        const int nn = (r >> 12) & 0xff;
+        h_out3[3 * i + 0] = ((int)(r & 0xfff) - nn) / 2;
+        h_out3[3 * i + 1] = nn;
+        h_out3[3 * i + 2] = (r >> 20) & 7;
+    }
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_probe_gsnr(qrmsa_ctx *ctx, int env, int src, int dst, int p, int initial_slot, int number_slots,
+                                double *h_gsnr_db) {
+    if (!ctx || !h_gsnr_db || env < 0 || env >= ctx->kp.n_envs) return QRMSA_ERR_ARG;
+    const KParams &kp = ctx->kp;
+    if (src < 0 || src >= kp.N || dst < 0 || dst >= kp.N || p < 0 || p >= kp.K || initial_slot < 0 ||
+        number_slots < 1 || initial_slot + number_slots > kp.S)
+        return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_stage(ctx, 256);
+    if (rc) return rc;
+    k_probe_gsnr<<<1, 32, kp.blob_bytes>>>(kp, env, src, dst, p, initial_slot, number_slots, (double *)ctx->stage);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(h_gsnr_db, ctx->stage, 8, cudaMemcpyDeviceToHost));
+    return QRMSA_OK;
+}

@@ -1,0 +1,675 @@
+// qrmsa_kernels.cuh -- sm_100a device code of the batched QRMSA environment step.
+//
+// Execution model: ONE WARP PER ENVIRONMENT.  Lane j holds word j of a 320/640-slot availability
+// bitmap, so the AND along a path, the contiguous-block search and the commit/release masks are
+// single warp-wide instructions; the GN-model sum strides the lanes over a link's channel records.
+// A warp keeps its env for all n_steps of a launch, so the env's state is pulled from HBM once per
+// launch and then lives in L1/L2.  No tensor cores: no stage is a dense contraction.
+//
+// HBM layout per env (all per-env blocks are contiguous, 128-byte aligned):
+//   bm     uint32 [E][W]      packed slot bitmaps, 1 = free           (reference: graph["available_slots"],
+//                                                                       int32[E][S], envs/qrmsa.pyx:302-305)
+//   cnt    uint16 [E]         channels on each link
+//   lists  uint32 [E][CAP]    channel records  c2 | n<<12 | mod<<20 | cls<<23   (reference:
+//                             topology[u][v]["running_services"], qrmsa.pyx:1305-1306)
+//                             c2 = 2*initial_slot + n  (centre frequency in half-slots)
+//   trace  uint4  [T]         {arrival f32, holding f32, src|dst<<8|rate<<16, action word}
+//                             request table == service table == decision log
+//   perm   uint16 [T]         request ids sorted by (float32(arrival+holding), id): the release schedule
+//                             (stands in for the heapq of qrmsa.pyx:1327-1330, :1113-1122)
+//   estate int4               {current request, release pointer, accepted, error}
+//
+// GN model (core/osnr.pyx:21-142), factorised: spans of a link are identical and all
+// frequencies sit on the half-slot grid, so with d = |c2_r - c2| (half-slots) the neighbour term is
+//     asinh(Q n_r (d + n_r)) - asinh(Q n_r (d - n_r))  =: G[class(n_r)][d],   Q = pi^2 |beta2| sb^2 / (4 alpha)
+//     phi_r * bw_r / |df|                               =  PHIN[class, mod] * INV[d]
+// and   1/GSNR = ASEC[n] * fc * PA[path] + CN[n] * (SELF[n] * PB[path] + sum_links sum_r (W1_l G - W2_l PHIN INV))
+// Tables G/INV/PHIN/W1/W2/SELF/CN/ASEC are built on the host in FP64 with the same libm the reference
+// uses and staged in shared memory with one TMA bulk copy per CTA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/qrmsa_b200.h"
+
+namespace qrmsa {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_THREADS = 1024;
+
+enum EnvError : int {
+    ENV_OK = 0,
+    ENV_ERR_LIST_OVERFLOW = 1,
+    ENV_ERR_RELEASE_NOT_FOUND = 2,
+    ENV_ERR_LOW_GSNR = 3,  // step_action: the reference raises ValueError (qrmsa.pyx:925-929)
+};
+
+struct KParams {
+    // dimensions
+    int n_envs, N, E, K, M, Mc, R, S, W, Hmax, NC, D, CAP, T, n_req, group_size;
+    // static tables in global memory
+    const uint8_t *path_hops;   // [N*N*K]
+    const uint8_t *path_links;  // [N*N*K*Hmax]
+    const double2 *path_gn;     // [N*N*K] {PA, PB}
+    const unsigned char *blob;  // shared-memory image, 16-byte multiple
+    int blob_bytes;
+    // byte offsets into the blob
+    int oG, oINV, oPHIN, oW1, oW2, oSELF, oCN, oASEC, oTHR, oNEED, oCLS, oRATE;
+    double f0, sb;
+    // per-env state
+    uint32_t *bm;
+    uint16_t *cnt;
+    uint32_t *lists;
+    uint4 *trace;
+    uint16_t *perm;
+    int4 *estate;
+    unsigned long long *counters;  // [n_groups][QRMSA_N_COUNTERS]
+    double *gsnr_log;              // nullable, [n_envs][T]
+    size_t bm_stride;              // uint32 words per env
+    size_t cnt_stride;             // uint16 per env
+};
+
+struct Tab {
+    const double *G, *INV, *PHIN, *W1, *W2, *SELF, *CN, *ASEC, *THR;
+    const uint8_t *need, *cls;
+    const int32_t *rate;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Stage the table blob into shared memory with the TMA (1-D bulk copy, completion on an mbarrier).
+__device__ __forceinline__ void stage_tables(const KParams &p, unsigned char *smem, uint64_t *mbar) {
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.blob_bytes) : "memory");
+        const int CH = 32768;
+        for (int off = 0; off < p.blob_bytes; off += CH) {
+            int sz = p.blob_bytes - off < CH ? p.blob_bytes - off : CH;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(smem + off)),
+                "l"(p.blob + off), "r"(sz), "r"(bar)
+                : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, q;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ Tab make_tab(const KParams &p, const unsigned char *s) {
+    Tab t;
+    t.G = (const double *)(s + p.oG);
+    t.INV = (const double *)(s + p.oINV);
+    t.PHIN = (const double *)(s + p.oPHIN);
+    t.W1 = (const double *)(s + p.oW1);
+    t.W2 = (const double *)(s + p.oW2);
+    t.SELF = (const double *)(s + p.oSELF);
+    t.CN = (const double *)(s + p.oCN);
+    t.ASEC = (const double *)(s + p.oASEC);
+    t.THR = (const double *)(s + p.oTHR);
+    t.need = (const uint8_t *)(s + p.oNEED);
+    t.cls = (const uint8_t *)(s + p.oCLS);
+    t.rate = (const int32_t *)(s + p.oRATE);
+    return t;
+}
+
+// word `lane` of (x >> b), x a multi-word bitmap spread over the lanes (lanes past the data hold 0)
+__device__ __forceinline__ uint32_t shr_multi(uint32_t x, int b, int lane) {
+    const int q = b >> 5;
+    uint32_t lo = __shfl_down_sync(FULL, x, q);
+    uint32_t hi = __shfl_down_sync(FULL, x, q + 1);
+    if (lane + q > 31) lo = 0;
+    if (lane + q + 1 > 31) hi = 0;
+    return __funnelshift_r(lo, hi, b);
+}
+
+// bits [s, e) of the multi-word bitmap that fall in word `lane`
+__device__ __forceinline__ uint32_t range_mask(int s, int e, int lane) {
+    const int lo = max(s - (lane << 5), 0), hi = min(e - (lane << 5), 32);
+    if (hi <= lo) return 0u;
+    const uint32_t upto_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+    return upto_hi & ~((1u << lo) - 1u);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// qrmsa.pyx:1482-1512: AND of the path's link rows; plus one virtual free slot at index S, which turns the
+// guard-band rule of qrmsa.pyx:529-540 ("n slots if the run touches the spectrum end, else n+1") into
+// "n+1 consecutive free slots".
+__device__ __forceinline__ uint32_t path_available(const KParams &p, const uint32_t *bm, int hops, int mylink,
+                                                   int lane) {
+    uint32_t av = 0xffffffffu;
+    for (int i = 0; i < hops; ++i) {
+        const int l = __shfl_sync(FULL, mylink, i);
+        if (lane < p.W) av &= bm[l * p.W + lane];  // mutable state: plain (coherent) load
+    }
+    if (lane >= p.W) av = 0u;
+    if (lane == (p.S >> 5)) av |= 1u << (p.S & 31);
+    return av;
+}
+
+// core/osnr.pyx:21-142 in the factorised form above.  Returns GSNR in dB (same value on every lane).
+__device__ __forceinline__ double gn_gsnr_db(const KParams &p, const Tab &t, const uint32_t *lists, int path, int hops,
+                                             int mylink, int mycnt, int s, int n, int ncls, int lane,
+                                             uint32_t &terms) {
+    const int c2 = 2 * s + n;
+    double x = 0.0;
+    for (int i = 0; i < hops; ++i) {
+        const int l = __shfl_sync(FULL, mylink, i);
+        const int c = __shfl_sync(FULL, mycnt, i);
+        const double w1 = t.W1[l], w2 = t.W2[l];
+        const uint32_t *lst = lists + (size_t)l * p.CAP;
+        terms += c;
+        for (int q = lane; q < c; q += 32) {
+            const uint32_t rec = lst[q];
+            const int d = abs((int)(rec & 0xfffu) - c2);
+            const double g = t.G[(rec >> 23) * p.D + d];
+            const double h = t.PHIN[rec >> 20] * t.INV[d];
+            x += w1 * g - w2 * h;
+        }
+    }
+    x = warp_sum(x);
+    const double2 pg = __ldg(p.path_gn + path);
+    const double fc = p.f0 + (p.sb * (double)s) + (p.sb * ((double)n / 2.0));
+    const double acc = t.ASEC[ncls] * fc * pg.x + t.CN[ncls] * (t.SELF[ncls] * pg.y + x);
+    return -10.0 * log10(acc);
+}
+
+// qrmsa.pyx:1288-1325 (+ the release key of :1327-1330 is implicit in the precomputed schedule)
+__device__ __forceinline__ int commit(const KParams &p, uint32_t *bm, uint16_t *cnt, uint32_t *lists, int hops,
+                                      int mylink, int mycnt, int s, int n, uint32_t rec, int lane) {
+    int e = s + n;
+    if (e < p.S) e += 1;
+    const uint32_t mask = lane < p.W ? range_mask(s, e, lane) : 0u;
+    for (int i = 0; i < hops; ++i) {
+        const int l = __shfl_sync(FULL, mylink, i);
+        if (mask) bm[l * p.W + lane] &= ~mask;
+    }
+    int err = 0;
+    if (lane < hops) {
+        if (mycnt >= p.CAP) {
+            err = 1;
+        } else {
+            lists[(size_t)mylink * p.CAP + mycnt] = rec;
+            cnt[mylink] = (uint16_t)(mycnt + 1);
+        }
+    }
+    return __any_sync(FULL, err);
+}
+
+// qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record
+__device__ __forceinline__ int release_service(const KParams &p, const Tab &t, uint32_t *bm, uint16_t *cnt,
+                                               uint32_t *lists, const uint4 rq, int lane) {
+    const uint32_t a = rq.w & QRMSA_ACTION_MASK;
+    const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+    const int s = a % p.S;
+    const int rel = (a / p.S) % p.Mc;
+    const int pi = a / (p.S * p.Mc);
+    const int m = (p.M - 1) - rel;
+    const int n = t.need[rate * p.M + m];
+    const int path = (src * p.N + dst) * p.K + pi;
+    const int hops = __ldg(p.path_hops + path);
+    const int mylink = lane < hops ? __ldg(p.path_links + (size_t)path * p.Hmax + lane) : 0;
+    const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
+                            ((uint32_t)t.cls[rate * p.M + m] << 23);
+    const int e = min(s + n + 1, p.S);
+    const uint32_t mask = lane < p.W ? range_mask(s, e, lane) : 0u;
+    int err = 0;
+    for (int i = 0; i < hops; ++i) {
+        const int l = __shfl_sync(FULL, mylink, i);
+        if (mask) bm[l * p.W + lane] |= mask;
+        uint32_t *lst = lists + (size_t)l * p.CAP;
+        const int c = cnt[l];
+        int found = -1;
+        for (int q0 = 0; q0 < c; q0 += 32) {
+            const int q = q0 + lane;
+            const uint32_t v = q < c ? lst[q] : 0xffffffffu;
+            const unsigned hit = __ballot_sync(FULL, v == target);
+            if (hit) {
+                found = q0 + __ffs(hit) - 1;
+                break;
+            }
+        }
+        if (found < 0) {
+            err = 1;
+        } else if (lane == 0) {
+            const uint32_t last = lst[c - 1];
+            lst[found] = last;
+            cnt[l] = (uint16_t)(c - 1);
+        }
+        __syncwarp();
+    }
+    return err;
+}
+
+struct Head {
+    int id;     // request id at the head of the release schedule, -1 = exhausted
+    float rel;  // its release time, float32(arrival + holding)  (qrmsa.pyx:1329)
+};
+
+__device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, const uint16_t *perm, int ptr) {
+    Head h;
+    h.id = -1;
+    h.rel = 0.f;
+    if (ptr < p.n_req) {
+        h.id = perm[ptr];
+        const uint4 r = tr[h.id];
+        h.rel = __fadd_rn(__uint_as_float(r.x), __uint_as_float(r.y));
+    }
+    return h;
+}
+
+// qrmsa.pyx:1067-1122 after a request has been decided: take the next request (clock := its arrival) and
+// release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
+// schedule exactly as they are absent from the reference heap.
+__device__ __forceinline__ int advance_and_release(const KParams &p, const Tab &t, uint4 *tr, const uint16_t *perm,
+                                                   uint32_t *bm, uint16_t *cnt, uint32_t *lists, int &cur,
+                                                   int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
+    cur += 1;
+    const float now = __uint_as_float(tr[cur].x);
+    int err = 0;
+    while (head.id >= 0 && head.id < cur && head.rel <= now) {
+        const uint4 rq = tr[head.id];
+        if (rq.w & QRMSA_FLAG_ACCEPTED) {
+            err |= release_service(p, t, bm, cnt, lists, rq, lane);
+            n_rel += 1;
+        }
+        rel_ptr += 1;
+        head = load_head(p, tr, perm, rel_ptr);
+    }
+    return err;
+}
+
+#define QCNT(slot, v) cnt_reg += (lane == (slot)) ? (uint32_t)(v) : 0u
+
+// --------------------------------------------------------------------------------------------------------
+// Fused first-fit heuristic + step, n_steps requests per env per launch.
+// heuristics.py:923-966 + qrmsa.pyx:838-1065.
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams p, const int n_steps) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    stage_tables(p, smem, &mbar);
+    const Tab t = make_tab(p, smem);
+
+    const int lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpc + (threadIdx.x >> 5);
+    const int gstride = gridDim.x * wpc;
+    const int reject = p.K * p.Mc * p.S;
+
+    for (int env = gw; env < p.n_envs; env += gstride) {
+        int4 st = p.estate[env];
+        if (st.w != ENV_OK) continue;
+        int cur = st.x, rel_ptr = st.y, accepted = st.z, err = 0;
+        uint4 *tr = p.trace + (size_t)env * p.T;
+        const uint16_t *perm = p.perm + (size_t)env * p.T;
+        uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
+        uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
+        uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
+        double *glog = p.gsnr_log ? p.gsnr_log + (size_t)env * p.T : nullptr;
+        Head head = load_head(p, tr, perm, rel_ptr);
+        uint32_t cnt_reg = 0;
+
+        for (int step = 0; step < n_steps && cur + 1 < p.n_req && !err; ++step) {
+            const uint4 rq = tr[cur];
+            const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+            const int pbase = (src * p.N + dst) * p.K;
+            uint32_t flags = QRMSA_FLAG_DECIDED;
+            int action = reject;
+            double g_acc = 0.0;
+            int blk_res = 0, blk_osnr = 0;
+            bool found = false;
+
+            for (int pi = 0; pi < p.K && !found; ++pi) {
+                const int path = pbase + pi;
+                const int hops = __ldg(p.path_hops + path);
+                if (hops == 0) continue;
+                const int mylink = lane < hops ? __ldg(p.path_links + (size_t)path * p.Hmax + lane) : 0;
+                const int mycnt = lane < hops ? cnt[mylink] : 0;
+                const uint32_t av = path_available(p, bm, hops, mylink, lane);
+                QCNT(QRMSA_CNT_LINKS_READ, hops);
+                QCNT(QRMSA_CNT_PATHS_TRIED, 1);
+                uint32_t r = av;
+                int a = 1;
+                bool counted = false;
+                for (int m = p.M - 1; m >= 0; --m) {
+                    const int n = t.need[rate * p.M + m];
+                    const int L = n + 1;
+                    if (L < a) { r = av; a = 1; }
+                    while (a < L) {
+                        const int b = min(a, L - a);
+                        r &= shr_multi(r, b, lane);
+                        a += b;
+                    }
+                    const unsigned any = __ballot_sync(FULL, r != 0u);
+                    if (!any) { blk_res = 1; continue; }
+                    const int fl = __ffs(any) - 1;
+                    const uint32_t w = __shfl_sync(FULL, r, fl);
+                    const int s = (fl << 5) + __ffs(w) - 1;
+                    const int ncls = t.cls[rate * p.M + m];
+                    uint32_t terms = 0;
+                    const double g = gn_gsnr_db(p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
+                    QCNT(QRMSA_CNT_GN_EVALS, 1);
+                    QCNT(QRMSA_CNT_GN_TERMS, terms);
+                    if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
+                    const double thr = t.THR[m];
+                    if (fabs(g - thr) < 1e-3) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+                    if (g >= thr) {
+                        found = true;
+                        action = pi * p.Mc * p.S + ((p.M - 1) - m) * p.S + s;
+                        g_acc = g;
+                        const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
+                                             ((uint32_t)ncls << 23);
+                        if (commit(p, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                        flags |= QRMSA_FLAG_ACCEPTED;
+                        accepted += 1;
+                        QCNT(QRMSA_CNT_ACCEPTED, 1);
+                        QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate[rate]);
+                        QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
+                        QCNT(QRMSA_CNT_MOD_HIST + m, 1);
+                        break;
+                    }
+                    blk_osnr = 1;
+                    blk_res = 0;
+                }
+            }
+            if (!found) {
+                QCNT(QRMSA_CNT_REJECTED, 1);
+                QCNT(QRMSA_CNT_BLOCKED_RESOURCES, blk_res);
+                QCNT(QRMSA_CNT_BLOCKED_OSNR, blk_osnr);
+            }
+            QCNT(QRMSA_CNT_DECIDED, 1);
+            QCNT(QRMSA_CNT_RATE_REQUESTED, t.rate[rate]);
+            if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
+            if (lane == 0) {
+                tr[cur].w = (uint32_t)action | flags;
+                if (glog) glog[cur] = g_acc;
+            }
+            __syncwarp();
+            uint32_t n_rel = 0;
+            if (advance_and_release(p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+                err = ENV_ERR_RELEASE_NOT_FOUND;
+            QCNT(QRMSA_CNT_RELEASES, n_rel);
+        }
+        if (err) QCNT(QRMSA_CNT_ERRORS, 1);
+        if (lane == 0) p.estate[env] = make_int4(cur, rel_ptr, accepted, err);
+        if (cnt_reg) atomicAdd(p.counters + (size_t)(env / p.group_size) * QRMSA_N_COUNTERS + lane,
+                               (unsigned long long)cnt_reg);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// env.step(action) with an external action per env (qrmsa.pyx:838-1065), one request per launch.
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+    k_step_action(const KParams p, const long long *__restrict__ ext_action, float *__restrict__ o_reward,
+                  uint8_t *__restrict__ o_status, double *__restrict__ o_gsnr, uint8_t *__restrict__ o_term,
+                  const int episode_length) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    stage_tables(p, smem, &mbar);
+    const Tab t = make_tab(p, smem);
+
+    const int lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpc + (threadIdx.x >> 5);
+    const int gstride = gridDim.x * wpc;
+    const int reject = p.K * p.Mc * p.S;
+
+    for (int env = gw; env < p.n_envs; env += gstride) {
+        int4 st = p.estate[env];
+        int cur = st.x, rel_ptr = st.y, accepted = st.z, err = st.w;
+        int status = QRMSA_STEP_IDLE;
+        float reward = 0.f;
+        double g = 0.0;
+        int term = 0;
+        uint32_t cnt_reg = 0;
+        if (err == ENV_OK && cur + 1 < p.n_req) {
+            uint4 *tr = p.trace + (size_t)env * p.T;
+            const uint16_t *perm = p.perm + (size_t)env * p.T;
+            uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
+            uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
+            uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
+            const uint4 rq = tr[cur];
+            const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+            const long long a64 = ext_action[env];
+            uint32_t flags = QRMSA_FLAG_DECIDED;
+            bool consume = true;
+            if (a64 == reject || a64 < 0 || a64 > reject) {
+                status = QRMSA_STEP_REJECT_ACTION;
+                reward = -6.0f;  // qrmsa.pyx:992-995
+            } else {
+                const int a = (int)a64;
+                const int s = a % p.S;
+                const int rel = (a / p.S) % p.Mc;
+                const int pi = (a / (p.S * p.Mc)) % p.K;
+                const int m = (p.M - 1 > 1) ? (p.M - 1) - rel : (p.Mc - 1) - rel;  // qrmsa.pyx:821-829
+                const int n = t.need[rate * p.M + m];
+                const int path = (src * p.N + dst) * p.K + pi;
+                const int hops = __ldg(p.path_hops + path);
+                const int mylink = lane < hops ? __ldg(p.path_links + (size_t)path * p.Hmax + lane) : 0;
+                const int mycnt = lane < hops ? cnt[mylink] : 0;
+                // is_path_free (qrmsa.pyx:1248-1264): [s, s+n (+1 guard if it ends before S)) free on every link
+                bool free_ok = hops > 0 && s + n <= p.S;
+                if (free_ok) {
+                    const uint32_t av = path_available(p, bm, hops, mylink, lane);
+                    const int e = (s + n < p.S) ? s + n + 1 : s + n;
+                    const uint32_t mask = lane < p.W ? range_mask(s, e, lane) : 0u;
+                    free_ok = !__any_sync(FULL, (av & mask) != mask);
+                }
+                if (!free_ok) {
+                    status = QRMSA_STEP_NOT_FREE;
+                    consume = false;
+                    // reward(): not accepted -> -3 * (1 + failed_ratio)  (qrmsa.pyx:1266-1271)
+                    const double proc = (double)(cur + 1);
+                    reward = (float)(-3.0 * (1.0 + (proc - (double)accepted) / proc));
+                } else {
+                    const int ncls = t.cls[rate * p.M + m];
+                    uint32_t terms = 0;
+                    g = gn_gsnr_db(p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
+                    const double thr = t.THR[m];
+                    if (fabs(g - thr) < 1e-3) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+                    if (g >= thr) {
+                        const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
+                                             ((uint32_t)ncls << 23);
+                        if (commit(p, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                        flags |= QRMSA_FLAG_ACCEPTED;
+                        accepted += 1;
+                        status = QRMSA_STEP_ACCEPTED;
+                        reward = 0.f;  // reward() falls off its end for accepted services (qrmsa.pyx:1266-1285)
+                        QCNT(QRMSA_CNT_ACCEPTED, 1);
+                        QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate[rate]);
+                        QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
+                        QCNT(QRMSA_CNT_MOD_HIST + m, 1);
+                    } else {
+                        status = QRMSA_STEP_LOW_GSNR;  // the reference raises here; the env is left untouched
+                        consume = false;
+                    }
+                }
+            }
+            if (consume) {
+                if (status == QRMSA_STEP_REJECT_ACTION) QCNT(QRMSA_CNT_REJECTED, 1);
+                QCNT(QRMSA_CNT_DECIDED, 1);
+                QCNT(QRMSA_CNT_RATE_REQUESTED, t.rate[rate]);
+                if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
+                if (lane == 0) {
+                    tr[cur].w = (uint32_t)(status == QRMSA_STEP_ACCEPTED ? (int)a64 : reject) | flags;
+                    if (p.gsnr_log) p.gsnr_log[(size_t)env * p.T + cur] = g;
+                }
+                __syncwarp();
+                Head head = load_head(p, tr, perm, rel_ptr);
+                uint32_t n_rel = 0;
+                if (advance_and_release(p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+                    err = ENV_ERR_RELEASE_NOT_FOUND;
+                QCNT(QRMSA_CNT_RELEASES, n_rel);
+                term = (cur + 1 == episode_length);  // episode_services_processed == episode_length (qrmsa.pyx:1056)
+            }
+            if (err) QCNT(QRMSA_CNT_ERRORS, 1);
+            if (lane == 0) p.estate[env] = make_int4(cur, rel_ptr, accepted, err);
+            if (cnt_reg) atomicAdd(p.counters + (size_t)(env / p.group_size) * QRMSA_N_COUNTERS + lane,
+                                   (unsigned long long)cnt_reg);
+        }
+        if (lane == 0) {
+            if (o_reward) o_reward[env] = reward;
+            if (o_status) o_status[env] = (uint8_t)status;
+            if (o_gsnr) o_gsnr[env] = g;
+            if (o_term) o_term[env] = (uint8_t)term;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// reset (qrmsa.pyx:427-504): every slot free, lists empty, release pointer / request index / episode counters 0
+// --------------------------------------------------------------------------------------------------------
+__global__ void k_reset(const KParams p) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t words = (size_t)p.n_envs * p.bm_stride;
+    const int rowwords = p.E * p.W;
+    for (size_t i = tid; i < words; i += nthreads) {
+        const int k = (int)(i % p.bm_stride);
+        uint32_t v = 0u;
+        if (k < rowwords) {
+            const int j = k % p.W;
+            const int left = p.S - (j << 5);
+            v = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+        }
+        p.bm[i] = v;
+    }
+    const size_t ncnt = (size_t)p.n_envs * p.cnt_stride;
+    for (size_t i = tid; i < ncnt; i += nthreads) p.cnt[i] = 0;
+    for (size_t i = tid; i < (size_t)p.n_envs; i += nthreads) p.estate[i] = make_int4(0, 0, 0, 0);
+}
+
+// Request-major SoA [n_req][n_envs] -> per-env AoS records, through a shared-memory tile so that both the
+// reads (consecutive envs) and the writes (consecutive requests of one env) are coalesced.
+__global__ void k_ingest_trace(const KParams p, const uint8_t *__restrict__ src, const uint8_t *__restrict__ dst,
+                               const uint8_t *__restrict__ rate, const float *__restrict__ arrival,
+                               const float *__restrict__ holding, const int n_req) {
+    __shared__ uint4 tile[32][33];
+    const int e0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int r = r0 + rr, e = e0 + tx;
+        if (r < n_req && e < p.n_envs) {
+            const size_t o = (size_t)r * p.n_envs + e;
+            uint4 v;
+            v.x = __float_as_uint(arrival[o]);
+            v.y = __float_as_uint(holding[o]);
+            v.z = (uint32_t)src[o] | ((uint32_t)dst[o] << 8) | ((uint32_t)rate[o] << 16);
+            v.w = 0u;
+            tile[rr][tx] = v;
+        }
+    }
+    __syncthreads();
+    for (int ee = ty; ee < 32; ee += 8) {
+        const int e = e0 + ee, r = r0 + tx;
+        if (r < n_req && e < p.n_envs) p.trace[(size_t)e * p.T + r] = tile[tx][ee];
+    }
+}
+
+// Release schedule: per env, request ids sorted by (float32(arrival + holding), id) -- the key of the
+// reference's heap (qrmsa.pyx:1327-1330).  One CTA per env, bitonic sort of 64-bit keys in shared memory.
+__global__ void __launch_bounds__(1024) k_build_schedule(const KParams p, const int n_req, const int n_pad) {
+    extern __shared__ __align__(16) unsigned long long keys[];
+    for (int env = blockIdx.x; env < p.n_envs; env += gridDim.x) {
+        const uint4 *tr = p.trace + (size_t)env * p.T;
+        for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+            unsigned long long k = ~0ull;
+            if (i < n_req) {
+                const uint4 r = tr[i];
+                const float rel = __fadd_rn(__uint_as_float(r.x), __uint_as_float(r.y));
+                k = ((unsigned long long)__float_as_uint(rel) << 32) | (unsigned)i;  // times are >= 0
+            }
+            keys[i] = k;
+        }
+        __syncthreads();
+        for (int k = 2; k <= n_pad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = keys[i], b = keys[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        uint16_t *perm = p.perm + (size_t)env * p.T;
+        for (int i = threadIdx.x; i < n_req; i += blockDim.x) perm[i] = (uint16_t)(keys[i] & 0xffffu);
+        __syncthreads();
+    }
+}
+
+// action words of requests [first, first+count) -> request-major int32 [count][n_envs]
+__global__ void k_gather_actions(const KParams p, const int first, const int count, int32_t *__restrict__ out) {
+    __shared__ uint32_t tile[32][33];
+    const int e0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int ee = ty; ee < 32; ee += 8) {
+        const int e = e0 + ee, r = r0 + tx;
+        if (r < count && e < p.n_envs) tile[ee][tx] = p.trace[(size_t)e * p.T + first + r].w;
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int r = r0 + rr, e = e0 + tx;
+        if (r < count && e < p.n_envs) out[(size_t)r * p.n_envs + e] = (int32_t)tile[tx][rr];
+    }
+}
+
+__global__ void k_gather_gsnr(const KParams p, const int first, const int count, double *__restrict__ out) {
+    const size_t n = (size_t)count * p.n_envs;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / p.n_envs), e = (int)(i % p.n_envs);
+        out[i] = p.gsnr_log[(size_t)e * p.T + first + r];
+    }
+}
+
+// calculate_osnr for a hypothetical channel on one env (core/osnr.pyx:21-142); one warp.
+__global__ void k_probe_gsnr(const KParams p, const int env, const int src, const int dst, const int pi, const int s,
+                             const int n, double *out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    stage_tables(p, smem, &mbar);
+    const Tab t = make_tab(p, smem);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x >= 32) return;
+    const int path = (src * p.N + dst) * p.K + pi;
+    const int hops = __ldg(p.path_hops + path);
+    const uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
+    const uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
+    const int mylink = lane < hops ? __ldg(p.path_links + (size_t)path * p.Hmax + lane) : 0;
+    const int mycnt = lane < hops ? cnt[mylink] : 0;
+    // class of n: search the class table through NEED/CLS
+    int ncls = -1;
+    for (int i = 0; i < p.R * p.M; ++i)
+        if (t.need[i] == n) ncls = t.cls[i];
+    double g = nan("");
+    if (ncls >= 0 && hops > 0) {
+        uint32_t terms = 0;
+        g = gn_gsnr_db(p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
+    }
+    if (lane == 0) *out = g;
+}
+
+}  // namespace qrmsa

@@ -1,0 +1,120 @@
+"""CUDA path vs the compiled reference's recorded outputs (tests/golden) and vs the oracle.
+
+Everything goes through the C ABI (optical_networking_gym_b200.engine.Engine -> libqrmsa_b200.so).
+Bar: bit-exact path / modulation / initial-slot / accept decisions and slot bitmaps; GSNR within
+1e-3 dB; decisions with a GSNR within 1e-3 dB of a threshold are flagged, not counted.
+"""
+import numpy as np
+import pytest
+
+from helpers import TRACE_KEYS, compare_decisions, load_golden, load_tables, parse_tag
+
+pytestmark = pytest.mark.gpu
+
+GSNR_TOL_DB = 1e-3
+
+SINGLE = ["run_nobel-eu_320_l300_s50", "run_nsfnet_320_l300_s50", "run_germany50_640_l800_s52",
+          "run_nobel-eu_320_l500_s7", "run_ring4_320_l60_s3"]
+MULTI = ["multi_nobel-eu_320_l300_b50", "multi_germany50_640_l800_b50"]
+
+
+def _engine(tb, n_envs, n_req):
+    from optical_networking_gym_b200.engine import Engine
+
+    eng = Engine(tb, n_envs, n_req)
+    eng.enable_gsnr_log(True)
+    return eng
+
+
+def _run(eng, g, multi, chunks):
+    from optical_networking_gym_b200 import _lib
+
+    tr = [np.ascontiguousarray(g[k].T if multi else g[k][:, None]) for k in TRACE_KEYS]
+    n_req = tr[0].shape[0]
+    eng.reset()
+    eng.load_trace_host(*tr)
+    done = 0
+    for c in chunks:
+        eng.step_first_fit(c)
+        done += c
+    assert done == n_req - 1
+    words = eng.actions_host(0, n_req - 1)
+    actions = (words & _lib.ACTION_MASK).astype(np.int64).T        # [env][step]
+    flagged = ((words.view(np.uint32) & _lib.FLAG_NEAR_THRESHOLD) != 0).T
+    accepted = ((words.view(np.uint32) & _lib.FLAG_ACCEPTED) != 0).T
+    gsnr = eng.gsnr_host(0, n_req - 1).T
+    return actions, flagged, accepted, gsnr
+
+
+@pytest.mark.parametrize("tag", SINGLE)
+def test_single_env_vs_reference(tag):
+    from optical_networking_gym_b200.engine import unpack_bitmaps
+
+    topo, S = parse_tag(tag)
+    tb = load_tables(topo, S)
+    g = load_golden(tag)
+    n_steps = len(g["action"])
+    eng = _engine(tb, 1, n_steps + 1)
+    # uneven chunking exercises state hand-over between launches
+    chunks = [1, 2, 37] + [n_steps - 40]
+    actions, flagged, accepted, gsnr = _run(eng, g, False, chunks)
+    n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
+    if n_exc == 0:
+        assert np.array_equal(accepted[0], g["accepted"].astype(bool))
+        assert np.abs(gsnr[0] - g["gsnr"]).max() < GSNR_TOL_DB
+        slots = unpack_bitmaps(eng.export_bitmaps(0, 1), S)[0]
+        assert np.array_equal(slots, g["final_slots"])
+        st = eng.env_state()[0]
+        assert st[0] == n_steps and st[1] == int(g["accepted"].sum()) and st[3] == 0
+        c = eng.counters_dict()
+        assert c["decided"] == n_steps and c["accepted"] == int(g["accepted"].sum())
+        assert c["gn_evals"] == len(g["qot_gsnr"])
+        assert c["errors"] == 0
+    # every near-threshold QoT check of the reference must have raised our flag on that step
+    near = np.abs(g["qot_gsnr"] - g["qot_thr"]) < GSNR_TOL_DB * 0.5
+    for s in np.unique(g["qot_step"][near]):
+        if s < n_cmp:
+            assert flagged[0, s]
+    eng.close()
+
+
+@pytest.mark.parametrize("tag", MULTI)
+def test_batched_envs_vs_reference(tag):
+    from optical_networking_gym_b200.engine import unpack_bitmaps
+
+    topo, S = parse_tag(tag)
+    tb = load_tables(topo, S)
+    g = load_golden(tag)
+    n_envs, n_steps = g["action"].shape
+    eng = _engine(tb, n_envs, n_steps + 1)
+    actions, flagged, accepted, gsnr = _run(eng, g, True, [n_steps])
+    n_cmp, n_exc = compare_decisions(actions, g["action"], flagged, tag)
+    assert n_exc <= max(1, n_envs // 8)
+    clean = [e for e in range(n_envs) if np.array_equal(actions[e], g["action"][e])]
+    assert len(clean) >= n_envs - n_exc
+    slots = unpack_bitmaps(eng.export_bitmaps(0, n_envs), S)
+    ref_slots = np.unpackbits(g["final_slots"], axis=2)[:, :, :S]
+    for e in clean:
+        assert np.array_equal(slots[e], ref_slots[e]), f"env {e}: slot bitmap differs"
+        assert np.abs(gsnr[e] - g["gsnr"][e]).max() < GSNR_TOL_DB
+    eng.close()
+
+
+def test_snapshots_mid_episode():
+    """Slot matrices after 500, 1000, ... steps equal the reference's snapshots."""
+    from optical_networking_gym_b200.engine import unpack_bitmaps
+
+    tag = "run_nobel-eu_320_l300_s50"
+    topo, S = parse_tag(tag)
+    tb, g = load_tables(topo, S), load_golden(tag)
+    n_steps = len(g["action"])
+    eng = _engine(tb, 1, n_steps + 1)
+    tr = [np.ascontiguousarray(g[k][:, None]) for k in TRACE_KEYS]
+    eng.reset(); eng.load_trace_host(*tr)
+    done = 0
+    for step, snap in zip(g["snap_steps"], g["snap_slots"]):
+        eng.step_first_fit(int(step) - done)
+        done = int(step)
+        slots = unpack_bitmaps(eng.export_bitmaps(0, 1), S)[0]
+        assert np.array_equal(slots, np.unpackbits(snap, axis=1)[:, :S]), f"snapshot at step {step}"
+    eng.close()
