@@ -139,31 +139,35 @@ extern "C" int qrmsa_tracegen_next(qrmsa_tracegen *g, int n_requests, uint8_t *h
     if (n_threads > g->n_envs) n_threads = g->n_envs;
     const int n_envs = g->n_envs, N = g->n_nodes, R = g->n_rates;
     const double lam_hold = 1.0 / g->mean_holding;  // qrmsa.pyx:1083
+    // env-blocked so that the request-major output arrays are written in runs of consecutive envs
     auto work = [&](int e0, int e1) {
-        for (int e = e0; e < e1; e++) {
-            MT19937 &rng = g->rng[e];
-            double now = g->now[e];
-            const double lam = g->lam_iat[e];
+        const int BLK = 16;
+        for (int b0 = e0; b0 < e1; b0 += BLK) {
+            const int b1 = b0 + BLK < e1 ? b0 + BLK : e1;
             for (int r = 0; r < n_requests; r++) {
-                size_t o = (size_t)r * n_envs + e;
-                float at = (float)(now + (-std::log(1.0 - rng.random()) / lam));
-                now = (double)at;
-                float ht = (float)(-std::log(1.0 - rng.random()) / lam_hold);
-                int s = bisect_right(g->src_cum.data(), rng.random() * (g->src_cum[N - 1] + 0.0), 0, N - 1);
-                const double *dc = g->dst_cum.data() + (size_t)s * N;
-                int d = bisect_right(dc, rng.random() * (dc[N - 1] + 0.0), 0, N - 1);
-                int br = bisect_right(g->rate_cum.data(), rng.random() * (g->rate_cum[R - 1] + 0.0), 0, R - 1);
-                h_arrival[o] = at; h_holding[o] = ht;
-                h_src[o] = (uint8_t)s; h_dst[o] = (uint8_t)d; h_rate[o] = (uint8_t)br;
+                const size_t row = (size_t)r * n_envs;
+                for (int e = b0; e < b1; e++) {
+                    MT19937 &rng = g->rng[e];
+                    const double lam = g->lam_iat[e];
+                    float at = (float)(g->now[e] + (-std::log(1.0 - rng.random()) / lam));
+                    g->now[e] = (double)at;
+                    float ht = (float)(-std::log(1.0 - rng.random()) / lam_hold);
+                    int s = bisect_right(g->src_cum.data(), rng.random() * (g->src_cum[N - 1] + 0.0), 0, N - 1);
+                    const double *dc = g->dst_cum.data() + (size_t)s * N;
+                    int d = bisect_right(dc, rng.random() * (dc[N - 1] + 0.0), 0, N - 1);
+                    int br = bisect_right(g->rate_cum.data(), rng.random() * (g->rate_cum[R - 1] + 0.0), 0, R - 1);
+                    const size_t o = row + e;
+                    h_arrival[o] = at; h_holding[o] = ht;
+                    h_src[o] = (uint8_t)s; h_dst[o] = (uint8_t)d; h_rate[o] = (uint8_t)br;
+                }
             }
-            g->now[e] = now;
         }
     };
     if (n_threads == 1) {
         work(0, n_envs);
     } else {
         std::vector<std::thread> th;
-        int per = (n_envs + n_threads - 1) / n_threads;
+        int per = ((n_envs + n_threads - 1) / n_threads + 15) / 16 * 16;
         for (int t = 0; t < n_threads; t++) {
             int e0 = t * per, e1 = e0 + per > n_envs ? n_envs : e0 + per;
             if (e0 < e1) th.emplace_back(work, e0, e1);

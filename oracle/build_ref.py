@@ -11,7 +11,8 @@ Its own `setup.py build_ext --inplace` writes into the source tree, and
      (`-march=native` of setup.py:29 is dropped on purpose: the built .so has to
      run on the GPU box, whose host CPU is not this container's),
   3. install the result (compiled .so + the package's pure-Python modules, no
-     .pyx/.c) into oracle/_ref/optical_networking_gym/.
+     .pyx/.c) into oracle/_ref/optical_networking_gym/, and the topology input
+     files (examples/topologies: data) into oracle/_ref/topologies/.
 
 oracle/_ref/ is git-ignored (never committed) but NOT gpurun-ignored, so the
 compiled reference travels to the GPU box, where /root/reference does not exist.
@@ -62,7 +63,8 @@ setup(
 
 
 def ref_available() -> bool:
-    return bool(glob.glob(os.path.join(OUT, "optical_networking_gym", "envs", "qrmsa*.so")))
+    return bool(glob.glob(os.path.join(OUT, "optical_networking_gym", "envs", "qrmsa*.so"))) and os.path.isdir(
+        os.path.join(OUT, "topologies"))
 
 
 def build(force: bool = False) -> bool:
@@ -88,8 +90,12 @@ def build(force: bool = False) -> bool:
             os.path.join(tmp, "optical_networking_gym"), dst,
             ignore=shutil.ignore_patterns("*.pyx", "*.c", "*.pxd", "__pycache__", "*.html"),
         )
-        # topology inputs the oracle harness needs at golden-generation time stay where they are
-        # (/root/reference/examples/topologies); only derived tables are committed (tests/golden).
+        # topology input files (data, not source) so that the compiled reference can be timed on the GPU
+        # box, where /root/reference does not exist; git-ignored like the rest of oracle/_ref
+        tdst = os.path.join(OUT, "topologies")
+        if os.path.isdir(tdst):
+            shutil.rmtree(tdst)
+        shutil.copytree(os.path.join(REF, "examples", "topologies"), tdst)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return ref_available()

@@ -29,7 +29,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 STUB_DIR = os.path.join(HERE, "gymnasium_stub")
-TOPO_DIR = os.environ.get("QRMSA_TOPOLOGY_DIR", "/root/reference/examples/topologies")
+TOPO_DIR = os.environ.get("QRMSA_TOPOLOGY_DIR") or (
+    os.path.join(REF_DIR, "topologies") if os.path.isdir(os.path.join(REF_DIR, "topologies"))
+    else "/root/reference/examples/topologies")
 
 TOPOLOGY_FILES = {
     "nsfnet": "nsfnet_chen.txt",
