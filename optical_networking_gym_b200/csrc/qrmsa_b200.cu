@@ -159,6 +159,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     for (size_t i = 0; i < ctx->need.size(); i++)
         for (int c = 0; c < NC; c++)
             if (cls_n[c] == ctx->need[i]) ctx->cls[i] = (uint8_t)c;
+    if (ctx->max_need + 1 > 97) { ctx->err = "a service (slots + guard) may span at most 4 bitmap words (number_slots <= 96)"; return QRMSA_ERR_UNSUPPORTED; }
     if ((S >> 5) + ((ctx->max_need + 1) >> 5) + 2 > 32) { ctx->err = "bitmap + shift distance exceed one warp"; return QRMSA_ERR_UNSUPPORTED; }
 
     // ---- GN tables (core/osnr.pyx:21-142), FP64, host libm
@@ -166,7 +167,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     const double alpha = t->link_alpha[0], sb = t->slot_bandwidth_hz, P = t->launch_power_w;
     const double l_eff_a = 1.0 / (2.0 * alpha);
     const int D = kp.D;
-    std::vector<double> G((size_t)NC * D), INV(D), PHIN(256, 0.0), W1(E), W2(E), SELF(NC), CN(NC), ASEC(NC), THR(M);
+    std::vector<double> G((size_t)NC * D), INV(D), PHIN(256, 0.0), W1(E), W2(E), SELF(NC), CN(NC), ASEC(NC), ACCT(M), ACCLO(M), ACCHI(M);
     for (int c = 0; c < NC; c++) {
         const double bw_r = sb * cls_n[c];
         for (int d = 0; d < D; d++) {
@@ -188,9 +189,16 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         leff[l] = (1.0 - exp(-2.0 * alpha * len)) / (2.0 * alpha);
         ex[l] = (exp(2.0 * alpha * len) - 1.0) * t->link_nf[l];
         W1[l] = t->link_n_spans[l] * leff[l];
-        W2[l] = t->link_n_spans[l] * leff[l] * (5.0 / 3.0) * (leff[l] / len);
+        W2[l] = -(t->link_n_spans[l] * leff[l] * (5.0 / 3.0) * (leff[l] / len));  // stored negated
     }
-    for (int m = 0; m < M; m++) THR[m] = t->mod_min_osnr[m] + t->margin_db;
+    for (int m = 0; m < M; m++) {
+        // accept iff gsnr_dB >= thr (heuristics.py:957-958)  <=>  acc = 1/GSNR <= 10^(-thr/10);
+        // near-threshold flag: |gsnr_dB - thr| < 1e-3 dB
+        const double thr = t->mod_min_osnr[m] + t->margin_db;
+        ACCT[m] = pow(10.0, -thr / 10.0);
+        ACCLO[m] = pow(10.0, -(thr + 1e-3) / 10.0);
+        ACCHI[m] = pow(10.0, -(thr - 1e-3) / 10.0);
+    }
     const size_t n_paths = (size_t)N * N * K;
     std::vector<double2> pgn(n_paths);
     for (size_t pi_ = 0; pi_ < n_paths; pi_++) {
@@ -217,7 +225,9 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     kp.oSELF = blob.add(SELF.data(), SELF.size() * 8);
     kp.oCN = blob.add(CN.data(), CN.size() * 8);
     kp.oASEC = blob.add(ASEC.data(), ASEC.size() * 8);
-    kp.oTHR = blob.add(THR.data(), THR.size() * 8);
+    kp.oACCT = blob.add(ACCT.data(), ACCT.size() * 8);
+    kp.oACCLO = blob.add(ACCLO.data(), ACCLO.size() * 8);
+    kp.oACCHI = blob.add(ACCHI.data(), ACCHI.size() * 8);
     kp.oNEED = blob.add(ctx->need.data(), ctx->need.size());
     kp.oCLS = blob.add(ctx->cls.data(), ctx->cls.size());
     kp.oRATE = blob.add(rate_milli.data(), rate_milli.size() * 4);
@@ -239,7 +249,9 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     const int wpc = ctx->threads / 32;
     const int want = (n_envs + wpc - 1) / wpc;
     ctx->grid = want < ctx->sm_count * ctas_per_sm ? want : ctx->sm_count * ctas_per_sm;
-    CK(cudaFuncSetAttribute(k_step_first_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_first_fit<320, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_first_fit<640, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_first_fit<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_action, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_probe_gsnr, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_build_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
@@ -364,7 +376,15 @@ extern "C" int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream) {
     if (ctx->kp.n_req < 2) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
     if (n_steps == 0) return QRMSA_OK;
     CK(cudaSetDevice(ctx->device));
-    k_step_first_fit<<<ctx->grid, ctx->threads, ctx->kp.blob_bytes, (cudaStream_t)stream>>>(ctx->kp, n_steps);
+    const KParams &kp = ctx->kp;
+    cudaStream_t st = (cudaStream_t)stream;
+    // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
+    if (kp.S == 320 && kp.M == 6 && kp.K == 5)
+        k_step_first_fit<320, 6, 5><<<ctx->grid, ctx->threads, kp.blob_bytes, st>>>(kp, n_steps);
+    else if (kp.S == 640 && kp.M == 6 && kp.K == 5)
+        k_step_first_fit<640, 6, 5><<<ctx->grid, ctx->threads, kp.blob_bytes, st>>>(kp, n_steps);
+    else
+        k_step_first_fit<0, 0, 0><<<ctx->grid, ctx->threads, kp.blob_bytes, st>>>(kp, n_steps);
     CK(cudaGetLastError());
     return QRMSA_OK;
 }

@@ -23,7 +23,9 @@
 // frequencies sit on the half-slot grid, so with d = |c2_r - c2| (half-slots) the neighbour term is
 //     asinh(Q n_r (d + n_r)) - asinh(Q n_r (d - n_r))  =: G[class(n_r)][d],   Q = pi^2 |beta2| sb^2 / (4 alpha)
 //     phi_r * bw_r / |df|                               =  PHIN[class, mod] * INV[d]
-// and   1/GSNR = ASEC[n] * fc * PA[path] + CN[n] * (SELF[n] * PB[path] + sum_links sum_r (W1_l G - W2_l PHIN INV))
+// and   1/GSNR = ASEC[n] * fc * PA[path] + CN[n] * (SELF[n] * PB[path] + sum_links (W1_l sum_r G - W2_l sum_r PHIN INV))
+// The accept test gsnr_dB >= threshold is made on the linear value (acc <= 10^(-thr/10)); log10 is only
+// evaluated for the optional GSNR log.
 // Tables G/INV/PHIN/W1/W2/SELF/CN/ASEC are built on the host in FP64 with the same libm the reference
 // uses and staged in shared memory with one TMA bulk copy per CTA.
 #pragma once
@@ -54,7 +56,7 @@ struct KParams {
     const unsigned char *blob;  // shared-memory image, 16-byte multiple
     int blob_bytes;
     // byte offsets into the blob
-    int oG, oINV, oPHIN, oW1, oW2, oSELF, oCN, oASEC, oTHR, oNEED, oCLS, oRATE;
+    int oG, oINV, oPHIN, oW1, oW2, oSELF, oCN, oASEC, oACCT, oACCLO, oACCHI, oNEED, oCLS, oRATE;
     double f0, sb;
     // per-env state
     uint32_t *bm;
@@ -70,7 +72,7 @@ struct KParams {
 };
 
 struct Tab {
-    const double *G, *INV, *PHIN, *W1, *W2, *SELF, *CN, *ASEC, *THR;
+    const double *G, *INV, *PHIN, *W1, *W2, *SELF, *CN, *ASEC, *ACCT, *ACCLO, *ACCHI;
     const uint8_t *need, *cls;
     const int32_t *rate;
 };
@@ -119,26 +121,42 @@ __device__ __forceinline__ Tab make_tab(const KParams &p, const unsigned char *s
     t.SELF = (const double *)(s + p.oSELF);
     t.CN = (const double *)(s + p.oCN);
     t.ASEC = (const double *)(s + p.oASEC);
-    t.THR = (const double *)(s + p.oTHR);
+    t.ACCT = (const double *)(s + p.oACCT);
+    t.ACCLO = (const double *)(s + p.oACCLO);
+    t.ACCHI = (const double *)(s + p.oACCHI);
     t.need = (const uint8_t *)(s + p.oNEED);
     t.cls = (const uint8_t *)(s + p.oCLS);
     t.rate = (const int32_t *)(s + p.oRATE);
     return t;
 }
 
-// word `lane` of (x >> b), x a multi-word bitmap spread over the lanes (lanes past the data hold 0)
-__device__ __forceinline__ uint32_t shr_multi(uint32_t x, int b, int lane) {
+// Compile-time problem dimensions (0 = take them from KParams at run time).  Fixing S/M/K removes the
+// integer divisions of the action decode and most address arithmetic from the per-step instruction stream.
+template <int S_, int M_, int K_>
+struct Dim {
+    const KParams &p;
+    __device__ __forceinline__ explicit Dim(const KParams &kp) : p(kp) {}
+    __device__ __forceinline__ int S() const { return S_ ? S_ : p.S; }
+    __device__ __forceinline__ int W() const { return S_ ? (S_ + 31) / 32 : p.W; }
+    __device__ __forceinline__ int D() const { return S_ ? 2 * S_ : p.D; }
+    __device__ __forceinline__ int CAP() const { return S_ ? ((S_ + 1) / 2 + 31) / 32 * 32 : p.CAP; }
+    __device__ __forceinline__ int M() const { return M_ ? M_ : p.M; }
+    __device__ __forceinline__ int K() const { return K_ ? K_ : p.K; }
+};
+
+// word `lane` of (x >> b), x a multi-word bitmap spread over the lanes.  Lanes past the data hold 0 and
+// qrmsa_create guarantees (S>>5) + ((max_need+1)>>5) + 2 <= 32, so every shuffle source that matters is in
+// range and an out-of-range source (own value of a lane past the data) is 0.
+__device__ __forceinline__ uint32_t shr_multi(uint32_t x, int b) {
     const int q = b >> 5;
-    uint32_t lo = __shfl_down_sync(FULL, x, q);
-    uint32_t hi = __shfl_down_sync(FULL, x, q + 1);
-    if (lane + q > 31) lo = 0;
-    if (lane + q + 1 > 31) hi = 0;
+    const uint32_t lo = __shfl_down_sync(FULL, x, q);
+    const uint32_t hi = __shfl_down_sync(FULL, x, q + 1);
     return __funnelshift_r(lo, hi, b);
 }
 
-// bits [s, e) of the multi-word bitmap that fall in word `lane`
-__device__ __forceinline__ uint32_t range_mask(int s, int e, int lane) {
-    const int lo = max(s - (lane << 5), 0), hi = min(e - (lane << 5), 32);
+// bits [s, e) of the multi-word bitmap that fall in word j
+__device__ __forceinline__ uint32_t range_mask(int s, int e, int j) {
+    const int lo = max(s - (j << 5), 0), hi = min(e - (j << 5), 32);
     if (hi <= lo) return 0u;
     const uint32_t upto_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
     return upto_hi & ~((1u << lo) - 1u);
@@ -152,62 +170,89 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // qrmsa.pyx:1482-1512: AND of the path's link rows; plus one virtual free slot at index S, which turns the
 // guard-band rule of qrmsa.pyx:529-540 ("n slots if the run touches the spectrum end, else n+1") into
-// "n+1 consecutive free slots".
-__device__ __forceinline__ uint32_t path_available(const KParams &p, const uint32_t *bm, int hops, int mylink,
-                                                   int lane) {
+// "n+1 consecutive free slots".  32/W link rows are fetched per pass (3 at W=10), then folded with shuffles.
+template <class DM>
+__device__ __forceinline__ uint32_t path_available(const DM &dm, const uint32_t *bm, int hops, int mylink, int lane) {
+    const int W = dm.W(), S = dm.S();
+    const int G = 32 / W;            // link rows per pass
+    const int grp = lane / W, j = lane - grp * W;
     uint32_t av = 0xffffffffu;
-    for (int i = 0; i < hops; ++i) {
-        const int l = __shfl_sync(FULL, mylink, i);
-        if (lane < p.W) av &= bm[l * p.W + lane];  // mutable state: plain (coherent) load
+#pragma unroll 1
+    for (int i0 = 0; i0 < hops; i0 += G) {
+        const int i = i0 + grp;
+        const int l = __shfl_sync(FULL, mylink, i & 31);
+        if (grp < G && i < hops) av &= bm[l * W + j];  // mutable state: plain (coherent) load
     }
-    if (lane >= p.W) av = 0u;
-    if (lane == (p.S >> 5)) av |= 1u << (p.S & 31);
+    for (int g = 1; g < G; ++g) av &= __shfl_down_sync(FULL, av, g * W);
+    if (lane >= W) av = 0u;
+    if (lane == (S >> 5)) av |= 1u << (S & 31);
     return av;
 }
 
-// core/osnr.pyx:21-142 in the factorised form above.  Returns GSNR in dB (same value on every lane).
-__device__ __forceinline__ double gn_gsnr_db(const KParams &p, const Tab &t, const uint32_t *lists, int path, int hops,
-                                             int mylink, int mycnt, int s, int n, int ncls, int lane,
-                                             uint32_t &terms) {
-    const int c2 = 2 * s + n;
+// core/osnr.pyx:21-142 in the factorised form above.  Returns acc = 1/GSNR (linear; same value on every lane).
+template <class DM>
+__device__ __forceinline__ double gn_inverse_gsnr(const DM &dm, const KParams &p, const Tab &t, const uint32_t *lists,
+                                                  int path, int hops, int mylink, int mycnt, int s, int n, int ncls,
+                                                  int lane, uint32_t &terms) {
+    const int c2 = 2 * s + n, D = dm.D(), CAP = dm.CAP();
     double x = 0.0;
+#pragma unroll 1
     for (int i = 0; i < hops; ++i) {
         const int l = __shfl_sync(FULL, mylink, i);
         const int c = __shfl_sync(FULL, mycnt, i);
-        const double w1 = t.W1[l], w2 = t.W2[l];
-        const uint32_t *lst = lists + (size_t)l * p.CAP;
+        const uint32_t *lst = lists + l * CAP;
+        double s1 = 0.0, s2 = 0.0;
         terms += c;
+#pragma unroll 1
         for (int q = lane; q < c; q += 32) {
             const uint32_t rec = lst[q];
             const int d = abs((int)(rec & 0xfffu) - c2);
-            const double g = t.G[(rec >> 23) * p.D + d];
-            const double h = t.PHIN[rec >> 20] * t.INV[d];
-            x += w1 * g - w2 * h;
+            s1 += t.G[(rec >> 23) * D + d];
+            s2 = fma(t.PHIN[rec >> 20], t.INV[d], s2);
         }
+        x = fma(t.W1[l], s1, x);
+        x = fma(t.W2[l], s2, x);  // W2 is stored negated
     }
     x = warp_sum(x);
     const double2 pg = __ldg(p.path_gn + path);
     const double fc = p.f0 + (p.sb * (double)s) + (p.sb * ((double)n / 2.0));
-    const double acc = t.ASEC[ncls] * fc * pg.x + t.CN[ncls] * (t.SELF[ncls] * pg.y + x);
-    return -10.0 * log10(acc);
+    return t.ASEC[ncls] * fc * pg.x + t.CN[ncls] * (t.SELF[ncls] * pg.y + x);
 }
 
-// qrmsa.pyx:1288-1325 (+ the release key of :1327-1330 is implicit in the precomputed schedule)
-__device__ __forceinline__ int commit(const KParams &p, uint32_t *bm, uint16_t *cnt, uint32_t *lists, int hops,
+// Set (release) or clear (commit) bits [s, e) on every link of the path: lane -> (hop = lane>>2, word = lane&3),
+// a service spans at most 4 bitmap words (number_slots + guard <= 97).
+template <bool SET, class DM>
+__device__ __forceinline__ void update_bitmaps(const DM &dm, uint32_t *bm, int hops, int mylink, int s, int e,
+                                               int lane) {
+    const int W = dm.W();
+    const int w0 = s >> 5;
+    const int k = lane & 3;
+    const int j = w0 + k;
+    const uint32_t mask = j < W ? range_mask(s, e, j) : 0u;
+#pragma unroll 1
+    for (int i0 = 0; i0 < hops; i0 += 8) {
+        const int i = i0 + (lane >> 2);
+        const int l = __shfl_sync(FULL, mylink, i & 31);
+        if (i < hops && mask) {
+            uint32_t *wp = bm + l * W + j;
+            *wp = SET ? (*wp | mask) : (*wp & ~mask);
+        }
+    }
+}
+
+// qrmsa.pyx:1288-1325 (the release key of :1327-1330 is implicit in the precomputed schedule)
+template <class DM>
+__device__ __forceinline__ int commit(const DM &dm, uint32_t *bm, uint16_t *cnt, uint32_t *lists, int hops,
                                       int mylink, int mycnt, int s, int n, uint32_t rec, int lane) {
     int e = s + n;
-    if (e < p.S) e += 1;
-    const uint32_t mask = lane < p.W ? range_mask(s, e, lane) : 0u;
-    for (int i = 0; i < hops; ++i) {
-        const int l = __shfl_sync(FULL, mylink, i);
-        if (mask) bm[l * p.W + lane] &= ~mask;
-    }
+    if (e < dm.S()) e += 1;
+    update_bitmaps<false>(dm, bm, hops, mylink, s, e, lane);
     int err = 0;
     if (lane < hops) {
-        if (mycnt >= p.CAP) {
+        if (mycnt >= dm.CAP()) {
             err = 1;
         } else {
-            lists[(size_t)mylink * p.CAP + mycnt] = rec;
+            lists[mylink * dm.CAP() + mycnt] = rec;
             cnt[mylink] = (uint16_t)(mycnt + 1);
         }
     }
@@ -215,29 +260,32 @@ __device__ __forceinline__ int commit(const KParams &p, uint32_t *bm, uint16_t *
 }
 
 // qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record
-__device__ __forceinline__ int release_service(const KParams &p, const Tab &t, uint32_t *bm, uint16_t *cnt,
-                                               uint32_t *lists, const uint4 rq, int lane) {
+template <class DM>
+__device__ __forceinline__ int release_service(const DM &dm, const KParams &p, const Tab &t, uint32_t *bm,
+                                               uint16_t *cnt, uint32_t *lists, const uint4 rq, int lane) {
+    const int S = dm.S(), M = dm.M(), CAP = dm.CAP();
     const uint32_t a = rq.w & QRMSA_ACTION_MASK;
     const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
-    const int s = a % p.S;
-    const int rel = (a / p.S) % p.Mc;
-    const int pi = a / (p.S * p.Mc);
-    const int m = (p.M - 1) - rel;
-    const int n = t.need[rate * p.M + m];
-    const int path = (src * p.N + dst) * p.K + pi;
+    const int s = a % S;
+    const int rel = (a / S) % M;
+    const int pi = a / (S * M);
+    const int m = (M - 1) - rel;
+    const int n = t.need[rate * M + m];
+    const int path = (src * p.N + dst) * dm.K() + pi;
     const int hops = __ldg(p.path_hops + path);
-    const int mylink = lane < hops ? __ldg(p.path_links + (size_t)path * p.Hmax + lane) : 0;
+    const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+    const int mycnt = lane < hops ? cnt[mylink] : 0;
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
-                            ((uint32_t)t.cls[rate * p.M + m] << 23);
-    const int e = min(s + n + 1, p.S);
-    const uint32_t mask = lane < p.W ? range_mask(s, e, lane) : 0u;
+                            ((uint32_t)t.cls[rate * M + m] << 23);
+    update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
     int err = 0;
+#pragma unroll 1
     for (int i = 0; i < hops; ++i) {
         const int l = __shfl_sync(FULL, mylink, i);
-        if (mask) bm[l * p.W + lane] |= mask;
-        uint32_t *lst = lists + (size_t)l * p.CAP;
-        const int c = cnt[l];
+        const int c = __shfl_sync(FULL, mycnt, i);
+        uint32_t *lst = lists + l * CAP;
         int found = -1;
+#pragma unroll 1
         for (int q0 = 0; q0 < c; q0 += 32) {
             const int q = q0 + lane;
             const uint32_t v = q < c ? lst[q] : 0xffffffffu;
@@ -250,12 +298,11 @@ __device__ __forceinline__ int release_service(const KParams &p, const Tab &t, u
         if (found < 0) {
             err = 1;
         } else if (lane == 0) {
-            const uint32_t last = lst[c - 1];
-            lst[found] = last;
-            cnt[l] = (uint16_t)(c - 1);
+            lst[found] = lst[c - 1];
         }
-        __syncwarp();
     }
+    if (lane < hops && mycnt > 0) cnt[mylink] = (uint16_t)(mycnt - 1);
+    __syncwarp();
     return err;
 }
 
@@ -279,16 +326,17 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
 // qrmsa.pyx:1067-1122 after a request has been decided: take the next request (clock := its arrival) and
 // release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
 // schedule exactly as they are absent from the reference heap.
-__device__ __forceinline__ int advance_and_release(const KParams &p, const Tab &t, uint4 *tr, const uint16_t *perm,
-                                                   uint32_t *bm, uint16_t *cnt, uint32_t *lists, int &cur,
-                                                   int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
+template <class DM>
+__device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
+                                                   const uint16_t *perm, uint32_t *bm, uint16_t *cnt, uint32_t *lists,
+                                                   int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
     cur += 1;
     const float now = __uint_as_float(tr[cur].x);
     int err = 0;
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];
         if (rq.w & QRMSA_FLAG_ACCEPTED) {
-            err |= release_service(p, t, bm, cnt, lists, rq, lane);
+            err |= release_service(dm, p, t, bm, cnt, lists, rq, lane);
             n_rel += 1;
         }
         rel_ptr += 1;
@@ -299,21 +347,31 @@ __device__ __forceinline__ int advance_and_release(const KParams &p, const Tab &
 
 #define QCNT(slot, v) cnt_reg += (lane == (slot)) ? (uint32_t)(v) : 0u
 
+// One QoT-checked candidate: accept iff gsnr >= threshold (heuristics.py:957-958), decided on the linear
+// value acc = 1/GSNR against ACCT[m] = 10^(-thr/10); |gsnr - thr| < 1e-3 dB <=> ACCLO[m] < acc < ACCHI[m].
+__device__ __forceinline__ bool qot_ok(const Tab &t, int m, double acc, uint32_t &flags) {
+    if (acc > t.ACCLO[m] && acc < t.ACCHI[m]) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+    return acc <= t.ACCT[m];
+}
+
 // --------------------------------------------------------------------------------------------------------
 // Fused first-fit heuristic + step, n_steps requests per env per launch.
 // heuristics.py:923-966 + qrmsa.pyx:838-1065.
 // --------------------------------------------------------------------------------------------------------
+template <int S_, int M_, int K_>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams p, const int n_steps) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
     stage_tables(p, smem, &mbar);
     const Tab t = make_tab(p, smem);
+    const Dim<S_, M_, K_> dm(p);
+    const int S = dm.S(), M = dm.M(), K = dm.K();
 
     const int lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
     const int gw = blockIdx.x * wpc + (threadIdx.x >> 5);
     const int gstride = gridDim.x * wpc;
-    const int reject = p.K * p.Mc * p.S;
+    const int reject = K * M * S;
 
     for (int env = gw; env < p.n_envs; env += gstride) {
         int4 st = p.estate[env];
@@ -323,40 +381,43 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
         const uint16_t *perm = p.perm + (size_t)env * p.T;
         uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
         uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
-        uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
+        uint32_t *lists = p.lists + (size_t)env * p.E * dm.CAP();
         double *glog = p.gsnr_log ? p.gsnr_log + (size_t)env * p.T : nullptr;
         Head head = load_head(p, tr, perm, rel_ptr);
         uint32_t cnt_reg = 0;
 
+#pragma unroll 1
         for (int step = 0; step < n_steps && cur + 1 < p.n_req && !err; ++step) {
             const uint4 rq = tr[cur];
             const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
-            const int pbase = (src * p.N + dst) * p.K;
+            const int pbase = (src * p.N + dst) * K;
             uint32_t flags = QRMSA_FLAG_DECIDED;
             int action = reject;
-            double g_acc = 0.0;
+            double acc_ok = 1.0;
             int blk_res = 0, blk_osnr = 0;
             bool found = false;
 
-            for (int pi = 0; pi < p.K && !found; ++pi) {
+#pragma unroll 1
+            for (int pi = 0; pi < K && !found; ++pi) {
                 const int path = pbase + pi;
                 const int hops = __ldg(p.path_hops + path);
                 if (hops == 0) continue;
-                const int mylink = lane < hops ? __ldg(p.path_links + (size_t)path * p.Hmax + lane) : 0;
+                const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
                 const int mycnt = lane < hops ? cnt[mylink] : 0;
-                const uint32_t av = path_available(p, bm, hops, mylink, lane);
+                const uint32_t av = path_available(dm, bm, hops, mylink, lane);
                 QCNT(QRMSA_CNT_LINKS_READ, hops);
                 QCNT(QRMSA_CNT_PATHS_TRIED, 1);
                 uint32_t r = av;
                 int a = 1;
                 bool counted = false;
-                for (int m = p.M - 1; m >= 0; --m) {
-                    const int n = t.need[rate * p.M + m];
+#pragma unroll 1
+                for (int m = M - 1; m >= 0; --m) {
+                    const int n = t.need[rate * M + m];
                     const int L = n + 1;
                     if (L < a) { r = av; a = 1; }
                     while (a < L) {
                         const int b = min(a, L - a);
-                        r &= shr_multi(r, b, lane);
+                        r &= shr_multi(r, b);
                         a += b;
                     }
                     const unsigned any = __ballot_sync(FULL, r != 0u);
@@ -364,21 +425,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                     const int fl = __ffs(any) - 1;
                     const uint32_t w = __shfl_sync(FULL, r, fl);
                     const int s = (fl << 5) + __ffs(w) - 1;
-                    const int ncls = t.cls[rate * p.M + m];
+                    const int ncls = t.cls[rate * M + m];
                     uint32_t terms = 0;
-                    const double g = gn_gsnr_db(p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
+                    const double acc = gn_inverse_gsnr(dm, p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
                     QCNT(QRMSA_CNT_GN_EVALS, 1);
                     QCNT(QRMSA_CNT_GN_TERMS, terms);
                     if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
-                    const double thr = t.THR[m];
-                    if (fabs(g - thr) < 1e-3) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
-                    if (g >= thr) {
+                    if (qot_ok(t, m, acc, flags)) {
                         found = true;
-                        action = pi * p.Mc * p.S + ((p.M - 1) - m) * p.S + s;
-                        g_acc = g;
+                        action = pi * M * S + ((M - 1) - m) * S + s;
+                        acc_ok = acc;
                         const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                                              ((uint32_t)ncls << 23);
-                        if (commit(p, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                        if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
                         flags |= QRMSA_FLAG_ACCEPTED;
                         accepted += 1;
                         QCNT(QRMSA_CNT_ACCEPTED, 1);
@@ -401,11 +460,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
             if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
             if (lane == 0) {
                 tr[cur].w = (uint32_t)action | flags;
-                if (glog) glog[cur] = g_acc;
+                if (glog) glog[cur] = found ? -10.0 * log10(acc_ok) : 0.0;  // 10*log10(1/acc), osnr.pyx:138
             }
             __syncwarp();
             uint32_t n_rel = 0;
-            if (advance_and_release(p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+            if (advance_and_release(dm, p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
         }
@@ -427,6 +486,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
     __shared__ uint64_t mbar;
     stage_tables(p, smem, &mbar);
     const Tab t = make_tab(p, smem);
+    const Dim<0, 0, 0> dm(p);
 
     const int lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
@@ -465,12 +525,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 const int n = t.need[rate * p.M + m];
                 const int path = (src * p.N + dst) * p.K + pi;
                 const int hops = __ldg(p.path_hops + path);
-                const int mylink = lane < hops ? __ldg(p.path_links + (size_t)path * p.Hmax + lane) : 0;
+                const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
                 const int mycnt = lane < hops ? cnt[mylink] : 0;
                 // is_path_free (qrmsa.pyx:1248-1264): [s, s+n (+1 guard if it ends before S)) free on every link
                 bool free_ok = hops > 0 && s + n <= p.S;
                 if (free_ok) {
-                    const uint32_t av = path_available(p, bm, hops, mylink, lane);
+                    const uint32_t av = path_available(dm, bm, hops, mylink, lane);
                     const int e = (s + n < p.S) ? s + n + 1 : s + n;
                     const uint32_t mask = lane < p.W ? range_mask(s, e, lane) : 0u;
                     free_ok = !__any_sync(FULL, (av & mask) != mask);
@@ -484,13 +544,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 } else {
                     const int ncls = t.cls[rate * p.M + m];
                     uint32_t terms = 0;
-                    g = gn_gsnr_db(p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
-                    const double thr = t.THR[m];
-                    if (fabs(g - thr) < 1e-3) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
-                    if (g >= thr) {
+                    const double acc = gn_inverse_gsnr(dm, p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
+                    g = -10.0 * log10(acc);
+                    if (qot_ok(t, m, acc, flags)) {
                         const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                                              ((uint32_t)ncls << 23);
-                        if (commit(p, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                        if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
                         flags |= QRMSA_FLAG_ACCEPTED;
                         accepted += 1;
                         status = QRMSA_STEP_ACCEPTED;
@@ -517,7 +576,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 __syncwarp();
                 Head head = load_head(p, tr, perm, rel_ptr);
                 uint32_t n_rel = 0;
-                if (advance_and_release(p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+                if (advance_and_release(dm, p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
                     err = ENV_ERR_RELEASE_NOT_FOUND;
                 QCNT(QRMSA_CNT_RELEASES, n_rel);
                 term = (cur + 1 == episode_length);  // episode_services_processed == episode_length (qrmsa.pyx:1056)
@@ -658,7 +717,7 @@ __global__ void k_probe_gsnr(const KParams p, const int env, const int src, cons
     const int hops = __ldg(p.path_hops + path);
     const uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
     const uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
-    const int mylink = lane < hops ? __ldg(p.path_links + (size_t)path * p.Hmax + lane) : 0;
+    const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
     const int mycnt = lane < hops ? cnt[mylink] : 0;
     // class of n: search the class table through NEED/CLS
     int ncls = -1;
@@ -667,7 +726,7 @@ __global__ void k_probe_gsnr(const KParams p, const int env, const int src, cons
     double g = nan("");
     if (ncls >= 0 && hops > 0) {
         uint32_t terms = 0;
-        g = gn_gsnr_db(p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
+        g = -10.0 * log10(gn_inverse_gsnr(Dim<0, 0, 0>(p), p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms));
     }
     if (lane == 0) *out = g;
 }
