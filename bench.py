@@ -239,7 +239,8 @@ def algorithmic_bytes_per_step(c, n_slots):
     rel = c["releases"] / dec
     b = R + Lr * W + Nq * C + a * (h * W + h * C + V + 8) + rel * (V + 8 + 2 * h * W + 2 * h * C)
     return b, dict(Lr=Lr, Nq=Nq, accept_ratio=a, hops=h, releases_per_step=rel,
-                   gn_evals_per_step=c["gn_evals"] / dec, gn_terms_per_step=c["gn_terms"] / dec)
+                   gn_evals_per_step=c["gn_evals"] / dec, gn_terms_per_step=c["gn_terms"] / dec,
+                   gn_pruned_per_step=c.get("gn_pruned", 0) / dec)
 
 
 def run_b200(args, rank, local_rank, world):
@@ -319,6 +320,7 @@ def run_b200(args, rank, local_rank, world):
     c1 = eng.counters().sum(0)
     delta = sum_over_ranks((c1 - c0).tolist())
     cd = {n: int(delta[i]) for i, n in enumerate(_lib.COUNTER_NAMES)}
+    cd["gn_pruned"] = int(delta[24])
     env_steps = cd["decided"]
     assert env_steps == world * n_envs * chunk * K, (env_steps, world, n_envs, chunk, K)
     assert cd["errors"] == 0

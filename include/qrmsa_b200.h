@@ -79,6 +79,7 @@ enum {
     QRMSA_CNT_PATHS_TRIED = 14,
     QRMSA_CNT_ERRORS = 15,        /* envs that hit an error state (list overflow, ValueError path)   */
     QRMSA_CNT_MOD_HIST = 16,      /* [16..23] accepted services per modulation index                 */
+    QRMSA_CNT_GN_PRUNED = 24,     /* QoT checks refused on the empty-network bound without a GN sum   */
     QRMSA_N_COUNTERS = 32
 };
 

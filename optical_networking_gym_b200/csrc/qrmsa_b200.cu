@@ -72,16 +72,6 @@ int ensure_stage(qrmsa_ctx *ctx, size_t bytes) {
     return QRMSA_OK;
 }
 
-struct Blob {
-    std::vector<unsigned char> bytes;
-    int add(const void *src, size_t n) {
-        size_t off = round_up(bytes.size(), 16);
-        bytes.resize(off + n);
-        memcpy(bytes.data() + off, src, n);
-        return (int)off;
-    }
-};
-
 const double PHI_MOD[6] = {1.0, 1.0, 2.0 / 3.0, 17.0 / 25.0, 69.0 / 100.0, 13.0 / 21.0};  // osnr.pyx:38-41
 
 }  // namespace
@@ -128,7 +118,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
 
     // ---- validation of what the kernels implement
     if (S < 2 || S > 960) { ctx->err = "n_slots must be in 2..960 (one bitmap word per lane + the virtual slot)"; return QRMSA_ERR_UNSUPPORTED; }
-    if (t->max_hops > 32) { ctx->err = "paths longer than 32 hops"; return QRMSA_ERR_UNSUPPORTED; }
+    if (t->max_hops > 32 || t->max_hops < 1) { ctx->err = "paths longer than 32 hops"; return QRMSA_ERR_UNSUPPORTED; }
     if (M > 8 || R > 255 || N > 255 || E > 255 || K > 255) { ctx->err = "table dimension too large"; return QRMSA_ERR_UNSUPPORTED; }
     if (kp.Mc != M) { ctx->err = "modulations_to_consider must equal the number of modulations"; return QRMSA_ERR_UNSUPPORTED; }
     if ((long long)K * M * S >= (1 << 24)) { ctx->err = "action space exceeds 24 bits"; return QRMSA_ERR_UNSUPPORTED; }
@@ -216,23 +206,45 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     std::vector<int32_t> rate_milli(R);
     for (int r = 0; r < R; r++) rate_milli[r] = (int32_t)llround(t->bit_rates[r] * 1000.0);
 
-    Blob blob;
-    kp.oG = blob.add(G.data(), G.size() * 8);
-    kp.oINV = blob.add(INV.data(), INV.size() * 8);
-    kp.oPHIN = blob.add(PHIN.data(), PHIN.size() * 8);
-    kp.oW1 = blob.add(W1.data(), W1.size() * 8);
-    kp.oW2 = blob.add(W2.data(), W2.size() * 8);
-    kp.oSELF = blob.add(SELF.data(), SELF.size() * 8);
-    kp.oCN = blob.add(CN.data(), CN.size() * 8);
-    kp.oASEC = blob.add(ASEC.data(), ASEC.size() * 8);
-    kp.oACCT = blob.add(ACCT.data(), ACCT.size() * 8);
-    kp.oACCLO = blob.add(ACCLO.data(), ACCLO.size() * 8);
-    kp.oACCHI = blob.add(ACCHI.data(), ACCHI.size() * 8);
-    kp.oNEED = blob.add(ctx->need.data(), ctx->need.size());
-    kp.oCLS = blob.add(ctx->cls.data(), ctx->cls.size());
-    kp.oRATE = blob.add(rate_milli.data(), rate_milli.size() * 4);
-    blob.bytes.resize(round_up(blob.bytes.size(), 16));
-    kp.blob_bytes = (int)blob.bytes.size();
+    // ---- "prunable" paths: every neighbour term W1_l*G[c][d] + W2_l*PHIN[c,m]*INV[d] (W2 negated) is >= 0 for
+    // all channel classes, modulations and admissible distances d >= n_c + 3 on all links of the path, so the
+    // empty-network value bounds acc from below and hopeless modulations can be refused without a GN sum.
+    std::vector<char> link_pos(E, 1);
+    for (int l = 0; l < E; l++)
+        for (int c = 0; c < NC && link_pos[l]; c++)
+            for (int m = 0; m < M && link_pos[l]; m++)
+                for (int d = cls_n[c] + 3; d < D; d++)
+                    if (W1[l] * G[(size_t)c * D + d] + W2[l] * (PHIN[(c << 3) | m] * INV[d]) < 0.0) { link_pos[l] = 0; break; }
+    std::vector<uint8_t> hops_dev(n_paths);
+    for (size_t pi_ = 0; pi_ < n_paths; pi_++) {
+        const int hops = t->path_hops[pi_];
+        bool ok = hops > 0;
+        for (int h = 0; h < hops; h++) ok = ok && link_pos[t->path_links[pi_ * t->max_hops + h]];
+        hops_dev[pi_] = (uint8_t)(hops | (ok ? 0x80 : 0));
+    }
+
+    // ---- shared-memory image, fixed layout (qrmsa_kernels.cuh namespace lay)
+    if (R * M > lay::MAX_RM || E > lay::MAX_E || NC > lay::MAX_NC || M > lay::MAX_M || R > lay::MAX_R) {
+        ctx->err = "table dimension exceeds the shared-memory layout capacity";
+        return QRMSA_ERR_UNSUPPORTED;
+    }
+    std::vector<unsigned char> blob((size_t)round_up(lay::G(D) + (size_t)NC * D * 8, 16), 0);
+    auto put = [&](int off, const void *src, size_t n) { memcpy(blob.data() + off, src, n); };
+    put(lay::PHIN, PHIN.data(), PHIN.size() * 8);
+    put(lay::W1, W1.data(), W1.size() * 8);
+    put(lay::W2, W2.data(), W2.size() * 8);
+    put(lay::SELF, SELF.data(), SELF.size() * 8);
+    put(lay::CN, CN.data(), CN.size() * 8);
+    put(lay::ASEC, ASEC.data(), ASEC.size() * 8);
+    put(lay::ACCT, ACCT.data(), ACCT.size() * 8);
+    put(lay::ACCLO, ACCLO.data(), ACCLO.size() * 8);
+    put(lay::ACCHI, ACCHI.data(), ACCHI.size() * 8);
+    put(lay::NEED, ctx->need.data(), ctx->need.size());
+    put(lay::CLS, ctx->cls.data(), ctx->cls.size());
+    put(lay::RATE, rate_milli.data(), rate_milli.size() * 4);
+    put(lay::INV, INV.data(), INV.size() * 8);
+    put(lay::G(D), G.data(), G.size() * 8);
+    kp.blob_bytes = (int)blob.size();
 
     // ---- device properties and launch shape
     CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -258,10 +270,10 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
 
     // ---- uploads and state
     int rc;
-    if ((rc = dev_upload(ctx, &kp.path_hops, t->path_hops, n_paths))) return rc;
+    if ((rc = dev_upload(ctx, &kp.path_hops, (const uint8_t *)hops_dev.data(), n_paths))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_links, t->path_links, n_paths * t->max_hops))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_gn, pgn.data(), n_paths))) return rc;
-    if ((rc = dev_upload(ctx, &kp.blob, blob.bytes.data(), blob.bytes.size()))) return rc;
+    if ((rc = dev_upload(ctx, &kp.blob, (const unsigned char *)blob.data(), blob.size()))) return rc;
     kp.bm_stride = round_up((size_t)E * kp.W, 32);
     kp.cnt_stride = round_up((size_t)E, 64);
     if ((rc = dev_alloc(ctx, &kp.bm, (size_t)n_envs * kp.bm_stride))) return rc;

@@ -55,8 +55,6 @@ struct KParams {
     const double2 *path_gn;     // [N*N*K] {PA, PB}
     const unsigned char *blob;  // shared-memory image, 16-byte multiple
     int blob_bytes;
-    // byte offsets into the blob
-    int oG, oINV, oPHIN, oW1, oW2, oSELF, oCN, oASEC, oACCT, oACCLO, oACCHI, oNEED, oCLS, oRATE;
     double f0, sb;
     // per-env state
     uint32_t *bm;
@@ -71,16 +69,53 @@ struct KParams {
     size_t cnt_stride;             // uint16 per env
 };
 
+// Shared-memory image of the static tables (byte offsets).  The layout is FIXED (capacities, not sizes) so
+// that every table access compiles to an LDS with an immediate offset from the dynamic-shared-memory base;
+// the only size-dependent offset is G's, which follows INV[D].
+namespace lay {
+constexpr int PHIN = 0;      // double[256]  phi(mod) * bw(class), index (class << 3) | mod
+constexpr int W1 = 2048;     // double[256]  n_spans * l_eff                       per link
+constexpr int W2 = 4096;     // double[256]  -n_spans * l_eff * (5/3) * l_eff / L  per link (negated)
+constexpr int SELF = 6144;   // double[32]   self-channel asinh term               per slot class
+constexpr int CN = 6400;     // double[32]   NLI prefactor / P                     per slot class
+constexpr int ASEC = 6656;   // double[32]   bw * h / P                            per slot class
+constexpr int ACCT = 6912;   // double[8]    10^(-thr/10)                          per modulation
+constexpr int ACCLO = 6976;  // double[8]    10^(-(thr+1e-3)/10)
+constexpr int ACCHI = 7040;  // double[8]    10^(-(thr-1e-3)/10)
+constexpr int NEED = 7104;   // u8[512]      slots needed  [rate*M + m]
+constexpr int CLS = 7616;    // u8[512]      slot class    [rate*M + m]
+constexpr int RATE = 8128;   // i32[256]     bit rate in Mb/s
+constexpr int INV = 9152;    // double[D]    1 / (d * slot_bw / 2)
+constexpr int MAX_RM = 512, MAX_E = 256, MAX_NC = 32, MAX_M = 8, MAX_R = 256;
+__host__ __device__ constexpr int G(int D) { return INV + 8 * D; }  // double[NC][D]
+}  // namespace lay
+
+extern __shared__ __align__(128) unsigned char qsmem[];
+
 struct Tab {
-    const double *G, *INV, *PHIN, *W1, *W2, *SELF, *CN, *ASEC, *ACCT, *ACCLO, *ACCHI;
-    const uint8_t *need, *cls;
-    const int32_t *rate;
+    __device__ __forceinline__ static double d(int byte_off, int idx) {
+        return *reinterpret_cast<const double *>(qsmem + byte_off + idx * 8);
+    }
+    __device__ __forceinline__ static double PHIN(int i) { return d(lay::PHIN, i); }
+    __device__ __forceinline__ static double W1(int i) { return d(lay::W1, i); }
+    __device__ __forceinline__ static double W2(int i) { return d(lay::W2, i); }
+    __device__ __forceinline__ static double SELF(int i) { return d(lay::SELF, i); }
+    __device__ __forceinline__ static double CN(int i) { return d(lay::CN, i); }
+    __device__ __forceinline__ static double ASEC(int i) { return d(lay::ASEC, i); }
+    __device__ __forceinline__ static double ACCT(int i) { return d(lay::ACCT, i); }
+    __device__ __forceinline__ static double ACCLO(int i) { return d(lay::ACCLO, i); }
+    __device__ __forceinline__ static double ACCHI(int i) { return d(lay::ACCHI, i); }
+    __device__ __forceinline__ static double INV(int i) { return d(lay::INV, i); }
+    __device__ __forceinline__ static double G(int D, int i) { return d(lay::G(D), i); }
+    __device__ __forceinline__ static int need(int i) { return qsmem[lay::NEED + i]; }
+    __device__ __forceinline__ static int cls(int i) { return qsmem[lay::CLS + i]; }
+    __device__ __forceinline__ static int rate(int i) { return *reinterpret_cast<const int *>(qsmem + lay::RATE + i * 4); }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Stage the table blob into shared memory with the TMA (1-D bulk copy, completion on an mbarrier).
-__device__ __forceinline__ void stage_tables(const KParams &p, unsigned char *smem, uint64_t *mbar) {
+__device__ __forceinline__ void stage_tables(const KParams &p, uint64_t *mbar) {
     const uint32_t bar = smem_u32(mbar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -94,7 +129,7 @@ __device__ __forceinline__ void stage_tables(const KParams &p, unsigned char *sm
             int sz = p.blob_bytes - off < CH ? p.blob_bytes - off : CH;
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    smem_u32(smem + off)),
+                    smem_u32(qsmem + off)),
                 "l"(p.blob + off), "r"(sz), "r"(bar)
                 : "memory");
         }
@@ -109,25 +144,6 @@ __device__ __forceinline__ void stage_tables(const KParams &p, unsigned char *sm
             : "r"(bar)
             : "memory");
     }
-}
-
-__device__ __forceinline__ Tab make_tab(const KParams &p, const unsigned char *s) {
-    Tab t;
-    t.G = (const double *)(s + p.oG);
-    t.INV = (const double *)(s + p.oINV);
-    t.PHIN = (const double *)(s + p.oPHIN);
-    t.W1 = (const double *)(s + p.oW1);
-    t.W2 = (const double *)(s + p.oW2);
-    t.SELF = (const double *)(s + p.oSELF);
-    t.CN = (const double *)(s + p.oCN);
-    t.ASEC = (const double *)(s + p.oASEC);
-    t.ACCT = (const double *)(s + p.oACCT);
-    t.ACCLO = (const double *)(s + p.oACCLO);
-    t.ACCHI = (const double *)(s + p.oACCHI);
-    t.need = (const uint8_t *)(s + p.oNEED);
-    t.cls = (const uint8_t *)(s + p.oCLS);
-    t.rate = (const int32_t *)(s + p.oRATE);
-    return t;
 }
 
 // Compile-time problem dimensions (0 = take them from KParams at run time).  Fixing S/M/K removes the
@@ -181,7 +197,7 @@ __device__ __forceinline__ uint32_t path_available(const DM &dm, const uint32_t 
     for (int i0 = 0; i0 < hops; i0 += G) {
         const int i = i0 + grp;
         const int l = __shfl_sync(FULL, mylink, i & 31);
-        if (grp < G && i < hops) av &= bm[l * W + j];  // mutable state: plain (coherent) load
+        if (grp < G && i < hops) av &= bm[(unsigned)(l * W + j)];  // mutable state: plain (coherent) load
     }
     for (int g = 1; g < G; ++g) av &= __shfl_down_sync(FULL, av, g * W);
     if (lane >= W) av = 0u;
@@ -189,34 +205,50 @@ __device__ __forceinline__ uint32_t path_available(const DM &dm, const uint32_t 
     return av;
 }
 
-// core/osnr.pyx:21-142 in the factorised form above.  Returns acc = 1/GSNR (linear; same value on every lane).
+// core/osnr.pyx:21-142 in the factorised form above:  acc = 1/GSNR = ase + cn * (selfpb + x)
+//   ase + cn*selfpb is the value in an EMPTY network; x >= 0 is the neighbour sum (every term is >= 0 on
+//   "prunable" paths, verified on the host), so a modulation whose empty-network value already misses its
+//   threshold by more than 1e-3 dB can be refused without walking the channel lists.
+struct GnBase {
+    double ase, cn, selfpb;
+    __device__ __forceinline__ double empty() const { return ase + cn * selfpb; }
+    __device__ __forceinline__ double with(double x) const { return ase + cn * (selfpb + x); }
+};
+
+__device__ __forceinline__ GnBase gn_base(const KParams &p, int path, int s, int n, int ncls) {
+    const double2 pg = __ldg(p.path_gn + path);
+    const double fc = p.f0 + (p.sb * (double)s) + (p.sb * ((double)n / 2.0));  // heuristics.py:948-951
+    GnBase b;
+    b.ase = Tab::ASEC(ncls) * fc * pg.x;
+    b.cn = Tab::CN(ncls);
+    b.selfpb = Tab::SELF(ncls) * pg.y;
+    return b;
+}
+
+// sum over the path's links and every channel on them (same value on every lane)
 template <class DM>
-__device__ __forceinline__ double gn_inverse_gsnr(const DM &dm, const KParams &p, const Tab &t, const uint32_t *lists,
-                                                  int path, int hops, int mylink, int mycnt, int s, int n, int ncls,
-                                                  int lane, uint32_t &terms) {
-    const int c2 = 2 * s + n, D = dm.D(), CAP = dm.CAP();
+__device__ __forceinline__ double gn_neighbours(const DM &dm, const uint32_t *lists, int hops, int mylink, int mycnt,
+                                                int c2, int lane, uint32_t &terms) {
+    const int D = dm.D(), CAP = dm.CAP();
     double x = 0.0;
 #pragma unroll 1
     for (int i = 0; i < hops; ++i) {
         const int l = __shfl_sync(FULL, mylink, i);
         const int c = __shfl_sync(FULL, mycnt, i);
-        const uint32_t *lst = lists + l * CAP;
+        const uint32_t *lst = lists + (unsigned)(l * CAP) + lane;
         double s1 = 0.0, s2 = 0.0;
         terms += c;
 #pragma unroll 1
-        for (int q = lane; q < c; q += 32) {
-            const uint32_t rec = lst[q];
+        for (int q = lane; q < c; q += 32, lst += 32) {
+            const uint32_t rec = *lst;
             const int d = abs((int)(rec & 0xfffu) - c2);
-            s1 += t.G[(rec >> 23) * D + d];
-            s2 = fma(t.PHIN[rec >> 20], t.INV[d], s2);
+            s1 += Tab::G(D, (rec >> 23) * D + d);
+            s2 = fma(Tab::PHIN(rec >> 20), Tab::INV(d), s2);
         }
-        x = fma(t.W1[l], s1, x);
-        x = fma(t.W2[l], s2, x);  // W2 is stored negated
+        x = fma(Tab::W1(l), s1, x);
+        x = fma(Tab::W2(l), s2, x);  // W2 is stored negated
     }
-    x = warp_sum(x);
-    const double2 pg = __ldg(p.path_gn + path);
-    const double fc = p.f0 + (p.sb * (double)s) + (p.sb * ((double)n / 2.0));
-    return t.ASEC[ncls] * fc * pg.x + t.CN[ncls] * (t.SELF[ncls] * pg.y + x);
+    return warp_sum(x);
 }
 
 // Set (release) or clear (commit) bits [s, e) on every link of the path: lane -> (hop = lane>>2, word = lane&3),
@@ -234,7 +266,7 @@ __device__ __forceinline__ void update_bitmaps(const DM &dm, uint32_t *bm, int h
         const int i = i0 + (lane >> 2);
         const int l = __shfl_sync(FULL, mylink, i & 31);
         if (i < hops && mask) {
-            uint32_t *wp = bm + l * W + j;
+            uint32_t *wp = bm + (unsigned)(l * W + j);
             *wp = SET ? (*wp | mask) : (*wp & ~mask);
         }
     }
@@ -252,7 +284,7 @@ __device__ __forceinline__ int commit(const DM &dm, uint32_t *bm, uint16_t *cnt,
         if (mycnt >= dm.CAP()) {
             err = 1;
         } else {
-            lists[mylink * dm.CAP() + mycnt] = rec;
+            lists[(unsigned)(mylink * dm.CAP() + mycnt)] = rec;
             cnt[mylink] = (uint16_t)(mycnt + 1);
         }
     }
@@ -261,7 +293,7 @@ __device__ __forceinline__ int commit(const DM &dm, uint32_t *bm, uint16_t *cnt,
 
 // qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record
 template <class DM>
-__device__ __forceinline__ int release_service(const DM &dm, const KParams &p, const Tab &t, uint32_t *bm,
+__device__ __forceinline__ int release_service(const DM &dm, const KParams &p, uint32_t *bm,
                                                uint16_t *cnt, uint32_t *lists, const uint4 rq, int lane) {
     const int S = dm.S(), M = dm.M(), CAP = dm.CAP();
     const uint32_t a = rq.w & QRMSA_ACTION_MASK;
@@ -270,20 +302,20 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int rel = (a / S) % M;
     const int pi = a / (S * M);
     const int m = (M - 1) - rel;
-    const int n = t.need[rate * M + m];
+    const int n = Tab::need(rate * M + m);
     const int path = (src * p.N + dst) * dm.K() + pi;
-    const int hops = __ldg(p.path_hops + path);
+    const int hops = __ldg(p.path_hops + path) & 0x7f;
     const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
     const int mycnt = lane < hops ? cnt[mylink] : 0;
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
-                            ((uint32_t)t.cls[rate * M + m] << 23);
+                            ((uint32_t)Tab::cls(rate * M + m) << 23);
     update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
     int err = 0;
 #pragma unroll 1
     for (int i = 0; i < hops; ++i) {
         const int l = __shfl_sync(FULL, mylink, i);
         const int c = __shfl_sync(FULL, mycnt, i);
-        uint32_t *lst = lists + l * CAP;
+        uint32_t *lst = lists + (unsigned)(l * CAP);
         int found = -1;
 #pragma unroll 1
         for (int q0 = 0; q0 < c; q0 += 32) {
@@ -327,7 +359,7 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
 // release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
 // schedule exactly as they are absent from the reference heap.
 template <class DM>
-__device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
+__device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, uint4 *tr,
                                                    const uint16_t *perm, uint32_t *bm, uint16_t *cnt, uint32_t *lists,
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
     cur += 1;
@@ -336,7 +368,7 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];
         if (rq.w & QRMSA_FLAG_ACCEPTED) {
-            err |= release_service(dm, p, t, bm, cnt, lists, rq, lane);
+            err |= release_service(dm, p, bm, cnt, lists, rq, lane);
             n_rel += 1;
         }
         rel_ptr += 1;
@@ -349,9 +381,9 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
 
 // One QoT-checked candidate: accept iff gsnr >= threshold (heuristics.py:957-958), decided on the linear
 // value acc = 1/GSNR against ACCT[m] = 10^(-thr/10); |gsnr - thr| < 1e-3 dB <=> ACCLO[m] < acc < ACCHI[m].
-__device__ __forceinline__ bool qot_ok(const Tab &t, int m, double acc, uint32_t &flags) {
-    if (acc > t.ACCLO[m] && acc < t.ACCHI[m]) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
-    return acc <= t.ACCT[m];
+__device__ __forceinline__ bool qot_ok(int m, double acc, uint32_t &flags) {
+    if (acc > Tab::ACCLO(m) && acc < Tab::ACCHI(m)) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+    return acc <= Tab::ACCT(m);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -360,10 +392,8 @@ __device__ __forceinline__ bool qot_ok(const Tab &t, int m, double acc, uint32_t
 // --------------------------------------------------------------------------------------------------------
 template <int S_, int M_, int K_>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams p, const int n_steps) {
-    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
-    stage_tables(p, smem, &mbar);
-    const Tab t = make_tab(p, smem);
+    stage_tables(p, &mbar);
     const Dim<S_, M_, K_> dm(p);
     const int S = dm.S(), M = dm.M(), K = dm.K();
 
@@ -391,6 +421,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
             const uint4 rq = tr[cur];
             const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
             const int pbase = (src * p.N + dst) * K;
+            // lane m holds (slots needed, slot class) of modulation m for this request's bit rate
+            const int mynd = lane < M ? (Tab::need(rate * M + lane) | (Tab::cls(rate * M + lane) << 8)) : 0;
             uint32_t flags = QRMSA_FLAG_DECIDED;
             int action = reject;
             double acc_ok = 1.0;
@@ -400,8 +432,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
 #pragma unroll 1
             for (int pi = 0; pi < K && !found; ++pi) {
                 const int path = pbase + pi;
-                const int hops = __ldg(p.path_hops + path);
+                const int hp = __ldg(p.path_hops + path);  // bit 7: every neighbour term of this path is >= 0
+                const int hops = hp & 0x7f;
                 if (hops == 0) continue;
+                const bool prunable = (hp & 0x80) != 0;
                 const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
                 const int mycnt = lane < hops ? cnt[mylink] : 0;
                 const uint32_t av = path_available(dm, bm, hops, mylink, lane);
@@ -412,7 +446,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                 bool counted = false;
 #pragma unroll 1
                 for (int m = M - 1; m >= 0; --m) {
-                    const int n = t.need[rate * M + m];
+                    const int nd = __shfl_sync(FULL, mynd, m);
+                    const int n = nd & 0xff, ncls = nd >> 8;
                     const int L = n + 1;
                     if (L < a) { r = av; a = 1; }
                     while (a < L) {
@@ -425,13 +460,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                     const int fl = __ffs(any) - 1;
                     const uint32_t w = __shfl_sync(FULL, r, fl);
                     const int s = (fl << 5) + __ffs(w) - 1;
-                    const int ncls = t.cls[rate * M + m];
+                    const GnBase gb = gn_base(p, path, s, n, ncls);
+                    if (prunable && gb.empty() >= Tab::ACCHI(m)) {  // hopeless even in an empty network
+                        QCNT(QRMSA_CNT_GN_PRUNED, 1);
+                        blk_osnr = 1;
+                        blk_res = 0;
+                        continue;
+                    }
                     uint32_t terms = 0;
-                    const double acc = gn_inverse_gsnr(dm, p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
+                    const double acc = gb.with(gn_neighbours(dm, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
                     QCNT(QRMSA_CNT_GN_EVALS, 1);
                     QCNT(QRMSA_CNT_GN_TERMS, terms);
                     if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
-                    if (qot_ok(t, m, acc, flags)) {
+                    if (qot_ok(m, acc, flags)) {
                         found = true;
                         action = pi * M * S + ((M - 1) - m) * S + s;
                         acc_ok = acc;
@@ -441,7 +482,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                         flags |= QRMSA_FLAG_ACCEPTED;
                         accepted += 1;
                         QCNT(QRMSA_CNT_ACCEPTED, 1);
-                        QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate[rate]);
+                        QCNT(QRMSA_CNT_RATE_PROVISIONED, Tab::rate(rate));
                         QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
                         QCNT(QRMSA_CNT_MOD_HIST + m, 1);
                         break;
@@ -456,7 +497,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                 QCNT(QRMSA_CNT_BLOCKED_OSNR, blk_osnr);
             }
             QCNT(QRMSA_CNT_DECIDED, 1);
-            QCNT(QRMSA_CNT_RATE_REQUESTED, t.rate[rate]);
+            QCNT(QRMSA_CNT_RATE_REQUESTED, Tab::rate(rate));
             if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
             if (lane == 0) {
                 tr[cur].w = (uint32_t)action | flags;
@@ -464,7 +505,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
             }
             __syncwarp();
             uint32_t n_rel = 0;
-            if (advance_and_release(dm, p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+            if (advance_and_release(dm, p, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
         }
@@ -482,10 +523,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
     k_step_action(const KParams p, const long long *__restrict__ ext_action, float *__restrict__ o_reward,
                   uint8_t *__restrict__ o_status, double *__restrict__ o_gsnr, uint8_t *__restrict__ o_term,
                   const int episode_length) {
-    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
-    stage_tables(p, smem, &mbar);
-    const Tab t = make_tab(p, smem);
+    stage_tables(p, &mbar);
     const Dim<0, 0, 0> dm(p);
 
     const int lane = threadIdx.x & 31;
@@ -522,9 +561,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 const int rel = (a / p.S) % p.Mc;
                 const int pi = (a / (p.S * p.Mc)) % p.K;
                 const int m = (p.M - 1 > 1) ? (p.M - 1) - rel : (p.Mc - 1) - rel;  // qrmsa.pyx:821-829
-                const int n = t.need[rate * p.M + m];
+                const int n = Tab::need(rate * p.M + m);
                 const int path = (src * p.N + dst) * p.K + pi;
-                const int hops = __ldg(p.path_hops + path);
+                const int hops = __ldg(p.path_hops + path) & 0x7f;
                 const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
                 const int mycnt = lane < hops ? cnt[mylink] : 0;
                 // is_path_free (qrmsa.pyx:1248-1264): [s, s+n (+1 guard if it ends before S)) free on every link
@@ -542,11 +581,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                     const double proc = (double)(cur + 1);
                     reward = (float)(-3.0 * (1.0 + (proc - (double)accepted) / proc));
                 } else {
-                    const int ncls = t.cls[rate * p.M + m];
+                    const int ncls = Tab::cls(rate * p.M + m);
                     uint32_t terms = 0;
-                    const double acc = gn_inverse_gsnr(dm, p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms);
+                    const double acc = gn_base(p, path, s, n, ncls).with(
+                        gn_neighbours(dm, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
                     g = -10.0 * log10(acc);
-                    if (qot_ok(t, m, acc, flags)) {
+                    if (qot_ok(m, acc, flags)) {
                         const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                                              ((uint32_t)ncls << 23);
                         if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
@@ -555,7 +595,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                         status = QRMSA_STEP_ACCEPTED;
                         reward = 0.f;  // reward() falls off its end for accepted services (qrmsa.pyx:1266-1285)
                         QCNT(QRMSA_CNT_ACCEPTED, 1);
-                        QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate[rate]);
+                        QCNT(QRMSA_CNT_RATE_PROVISIONED, Tab::rate(rate));
                         QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
                         QCNT(QRMSA_CNT_MOD_HIST + m, 1);
                     } else {
@@ -567,7 +607,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
             if (consume) {
                 if (status == QRMSA_STEP_REJECT_ACTION) QCNT(QRMSA_CNT_REJECTED, 1);
                 QCNT(QRMSA_CNT_DECIDED, 1);
-                QCNT(QRMSA_CNT_RATE_REQUESTED, t.rate[rate]);
+                QCNT(QRMSA_CNT_RATE_REQUESTED, Tab::rate(rate));
                 if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
                 if (lane == 0) {
                     tr[cur].w = (uint32_t)(status == QRMSA_STEP_ACCEPTED ? (int)a64 : reject) | flags;
@@ -576,7 +616,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 __syncwarp();
                 Head head = load_head(p, tr, perm, rel_ptr);
                 uint32_t n_rel = 0;
-                if (advance_and_release(dm, p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+                if (advance_and_release(dm, p, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
                     err = ENV_ERR_RELEASE_NOT_FOUND;
                 QCNT(QRMSA_CNT_RELEASES, n_rel);
                 term = (cur + 1 == episode_length);  // episode_services_processed == episode_length (qrmsa.pyx:1056)
@@ -707,14 +747,12 @@ __global__ void k_gather_gsnr(const KParams p, const int first, const int count,
 // calculate_osnr for a hypothetical channel on one env (core/osnr.pyx:21-142); one warp.
 __global__ void k_probe_gsnr(const KParams p, const int env, const int src, const int dst, const int pi, const int s,
                              const int n, double *out) {
-    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
-    stage_tables(p, smem, &mbar);
-    const Tab t = make_tab(p, smem);
+    stage_tables(p, &mbar);
     const int lane = threadIdx.x & 31;
     if (threadIdx.x >= 32) return;
     const int path = (src * p.N + dst) * p.K + pi;
-    const int hops = __ldg(p.path_hops + path);
+    const int hops = __ldg(p.path_hops + path) & 0x7f;
     const uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
     const uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
     const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
@@ -722,11 +760,12 @@ __global__ void k_probe_gsnr(const KParams p, const int env, const int src, cons
     // class of n: search the class table through NEED/CLS
     int ncls = -1;
     for (int i = 0; i < p.R * p.M; ++i)
-        if (t.need[i] == n) ncls = t.cls[i];
+        if (Tab::need(i) == n) ncls = Tab::cls(i);
     double g = nan("");
     if (ncls >= 0 && hops > 0) {
         uint32_t terms = 0;
-        g = -10.0 * log10(gn_inverse_gsnr(Dim<0, 0, 0>(p), p, t, lists, path, hops, mylink, mycnt, s, n, ncls, lane, terms));
+        g = -10.0 * log10(gn_base(p, path, s, n, ncls).with(
+            gn_neighbours(Dim<0, 0, 0>(p), lists, hops, mylink, mycnt, 2 * s + n, lane, terms)));
     }
     if (lane == 0) *out = g;
 }

@@ -157,6 +157,7 @@ class Engine:
         row = c.sum(0) if group is None else c[group]
         d = {n: int(row[i]) for i, n in enumerate(_lib.COUNTER_NAMES)}
         d["mod_hist"] = row[16:24].copy()
+        d["gn_pruned"] = int(row[24])
         return d
 
     def counters_device_ptr(self) -> int:
