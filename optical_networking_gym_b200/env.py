@@ -1,0 +1,536 @@
+"""QRMSAEnv-compatible host API over the CUDA engine.
+
+Two classes:
+
+* `QRMSAEnv`  -- ONE environment with the reference's constructor, `reset(seed, options)`,
+  `step(action:int) -> (obs, reward, terminated, truncated, info)` and the attribute / method surface the
+  reference's heuristics read (reference envs/qrmsa.pyx:206-237, :427-504, :838-1065; heuristics/
+  heuristics.py:923-966).  State lives on the GPU (engine with n_envs = 1); helper methods pull it back.
+  This is the compatibility path: correct, not fast.
+* `BatchedQRMSAEnv` -- n_envs environments stepped together: `reset()`, `step(actions[n_envs])`,
+  `step_first_fit(n_steps)` (the fused heuristic + step of the benchmark loop,
+  examples/JOCN_Benchmark_2024/graph_load.py:161-163) and `action_masks()`.
+
+Request streams: env i replays `random.Random(base_seed + i)` exactly as the reference draws it
+(tracegen.py).  The reference seeds its generator from OS entropy (qrmsa.pyx:241) -- its `seed=` argument
+does not reach it -- so any seed reproduces *a* valid reference run; passing the same seed the oracle
+harness patches in reproduces *that* run bit for bit.
+
+Not implemented yet (SURVEY §8f "next" rows): `gen_observation=True` (observation features and the
+GSNR-validated action mask), `measure_disruptions`, `defragmentation`, `bands`; they raise.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .engine import Engine, unpack_bitmaps
+from .tables import StaticTables
+from .tracegen import TraceGenerator
+
+
+# --------------------------------------------------------------------------------------------------------
+# tiny stand-ins for gymnasium.spaces (gymnasium is optional; only `.n` / `.shape` / `sample` are used by the
+# reference's callers: heuristics.py `env.action_space.n - 1`, SB3 reads shape/dtype)
+# --------------------------------------------------------------------------------------------------------
+class Discrete:
+    def __init__(self, n: int, seed=None):
+        self.n = int(n)
+        self.shape = ()
+        self.dtype = np.int64
+        self._rng = np.random.default_rng(seed)
+
+    def sample(self):
+        return int(self._rng.integers(self.n))
+
+    def contains(self, x):
+        return 0 <= int(x) < self.n
+
+
+class Box:
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+
+class Service:
+    """Request + allocation record, same field names as the reference Service (qrmsa.pyx:29-116)."""
+
+    def __init__(self, service_id, source, source_id, destination, destination_id, arrival_time, holding_time,
+                 bit_rate):
+        self.service_id = int(service_id)
+        self.source = source
+        self.source_id = int(source_id)
+        self.destination = destination
+        self.destination_id = str(destination_id)      # a str in the reference (qrmsa.pyx:34,1146)
+        self.arrival_time = float(np.float32(arrival_time))
+        self.holding_time = float(np.float32(holding_time))
+        self.bit_rate = float(np.float32(bit_rate))
+        self.path = None
+        self.initial_slot = -1
+        self.number_slots = 0
+        self.center_frequency = 0.0
+        self.bandwidth = 0.0
+        self.launch_power = 0.0
+        self.current_modulation = None
+        self.accepted = False
+        self.blocked_due_to_resources = False
+        self.blocked_due_to_osnr = False
+        self.OSNR = self.ASE = self.NLI = 0.0
+
+    def __repr__(self):
+        return (f"Service(id={self.service_id}, {self.source}->{self.destination}, bit_rate={self.bit_rate}, "
+                f"arrival={self.arrival_time}, holding={self.holding_time})")
+
+
+def _unsupported(name):
+    raise NotImplementedError(f"{name} is not implemented in the B200 path yet (SURVEY §8f 'next' rows)")
+
+
+def _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, bit_rate_selection):
+    if measure_disruptions:
+        _unsupported("measure_disruptions=True")
+    if defragmentation:
+        _unsupported("defragmentation=True")
+    if bands:
+        _unsupported("bands (multiband)")
+    if gen_observation:
+        _unsupported("gen_observation=True (observation features + GSNR action mask)")
+    if bit_rate_selection != "discrete":
+        _unsupported("bit_rate_selection='continuous'")
+
+
+class _Common:
+    """Shared construction: static tables from a reference topology graph (or a StaticTables)."""
+
+    def _setup(self, topology, num_spectrum_resources, bit_rates, launch_power_dbm, margin, frequency_start,
+               frequency_slot_bandwidth, channel_width, k_paths, modulations_to_consider, bandwidth):
+        if isinstance(topology, StaticTables):
+            self.topology = None
+            self.tables = topology
+        else:
+            self.topology = topology
+            self.tables = StaticTables.from_topology(
+                topology, num_spectrum_resources=num_spectrum_resources, bit_rates=bit_rates,
+                launch_power_dbm=launch_power_dbm, margin=margin, frequency_start=frequency_start,
+                frequency_slot_bandwidth=frequency_slot_bandwidth, channel_width=channel_width, k_paths=k_paths,
+                modulations_to_consider=modulations_to_consider)
+        tb = self.tables
+        frequency_end = frequency_start + frequency_slot_bandwidth * tb.n_slots
+        assert math.isclose(frequency_end - frequency_start, bandwidth, rel_tol=1e-5), \
+            "bandwidth must equal num_spectrum_resources * frequency_slot_bandwidth (qrmsa.pyx:294-295)"
+        self.num_spectrum_resources = tb.n_slots
+        self.k_paths = tb.k_paths
+        self.modulations_to_consider = tb.mods_to_consider
+        self.max_modulation_idx = tb.n_mods - 1
+        self.bit_rates = tuple(bit_rates)
+        self.frequency_start = frequency_start
+        self.frequency_slot_bandwidth = frequency_slot_bandwidth
+        self.frequency_end = frequency_end
+        self.launch_power_dbm = launch_power_dbm
+        self.launch_power = tb.launch_power_w
+        self.margin = margin
+        self.channel_width = channel_width
+        self.action_space = Discrete(tb.n_actions)                                     # qrmsa.pyx:319-321
+        self.observation_space = Box(-5, 5, (1 + 2 + tb.k_paths + tb.k_paths * tb.mods_to_consider * 12,))  # :323-335
+        self.reject_action = self.action_space.n - 1
+        if self.topology is not None:
+            self.k_shortest_paths = self.topology.graph["ksp"]
+            self.modulations = self.topology.graph.get("modulations", [])
+            self._nodes = list(self.topology.graph["node_indices"])
+        else:
+            self.k_shortest_paths = None
+            self.modulations = None
+            self._nodes = list(tb.node_names) or [str(i) for i in range(tb.n_nodes)]
+
+
+# ========================================================================================================
+class QRMSAEnv(_Common):
+    """Single environment, drop-in for the reference `QRMSAEnv` (constructor: qrmsa.pyx:206-237)."""
+
+    def __init__(self, topology, num_spectrum_resources: int = 320, episode_length: int = 1000, load: float = 10.0,
+                 mean_service_holding_time: float = 10800.0, bit_rate_selection: str = "continuous",
+                 bit_rates: Sequence = (10, 40, 100), bit_rate_probabilities=None, node_request_probabilities=None,
+                 bit_rate_lower_bound: float = 25.0, bit_rate_higher_bound: float = 100.0,
+                 launch_power_dbm: float = 0.0, bandwidth: float = 4e12, frequency_start: float = (3e8 / 1565e-9),
+                 frequency_slot_bandwidth: float = 12.5e9, margin: float = 0.0, measure_disruptions: bool = False,
+                 seed=None, allow_rejection: bool = True, reset: bool = True, channel_width: float = 12.5,
+                 k_paths: int = 5, file_name: str = "", blocks_to_consider: int = 1, modulations_to_consider: int = 6,
+                 defragmentation: bool = False, n_defrag_services: int = 0, gen_observation: bool = True,
+                 bands=None, device: int = 0):
+        _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, bit_rate_selection)
+        if seed is not None and not isinstance(seed, (int, np.integer)):
+            raise ValueError("Seed must be an integer.")                       # qrmsa.pyx:342
+        if file_name:
+            _unsupported("per-service CSV (file_name)")
+        self._setup(topology, num_spectrum_resources, bit_rates, launch_power_dbm, margin, frequency_start,
+                    frequency_slot_bandwidth, channel_width, k_paths, modulations_to_consider, bandwidth)
+        self.episode_length = int(episode_length)
+        self.load = float(load)
+        self.mean_service_holding_time = float(mean_service_holding_time)
+        self.allow_rejection = allow_rejection
+        self.gen_observation = gen_observation
+        self.input_seed = int(seed) % (2 ** 31) if seed is not None else int.from_bytes(os.urandom(4), "little") >> 1
+        tb = self.tables
+        self._gen = TraceGenerator(1, tb.n_nodes, tb.n_rates, self.load, self.mean_service_holding_time,
+                                   base_seed=self.input_seed, node_request_probabilities=node_request_probabilities,
+                                   bit_rate_probabilities=bit_rate_probabilities, n_threads=1)
+        self._eng = Engine(tb, 1, max(self.episode_length, 2), device=device)
+        self._eng.enable_gsnr_log(True)
+        self._block = None
+        self._cur = 0
+        self.current_time = 0.0
+        self.current_service: Optional[Service] = None
+        # cumulative counters (qrmsa.pyx:152-159) and per-episode ones
+        self.services_processed = self.services_accepted = 0
+        self.episode_services_processed = self.episode_services_accepted = 0
+        self.bit_rate_requested = self.bit_rate_provisioned = 0.0
+        self.episode_bit_rate_requested = self.episode_bit_rate_provisioned = 0.0
+        self.bl_resource = self.bl_osnr = self.bl_reject = 0
+        self.episode_modulation_histogram = {}
+        import torch
+
+        self._dev = torch.device("cuda", device)
+        self._t_action = torch.zeros(1, dtype=torch.int64, device=self._dev)
+        self._t_reward = torch.zeros(1, dtype=torch.float32, device=self._dev)
+        self._t_status = torch.zeros(1, dtype=torch.uint8, device=self._dev)
+        self._t_gsnr = torch.zeros(1, dtype=torch.float64, device=self._dev)
+        self._t_term = torch.zeros(1, dtype=torch.uint8, device=self._dev)
+        if reset:
+            self.reset()
+
+    # ------------------------------------------------------------------ gym API
+    def _observation(self):
+        obs = np.zeros((self.observation_space.shape[0],), dtype=np.float32)   # gen_observation=False, :584-587
+        return obs, {"mask": np.zeros((self.action_space.n,), dtype=np.uint8)}
+
+    def _service_from_block(self, i: int) -> Service:
+        b = self._block
+        src, dst = int(b[0][i]), int(b[1][i])
+        return Service(service_id=i, source=self._nodes[src], source_id=src, destination=self._nodes[dst],
+                       destination_id=dst, arrival_time=b[3][i], holding_time=b[4][i],
+                       bit_rate=self.bit_rates[int(b[2][i])])
+
+    def _account_new_service(self):
+        svc = self.current_service
+        self.current_time = svc.arrival_time
+        self.services_processed += 1
+        self.episode_services_processed += 1
+        self.bit_rate_requested += svc.bit_rate
+        self.episode_bit_rate_requested += svc.bit_rate
+
+    def reset(self, seed=None, options=None):
+        """qrmsa.pyx:427-504.  Wipes the network, keeps the clock and the request stream running."""
+        if options is not None and options.get("only_episode_counters"):
+            _unsupported("reset(options={'only_episode_counters': True})")
+        L = self.episode_length
+        if self._block is None:
+            leftover = [np.zeros(0, a) for a in (np.uint8, np.uint8, np.uint8, np.float32, np.float32)]
+        else:  # requests generated but never made current keep their place in the stream
+            leftover = [a[self._cur + 1:] for a in self._block]
+        need = L - len(leftover[0])
+        fresh = [a[:, 0] for a in self._gen.next(max(need, 0))]
+        self._block = [np.concatenate([lo, fr])[:L] for lo, fr in zip(leftover, fresh)]
+        self._eng.reset()
+        self._eng.load_trace_host(*[np.ascontiguousarray(a[:, None]) for a in self._block])
+        self._cur = 0
+        self.episode_services_processed = self.episode_services_accepted = 0
+        self.episode_bit_rate_requested = self.episode_bit_rate_provisioned = 0.0
+        self.bit_rate_requested = self.bit_rate_provisioned = 0.0            # :466-467 (full reset)
+        self.bl_resource = self.bl_osnr = self.bl_reject = 0
+        self.episode_modulation_histogram = {int(se): 0 for se in self.tables.mod_se}
+        self.current_service = self._service_from_block(0)
+        self._account_new_service()
+        obs, mask = self._observation()
+        return obs, mask.copy()
+
+    def step(self, action: int):
+        """qrmsa.pyx:838-1065."""
+        import torch
+
+        tb = self.tables
+        svc = self.current_service
+        svc.blocked_due_to_resources = svc.blocked_due_to_osnr = False
+        self._t_action[0] = int(action)
+        self._eng.step_action(self._t_action, self._t_reward, self._t_status, self._t_gsnr, self._t_term)
+        torch.cuda.current_stream().synchronize()
+        status = int(self._t_status[0])
+        reward = float(self._t_reward[0])
+        gsnr = float(self._t_gsnr[0])
+        if status == _lib.STEP_IDLE:
+            raise RuntimeError("step() called after the episode terminated; call reset()")
+        route = modulation_idx = initial_slot = -1
+        osnr_req = 0.0
+        if action != self.reject_action:
+            initial_slot, modulation_idx, route = self.encoded_decimal_to_array(int(action))[::-1]
+            osnr_req = float(tb.mod_min_osnr[modulation_idx]) + self.margin
+        if status == _lib.STEP_NOT_FREE:                                      # :886-897: request not consumed
+            svc.blocked_due_to_resources, svc.accepted = True, False
+            obs, mask = self._observation()
+            info = {"blocked_due_to_resources": 1, "blocked_due_to_osnr": 0, "rejected": 1}
+            info.update(mask)
+            return obs, reward, False, False, info
+        if status == _lib.STEP_LOW_GSNR:                                      # :925-929
+            raise ValueError(f"Osnr {gsnr} is not enough for service {svc.service_id} with modulation index "
+                             f"{modulation_idx}, and osnr_req {osnr_req}.")
+        if status == _lib.STEP_ACCEPTED:
+            n = int(tb.slots_needed[int(self._block[2][self._cur]) * tb.n_mods + modulation_idx])
+            svc.accepted = True
+            svc.OSNR = gsnr
+            svc.initial_slot, svc.number_slots = initial_slot, n
+            svc.center_frequency = (self.frequency_start + (self.frequency_slot_bandwidth * initial_slot)
+                                    + (self.frequency_slot_bandwidth * (n / 2.0)))
+            svc.bandwidth = self.frequency_slot_bandwidth * n
+            svc.launch_power = self.launch_power
+            if self.k_shortest_paths is not None:
+                svc.path = self.k_shortest_paths[svc.source, svc.destination][route]
+                svc.current_modulation = self.modulations[modulation_idx]
+            self.services_accepted += 1
+            self.episode_services_accepted += 1
+            self.bit_rate_provisioned += svc.bit_rate
+            self.episode_bit_rate_provisioned = float(int(self.episode_bit_rate_provisioned + svc.bit_rate))  # :1319
+            self.episode_modulation_histogram[int(tb.mod_se[modulation_idx])] += 1
+        else:
+            svc.accepted = False
+            self.bl_reject += 1
+        info = {
+            "episode_services_accepted": self.episode_services_accepted,
+            "service_blocking_rate": 0.0, "episode_service_blocking_rate": 0.0,
+            "bit_rate_blocking_rate": 0.0, "episode_bit_rate_blocking_rate": 0.0,
+            "disrupted_services": 0.0, "episode_disrupted_services": 0.0,
+            "osnr": gsnr if status == _lib.STEP_ACCEPTED else 0.0, "osnr_req": osnr_req,
+            "chosen_path_index": route, "chosen_slot": initial_slot,
+            "episode_defrag_cicles": 0, "episode_service_realocations": 0,
+        }
+        if self.services_processed > 0:
+            info["service_blocking_rate"] = float(self.services_processed - self.services_accepted) / self.services_processed
+        if self.episode_services_processed > 0:
+            info["episode_service_blocking_rate"] = (float(self.episode_services_processed - self.episode_services_accepted)
+                                                     / float(self.episode_services_processed))
+        if self.bit_rate_requested > 0:
+            info["bit_rate_blocking_rate"] = float(self.bit_rate_requested - self.bit_rate_provisioned) / self.bit_rate_requested
+        if self.episode_bit_rate_requested > 0:
+            info["episode_bit_rate_blocking_rate"] = (float(self.episode_bit_rate_requested - self.episode_bit_rate_provisioned)
+                                                      / self.episode_bit_rate_requested)
+        for se in self.tables.mod_se:
+            info["modulation_{}".format(str(float(se)))] = self.episode_modulation_histogram.get(int(se), 0)
+        # next request (qrmsa.pyx:1052-1054)
+        self._cur += 1
+        self.current_service = self._service_from_block(self._cur)
+        self._account_new_service()
+        terminated = self.episode_services_processed == self.episode_length
+        assert terminated == bool(self._t_term[0])
+        if terminated:
+            info["blocked_due_to_resources"] = self.bl_resource
+            info["blocked_due_to_osnr"] = self.bl_osnr
+            info["rejected"] = self.bl_reject
+        obs, mask = self._observation()
+        info.update(mask)
+        return obs, reward, terminated, False, info
+
+    # ------------------------------------------------------------------ heuristics' call surface
+    def encoded_decimal_to_array(self, decimal: int, max_values=None):
+        """qrmsa.pyx:801-834 -> [route, modulation index, initial slot]."""
+        if max_values is None:
+            max_values = [self.k_paths, self.modulations_to_consider, self.num_spectrum_resources]
+        arr = []
+        for mv in reversed(max_values):
+            arr.insert(0, decimal % mv)
+            decimal //= mv
+        if self.max_modulation_idx > 1:
+            allowed = list(range(self.max_modulation_idx, self.max_modulation_idx - self.modulations_to_consider, -1))
+        else:
+            allowed = list(reversed(range(0, self.modulations_to_consider)))
+        arr[1] = allowed[arr[1]]
+        return arr
+
+    def get_number_slots(self, service, modulation) -> int:
+        """qrmsa.pyx:1198-1205 (bands=None)."""
+        return int(math.ceil(service.bit_rate / (modulation.spectral_efficiency * self.channel_width)))
+
+    def _path_link_indices(self, path):
+        nl = path.node_list
+        return [int(self.topology[nl[i]][nl[i + 1]]["index"]) for i in range(len(nl) - 1)]
+
+    def available_slots_matrix(self) -> np.ndarray:
+        """topology.graph['available_slots'] equivalent: int32 [E][S], 1 = free."""
+        return self._eng.export_slots(0)
+
+    def get_available_slots(self, path) -> np.ndarray:
+        """qrmsa.pyx:1482-1512."""
+        m = self.available_slots_matrix()
+        out = m[self._path_link_indices(path)[0]].copy()
+        for l in self._path_link_indices(path)[1:]:
+            out *= m[l]
+        return out
+
+    def _get_spectrum_slots(self, path_idx: int):
+        """qrmsa.pyx:1533-1542."""
+        m = self.available_slots_matrix()
+        svc = self.current_service
+        return [m[l] for l in self._path_link_indices(self.k_shortest_paths[svc.source, svc.destination][path_idx])]
+
+    def _get_candidates(self, available_slots, num_slots_required: int, total_slots: int):
+        """qrmsa.pyx:515-541: valid start slots under the guard-band rule."""
+        av = np.asarray(available_slots).astype(np.int8)
+        edges = np.flatnonzero(np.diff(np.concatenate([[0], av, [0]])))
+        out = []
+        for start, end in zip(edges[::2], edges[1::2]):
+            length = end - start
+            if start + length == total_slots:
+                if length >= num_slots_required:
+                    out.extend(range(start, start + length - num_slots_required + 1))
+            elif length >= num_slots_required + 1:
+                out.extend(range(start, start + length - (num_slots_required + 1) + 1))
+        return [int(x) for x in out]
+
+    def is_path_free(self, path, initial_slot: int, number_slots: int) -> bool:
+        """qrmsa.pyx:1248-1264."""
+        end = initial_slot + number_slots
+        if end > self.num_spectrum_resources:
+            return False
+        if end < self.num_spectrum_resources:
+            end += 1
+        m = self.available_slots_matrix()
+        return all(not np.any(m[l, initial_slot:end] == 0) for l in self._path_link_indices(path))
+
+    def running_services_on_link(self, link_index: int) -> np.ndarray:
+        """Channels on a link as rows (initial_slot, number_slots, modulation index)."""
+        return self._eng.export_link_list(0, link_index)
+
+    def calculate_osnr(self, service):
+        """core.osnr.calculate_osnr(env, service) for the candidate written on `service` (path, initial_slot,
+        number_slots); returns (gsnr_dB, None, None) -- ASE-only / NLI-only figures are not produced."""
+        svc = self.current_service
+        paths = self.k_shortest_paths[svc.source, svc.destination]
+        p = next(i for i, pth in enumerate(paths) if pth is service.path)
+        g = self._eng.probe_gsnr(0, svc.source_id, int(svc.destination_id), p, service.initial_slot,
+                                 service.number_slots)
+        return g, None, None
+
+    def close(self):
+        self._eng.close()
+        self._gen.close()
+
+
+def calculate_osnr(env, service):
+    """Module-level form used by the reference heuristics: `calculate_osnr(env, service)` (osnr.pyx:21)."""
+    while not isinstance(env, QRMSAEnv) and hasattr(env, "env"):
+        env = env.env
+    return env.calculate_osnr(service)
+
+
+# ========================================================================================================
+class BatchedQRMSAEnv(_Common):
+    """n_envs environments on one GPU, stepped together.  Env i replays random.Random(base_seed + i);
+    `load` may be a scalar or one value per env (load sweeps: set n_groups for per-load counters)."""
+
+    def __init__(self, topology, n_envs: int, num_spectrum_resources: int = 320, episode_length: int = 1000,
+                 load=10.0, mean_service_holding_time: float = 10800.0, bit_rate_selection: str = "discrete",
+                 bit_rates: Sequence = (10, 40, 100), bit_rate_probabilities=None, node_request_probabilities=None,
+                 launch_power_dbm: float = 0.0, bandwidth: float = 4e12, frequency_start: float = (3e8 / 1565e-9),
+                 frequency_slot_bandwidth: float = 12.5e9, margin: float = 0.0, measure_disruptions: bool = False,
+                 seed: int = 50, allow_rejection: bool = True, reset: bool = True, channel_width: float = 12.5,
+                 k_paths: int = 5, modulations_to_consider: int = 6, defragmentation: bool = False,
+                 gen_observation: bool = False, bands=None, device: int = 0, n_groups: int = 1, n_threads: int = 0):
+        _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, bit_rate_selection)
+        self._setup(topology, num_spectrum_resources, bit_rates, launch_power_dbm, margin, frequency_start,
+                    frequency_slot_bandwidth, channel_width, k_paths, modulations_to_consider, bandwidth)
+        import torch
+
+        self.n_envs = int(n_envs)
+        self.episode_length = int(episode_length)
+        self.base_seed = int(seed)
+        tb = self.tables
+        self._gen = TraceGenerator(self.n_envs, tb.n_nodes, tb.n_rates, load, mean_service_holding_time,
+                                   base_seed=self.base_seed, node_request_probabilities=node_request_probabilities,
+                                   bit_rate_probabilities=bit_rate_probabilities, n_threads=n_threads)
+        self._eng = Engine(tb, self.n_envs, max(self.episode_length, 2), device=device)
+        if n_groups > 1:
+            self._eng.set_groups(n_groups)
+        self._dev = torch.device("cuda", device)
+        shape = (self.episode_length, self.n_envs)
+        self._pinned = [torch.empty(shape, dtype=dt, pin_memory=True) for dt in
+                        (torch.uint8, torch.uint8, torch.uint8, torch.float32, torch.float32)]
+        self._trace = [p.numpy() for p in self._pinned]
+        self._reward = torch.zeros(self.n_envs, dtype=torch.float32, device=self._dev)
+        self._status = torch.zeros(self.n_envs, dtype=torch.uint8, device=self._dev)
+        self._gsnr = torch.zeros(self.n_envs, dtype=torch.float64, device=self._dev)
+        self._term = torch.zeros(self.n_envs, dtype=torch.uint8, device=self._dev)
+        self._obs = torch.zeros((self.n_envs, self.observation_space.shape[0]), dtype=torch.float32, device=self._dev)
+        self.steps_done = 0
+        if reset:
+            self.reset()
+
+    @property
+    def engine(self) -> Engine:
+        return self._eng
+
+    def reset(self, seed=None, options=None):
+        """Every env: network wiped, next `episode_length` requests of its stream attached (qrmsa.pyx:427-504)."""
+        self._gen.next(self.episode_length, out=self._trace)
+        self._eng.reset()
+        self._eng.load_trace_host(*self._trace)
+        self.steps_done = 0
+        return self._obs, {"mask": None}
+
+    def current_requests(self):
+        """(src, dst, rate index, arrival, holding) host arrays of the episode, [episode_length, n_envs]."""
+        return self._trace
+
+    def step(self, actions):
+        """actions: int64 CUDA tensor [n_envs] -> (obs, reward, terminated, truncated, info) of device tensors."""
+        self._eng.step_action(actions, self._reward, self._status, self._gsnr, self._term)
+        self.steps_done += 1
+        info = {"status": self._status, "osnr": self._gsnr, "mask": None}
+        return self._obs, self._reward, self._term.bool(), self._term.bool() & False, info
+
+    def step_first_fit(self, n_steps: int = 1):
+        """n_steps of `heuristic_shortest_available_path_first_fit_best_modulation` + `env.step` per env."""
+        n_steps = min(int(n_steps), self.episode_length - 1 - self.steps_done)
+        self._eng.step_first_fit(n_steps)
+        self.steps_done += n_steps
+        return n_steps
+
+    @property
+    def terminated(self) -> bool:
+        return self.steps_done >= self.episode_length - 1
+
+    def action_masks(self):
+        _unsupported("action_masks() with GSNR validation (gen_observation=True)")
+
+    def actions(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Decided action indices [count, n_envs] (reject = k*M*S) and near-threshold flags."""
+        count = self.steps_done - first if count is None else count
+        w = self._eng.actions_host(first, count)
+        return (w & _lib.ACTION_MASK).astype(np.int64), (w.view(np.uint32) & _lib.FLAG_NEAR_THRESHOLD) != 0
+
+    def counters(self, group: Optional[int] = None) -> dict:
+        return self._eng.counters_dict(group)
+
+    def episode_info(self, group: Optional[int] = None) -> dict:
+        """Blocking statistics in the reference's `info` vocabulary (qrmsa.pyx:996-1050), aggregated."""
+        c = self.counters(group)
+        dec = max(c["decided"], 1)
+        req = max(c["rate_requested_milli"], 1)
+        return {
+            "episode_services_processed": c["decided"], "episode_services_accepted": c["accepted"],
+            "episode_service_blocking_rate": (c["decided"] - c["accepted"]) / dec,
+            "episode_bit_rate_blocking_rate": (c["rate_requested_milli"] - c["rate_provisioned_milli"]) / req,
+            "rejected": c["rejected"], "near_threshold_decisions": c["near_threshold"],
+            **{f"modulation_{float(se)}": int(c["mod_hist"][i]) for i, se in enumerate(self.tables.mod_se)},
+        }
+
+    def available_slots(self, env: int) -> np.ndarray:
+        return self._eng.export_slots(env)
+
+    def bitmaps(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n_envs - first if count is None else count
+        return unpack_bitmaps(self._eng.export_bitmaps(first, count), self.tables.n_slots)
+
+    def close(self):
+        self._eng.close()
+        self._gen.close()

@@ -1,0 +1,61 @@
+"""Python-level heuristics written against the QRMSAEnv call surface (single-env compatibility path).
+
+Same names, arguments and return convention `(action, blocked_due_to_resources, blocked_due_to_osnr)` as
+reference heuristics/heuristics.py:36-54 and :923-966.  The batched fast path does not go through here:
+`BatchedQRMSAEnv.step_first_fit` runs the same policy fused with the step inside one CUDA kernel; this
+module exists so that user-written Python heuristics (which read `get_available_slots`, `_get_candidates`,
+`get_number_slots`, `calculate_osnr`) keep working when the env is switched to the B200 one.
+"""
+from __future__ import annotations
+
+from .env import QRMSAEnv, calculate_osnr
+
+
+def get_qrmsa_env(env) -> QRMSAEnv:
+    """Unwrap `.env` chains down to the QRMSAEnv (heuristics.py:15-33)."""
+    while not isinstance(env, QRMSAEnv):
+        if not hasattr(env, "env"):
+            raise ValueError("no QRMSAEnv found in the wrapper chain")
+        env = env.env
+    return env
+
+
+def get_action_index(env: QRMSAEnv, path_index: int, modulation_index: int, initial_slot: int) -> int:
+    """(path, absolute modulation index, slot) -> action (heuristics.py:36-54)."""
+    relative = env.max_modulation_idx - modulation_index
+    return (path_index * env.modulations_to_consider * env.num_spectrum_resources
+            + relative * env.num_spectrum_resources + initial_slot)
+
+
+def heuristic_shortest_available_path_first_fit_best_modulation(env):
+    """Shortest path first, most efficient modulation first, first-fit slot, accept on GSNR >= threshold
+    (heuristics.py:923-966)."""
+    sim = get_qrmsa_env(env)
+    svc = sim.current_service
+    blocked_resources = blocked_osnr = False
+    for path_idx, path in enumerate(sim.k_shortest_paths[svc.source, svc.destination]):
+        available = sim.get_available_slots(path)
+        for modulation_idx in range(sim.max_modulation_idx, -1, -1):
+            modulation = sim.modulations[modulation_idx]
+            n = sim.get_number_slots(svc, modulation)
+            if n <= 0:
+                continue
+            starts = sim._get_candidates(available, n, sim.num_spectrum_resources)
+            if not starts:
+                blocked_resources = True
+                continue
+            svc.path, svc.initial_slot, svc.number_slots, svc.current_modulation = path, starts[0], n, modulation
+            svc.center_frequency = (sim.frequency_start + (sim.frequency_slot_bandwidth * starts[0])
+                                    + (sim.frequency_slot_bandwidth * (n / 2)))
+            svc.bandwidth = sim.frequency_slot_bandwidth * n
+            svc.launch_power = sim.launch_power
+            osnr, _, _ = calculate_osnr(sim, svc)
+            if osnr >= modulation.minimum_osnr + sim.margin:
+                return get_action_index(sim, path_idx, modulation_idx, starts[0]), False, False
+            blocked_osnr = True
+            blocked_resources = False
+    return sim.action_space.n - 1, blocked_resources, blocked_osnr
+
+
+# identical decisions in the reference (heuristics.py:431-490)
+shortest_available_path_lowest_spectrum_best_modulation = heuristic_shortest_available_path_first_fit_best_modulation

@@ -1,0 +1,146 @@
+"""BASELINE-size runs (65,536 envs, nobel-eu/320) checked through size-independent properties:
+bitmap <-> channel-list consistency, chunking invariance, drain-to-empty, counter identities, and a
+sampled subset against the oracle."""
+import numpy as np
+import pytest
+
+from helpers import compare_decisions, load_tables
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+N_ENVS, N_REQ = 65536, 321
+
+
+def _trace(n_envs, n_req, seed=50, load=300.0, tb=None):
+    from optical_networking_gym_b200.tracegen import TraceGenerator
+
+    return TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, load, base_seed=seed).next(n_req)
+
+
+def _occupancy_from_lists(eng, tb, env):
+    S = tb.n_slots
+    occ = np.ones((tb.n_links, S), np.uint8)
+    for l in range(tb.n_links):
+        for s, n, m in eng.export_link_list(env, l):
+            e = min(s + n + 1, S)
+            assert occ[l, s:e].all(), "two channels overlap (guard slot included)"
+            occ[l, s:e] = 0
+    return occ
+
+
+def test_full_size_properties():
+    from optical_networking_gym_b200 import _lib
+    from optical_networking_gym_b200.engine import Engine, unpack_bitmaps
+
+    tb = load_tables("nobel-eu", 320)
+    tr = _trace(N_ENVS, N_REQ, tb=tb)
+    eng = Engine(tb, N_ENVS, N_REQ)
+    eng.reset(); eng.load_trace_host(*tr)
+    eng.step_first_fit(N_REQ - 1)
+    c = eng.counters_dict()
+    assert c["decided"] == N_ENVS * (N_REQ - 1) and c["errors"] == 0
+    assert c["accepted"] + c["rejected"] == c["decided"]
+    assert int(c["mod_hist"].sum()) == c["accepted"]
+    assert c["releases"] <= c["accepted"]
+    st = eng.env_state()
+    assert (st[:, 0] == N_REQ - 1).all() and (st[:, 3] == 0).all() and int(st[:, 1].sum()) == c["accepted"]
+    words = eng.actions_host(0, N_REQ - 1).view(np.uint32)
+    assert ((words & _lib.FLAG_DECIDED) != 0).all()
+    assert int(((words & _lib.FLAG_ACCEPTED) != 0).sum()) == c["accepted"]
+    reject = tb.n_actions - 1
+    assert (((words & _lib.ACTION_MASK) == reject) == ((words & _lib.FLAG_ACCEPTED) == 0)).all()
+    # sampled envs: bitmaps equal the occupancy implied by the channel lists, and equal the oracle
+    sample = [0, 1, 31, 32, 4095, 32768, 65535]
+    acts = (words & _lib.ACTION_MASK).astype(np.int64)
+    flagged = (words & _lib.FLAG_NEAR_THRESHOLD) != 0
+    ref = []
+    for e in sample:
+        bm = unpack_bitmaps(eng.export_bitmaps(e, 1), tb.n_slots)[0]
+        assert np.array_equal(bm, _occupancy_from_lists(eng, tb, e)), f"env {e}"
+        o = orc.OracleEnv(tb, N_REQ)
+        o.reset(*[a[:, e] for a in tr])
+        r = o.run_first_fit(N_REQ - 1, log_qot=False)
+        ref.append(r["action"])
+        if np.array_equal(r["action"], acts[:, e]):
+            assert np.array_equal(o.slots(), bm)
+    compare_decisions(acts[:, sample].T, np.array(ref), flagged[:, sample].T, "full-size sample")
+    eng.close()
+
+
+def test_chunking_invariance_and_determinism():
+    """One launch of N steps == many launches of uneven chunks == a second run (bit-identical state)."""
+    from optical_networking_gym_b200.engine import Engine
+
+    tb = load_tables("nobel-eu", 320)
+    n_envs, n_req = 4096, 201
+    tr = _trace(n_envs, n_req, seed=7, tb=tb)
+    outs = []
+    for chunks in ([n_req - 1], [1, 7, 64, 128], [50, 50, 50, 50]):
+        eng = Engine(tb, n_envs, n_req)
+        eng.reset(); eng.load_trace_host(*tr)
+        for ch in chunks:
+            eng.step_first_fit(ch)
+        outs.append((eng.actions_host(0, n_req - 1), eng.export_bitmaps(0, n_envs), eng.counters()))
+        eng.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        assert np.array_equal(o[2][:, :6], outs[0][2][:, :6])
+
+
+def test_drain_to_empty_network():
+    """If the last request arrives after every release time, the network must be all-free and every
+    channel list empty (encode -> release round trip)."""
+    from optical_networking_gym_b200.engine import Engine
+
+    tb = load_tables("nobel-eu", 320)
+    n_envs, n_req = 2048, 150
+    src, dst, rate, arr, hold = [a.copy() for a in _trace(n_envs, n_req, seed=11, tb=tb)]
+    arr[-1] = np.float32(3e9)          # far beyond any arrival + holding
+    eng = Engine(tb, n_envs, n_req)
+    eng.reset(); eng.load_trace_host(src, dst, rate, arr, hold)
+    eng.step_first_fit(n_req - 1)
+    c = eng.counters_dict()
+    assert c["releases"] == c["accepted"] and c["errors"] == 0
+    bm = eng.export_bitmaps(0, n_envs)
+    full = np.full(10, 0xFFFFFFFF, np.uint32)
+    assert (bm == full).all()
+    for e in (0, 777, 2047):
+        for l in range(tb.n_links):
+            assert len(eng.export_link_list(e, l)) == 0
+    eng.close()
+
+
+def test_groups_and_load_sweep_counters():
+    """Per-load-point counters (JOCN-style sweep): blocking grows with load; groups sum to the total."""
+    from optical_networking_gym_b200.engine import Engine
+    from optical_networking_gym_b200.tracegen import TraceGenerator
+
+    tb = load_tables("nobel-eu", 320)
+    loads = np.repeat([100.0, 300.0, 500.0, 700.0], 256)
+    n_envs, n_req = len(loads), 1000
+    tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, loads, base_seed=5).next(n_req)
+    eng = Engine(tb, n_envs, n_req)
+    eng.set_groups(4)
+    eng.reset(); eng.load_trace_host(*tr)
+    eng.step_first_fit(n_req - 1)
+    c = eng.counters()
+    assert c.shape == (4, 32) and (c[:, 0] == 256 * (n_req - 1)).all()
+    blocking = (c[:, 0] - c[:, 1]) / c[:, 0]
+    assert (np.diff(blocking) > 0).all() and blocking[0] < 0.03 and blocking[-1] > 0.05
+    eng.close()
+
+
+def test_unsupported_configurations_fail_loudly():
+    from optical_networking_gym_b200.engine import Engine, QRMSAError
+
+    tb = load_tables("ring4", 320)
+    with pytest.raises(QRMSAError, match="max_requests"):
+        Engine(tb, 4, 20000)
+    bad = tb.replace(link_alpha=tb.link_alpha * np.linspace(1.0, 1.1, tb.n_links))
+    with pytest.raises(QRMSAError, match="attenuation"):
+        Engine(bad, 4, 16)
+    eng = Engine(tb, 4, 16)
+    with pytest.raises(QRMSAError, match="no trace loaded"):
+        eng.step_first_fit(1)
+    eng.close()

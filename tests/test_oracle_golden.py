@@ -1,0 +1,99 @@
+"""The oracle (oracle/qrmsa_oracle.c) against every golden vector recorded from the compiled reference.
+CPU only.  Bar: bit-exact actions / accept flags / slot matrices, GSNR to 1e-9 dB."""
+import numpy as np
+import pytest
+
+from helpers import TRACE_KEYS, load_golden, load_tables, parse_tag
+from oracle import oracle as orc
+
+SINGLE = ["run_nobel-eu_320_l300_s50", "run_nsfnet_320_l300_s50", "run_germany50_640_l800_s52",
+          "run_nobel-eu_320_l500_s7", "run_ring4_320_l60_s3"]
+MULTI = ["multi_nobel-eu_320_l300_b50", "multi_germany50_640_l800_b50"]
+
+
+@pytest.mark.parametrize("tag", SINGLE)
+def test_oracle_single(tag):
+    topo, S = parse_tag(tag)
+    tb, g = load_tables(topo, S), load_golden(tag)
+    n = len(g["action"])
+    o = orc.OracleEnv(tb, n + 1)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    done = 0
+    acts, gs = [], []
+    for step, snap in zip(g["snap_steps"], g["snap_slots"]):
+        r = o.run_first_fit(int(step) - done, log_qot=False)
+        acts.append(r["action"]); gs.append(r["gsnr"])
+        done = int(step)
+        assert np.array_equal(o.slots(), np.unpackbits(snap, axis=1)[:, :S]), f"snapshot {step}"
+    r = o.run_first_fit(n - done, log_qot=False)
+    acts.append(r["action"]); gs.append(r["gsnr"])
+    assert np.array_equal(np.concatenate(acts), g["action"])
+    assert np.abs(np.concatenate(gs) - g["gsnr"]).max() < 1e-9
+    assert np.array_equal(o.slots(), g["final_slots"])
+    c = o.counters()
+    assert c["accepted"] == int(g["accepted"].sum()) and c["ep_processed"] == n + 1
+
+
+def test_oracle_qot_log_matches_reference():
+    tag = "run_nobel-eu_320_l500_s7"
+    topo, S = parse_tag(tag)
+    tb, g = load_tables(topo, S), load_golden(tag)
+    n = len(g["action"])
+    o = orc.OracleEnv(tb, n + 1)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    r = o.run_first_fit(n, log_qot=True)
+    assert np.array_equal(r["qot_step"], g["qot_step"])
+    assert np.array_equal(r["qot_thr"], g["qot_thr"])
+    assert np.abs(r["qot_gsnr"] - g["qot_gsnr"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("tag", MULTI)
+def test_oracle_multi(tag):
+    topo, S = parse_tag(tag)
+    tb, g = load_tables(topo, S), load_golden(tag)
+    n_envs, n = g["action"].shape
+    ref_slots = np.unpackbits(g["final_slots"], axis=2)[:, :, :S]
+    for e in range(n_envs):
+        o = orc.OracleEnv(tb, n + 1)
+        o.reset(*[g[k][e] for k in TRACE_KEYS])
+        r = o.run_first_fit(n, log_qot=False)
+        assert np.array_equal(r["action"], g["action"][e]), f"env {e}"
+        assert np.array_equal(o.slots(), ref_slots[e])
+        assert np.abs(r["gsnr"] - g["gsnr"][e]).max() < 1e-9
+
+
+def test_oracle_step_action_vs_reference():
+    """env.step() with external actions: accepted / reject / not-free (request not consumed) / low GSNR (raise)."""
+    g = load_golden("rl_nsfnet_320_l210_s11")
+    tb = load_tables("nsfnet", 320)
+    n_req = len(g["src"])
+    o = orc.OracleEnv(tb, n_req)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    for i, (a, st, rw, gs) in enumerate(zip(g["action"], g["status"], g["reward"], g["gsnr"])):
+        status, reward, gsnr, term = o.step_action(int(a), n_req)
+        assert status == st, f"call {i}: status {status} != {st}"
+        if st != 3:
+            assert reward == pytest.approx(rw, abs=1e-12)
+        if st == 0:
+            assert gsnr == pytest.approx(gs, abs=1e-9)
+        assert term == bool(g["term"][i])
+    assert np.array_equal(o.slots(), g["final_slots"])
+
+
+def test_oracle_edge_cases():
+    tb = load_tables("ring4", 320)
+    # a single request: no step possible (a step needs the following request)
+    o = orc.OracleEnv(tb, 1)
+    o.reset(np.array([0], np.uint8), np.array([1], np.uint8), np.array([0], np.uint8),
+            np.array([1.0], np.float32), np.array([5.0], np.float32))
+    with pytest.raises(RuntimeError):
+        o.run_first_fit(1)
+    # zero holding time: released at the next arrival, network returns to all-free
+    n = 50
+    src = np.zeros(n, np.uint8); dst = np.full(n, 2, np.uint8); rate = np.full(n, 4, np.uint8)
+    arr = np.arange(1, n + 1, dtype=np.float32); hold = np.zeros(n, np.float32)
+    o = orc.OracleEnv(tb, n)
+    o.reset(src, dst, rate, arr, hold)
+    r = o.run_first_fit(n - 1)
+    assert r["accepted"].all() and (r["action"] == r["action"][0]).all()
+    assert o.slots().all()

@@ -1,0 +1,58 @@
+"""Host request generator (csrc/tracegen.cpp) vs traces recorded from the compiled reference and vs CPython's
+own `random` driven in the reference's draw order (oracle.generate_trace_python).  CPU only."""
+import numpy as np
+import pytest
+
+from helpers import TRACE_KEYS, load_golden, load_tables, parse_tag
+from oracle import oracle as orc
+from optical_networking_gym_b200.tracegen import TraceGenerator
+
+
+@pytest.mark.parametrize("tag", ["run_nobel-eu_320_l300_s50", "run_nsfnet_320_l300_s50", "run_germany50_640_l800_s52",
+                                 "run_nobel-eu_320_l500_s7", "run_ring4_320_l60_s3"])
+def test_single_stream_vs_reference(tag):
+    topo, S = parse_tag(tag)
+    tb, g = load_tables(topo, S), load_golden(tag)
+    tg = TraceGenerator(1, tb.n_nodes, tb.n_rates, float(g["meta_load"]), base_seed=int(g["meta_seed"]))
+    n = len(g["src"])
+    a = tg.next(n // 3)
+    b = tg.next(n - n // 3)          # the clock and the MT state persist across calls
+    for i, k in enumerate(TRACE_KEYS):
+        assert np.array_equal(np.concatenate([a[i], b[i]])[:, 0], g[k]), k
+
+
+def test_batch_streams_vs_reference():
+    g = load_golden("multi_nobel-eu_320_l300_b50")
+    tb = load_tables("nobel-eu", 320)
+    n_envs, n = g["src"].shape
+    for threads in (1, 3):
+        tg = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, 300.0, base_seed=int(g["meta_seed"]), n_threads=threads)
+        out = tg.next(n)
+        for i, k in enumerate(TRACE_KEYS):
+            assert np.array_equal(out[i].T, g[k]), k
+
+
+@pytest.mark.parametrize("seed,load,nodes,rates", [(0, 10.0, 4, 3), (1, 777.5, 14, 5), (2 ** 31 - 1, 50.0, 50, 2),
+                                                    (2 ** 32 + 5, 300.0, 28, 5), (123456789012, 1.5, 7, 1)])
+def test_vs_cpython_random(seed, load, nodes, rates):
+    ref, _, _ = orc.generate_trace_python(nodes, rates, load, 10800.0, seed, 400)
+    out = TraceGenerator(1, nodes, rates, load, base_seed=seed).next(400)
+    for i, k in enumerate(TRACE_KEYS):
+        assert np.array_equal(out[i][:, 0], ref[k]), k
+
+
+def test_per_env_loads_and_seeds():
+    loads = np.array([100.0, 200.0, 300.0, 400.0])
+    out = TraceGenerator(4, 14, 5, loads, base_seed=9).next(100)
+    for e in range(4):
+        ref, _, _ = orc.generate_trace_python(14, 5, float(loads[e]), 10800.0, 9 + e, 100)
+        for i, k in enumerate(TRACE_KEYS):
+            assert np.array_equal(out[i][:, e], ref[k])
+
+
+def test_properties():
+    out = TraceGenerator(8, 28, 5, 300.0, base_seed=3).next(2000)
+    src, dst, rate, arr, hold = out
+    assert (src != dst).all() and src.max() < 28 and dst.max() < 28 and rate.max() < 5
+    assert (np.diff(arr, axis=0) >= 0).all() and (hold >= 0).all()
+    assert abs(np.diff(arr, axis=0).mean() - 10800.0 / 300.0) < 1.5
