@@ -149,6 +149,10 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     for (size_t i = 0; i < ctx->need.size(); i++)
         for (int c = 0; c < NC; c++)
             if (cls_n[c] == ctx->need[i]) ctx->cls[i] = (uint8_t)c;
+    kp.need_monotone = 1;
+    for (int r = 0; r < R; r++)
+        for (int m = 0; m + 1 < M; m++)
+            if (ctx->need[(size_t)r * M + m] < ctx->need[(size_t)r * M + m + 1]) kp.need_monotone = 0;
     if (ctx->max_need + 1 > 97) { ctx->err = "a service (slots + guard) may span at most 4 bitmap words (number_slots <= 96)"; return QRMSA_ERR_UNSUPPORTED; }
     if ((S >> 5) + ((ctx->max_need + 1) >> 5) + 2 > 32) { ctx->err = "bitmap + shift distance exceed one warp"; return QRMSA_ERR_UNSUPPORTED; }
 
@@ -255,9 +259,16 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         ctx->err = "GN tables (" + std::to_string(kp.blob_bytes) + " B) exceed shared memory per block";
         return QRMSA_ERR_UNSUPPORTED;
     }
+    // one 1024-thread CTA per SM: the 32 warps share one copy of the GN tables, which leaves the rest of the
+    // 228 KB for L1 (env state is re-read from L1/L2 across the steps of a launch); QRMSA_CTAS_PER_SM=2 selects
+    // two 512-thread CTAs instead (same warps, two table copies) for experiments
     int ctas_per_sm = 1;
     ctx->threads = 1024;
-    if (2 * (size_t)(kp.blob_bytes + 1024 + 64) <= (size_t)smem_sm) { ctas_per_sm = 2; ctx->threads = 512; }
+    const char *env_ctas = getenv("QRMSA_CTAS_PER_SM");
+    if (env_ctas && atoi(env_ctas) == 2 && 2 * (size_t)(kp.blob_bytes + 1024 + 64) <= (size_t)smem_sm) {
+        ctas_per_sm = 2;
+        ctx->threads = 512;
+    }
     const int wpc = ctx->threads / 32;
     const int want = (n_envs + wpc - 1) / wpc;
     ctx->grid = want < ctx->sm_count * ctas_per_sm ? want : ctx->sm_count * ctas_per_sm;

@@ -49,6 +49,7 @@ enum EnvError : int {
 struct KParams {
     // dimensions
     int n_envs, N, E, K, M, Mc, R, S, W, Hmax, NC, D, CAP, T, n_req, group_size;
+    int need_monotone;  // slots_needed never decreases as the modulation index falls (true for SE-sorted tables)
     // static tables in global memory
     const uint8_t *path_hops;   // [N*N*K]
     const uint8_t *path_links;  // [N*N*K*Hmax]
@@ -90,12 +91,14 @@ constexpr int MAX_RM = 512, MAX_E = 256, MAX_NC = 32, MAX_M = 8, MAX_R = 256;
 __host__ __device__ constexpr int G(int D) { return INV + 8 * D; }  // double[NC][D]
 }  // namespace lay
 
+// The same dynamic-shared-memory block under three element types: indexing the __shared__ arrays directly keeps
+// the accesses in the shared address space (LDS with an immediate offset, no generic-pointer conversion).
 extern __shared__ __align__(128) unsigned char qsmem[];
+extern __shared__ __align__(128) double qsmem_f64[];
+extern __shared__ __align__(128) int qsmem_i32[];
 
 struct Tab {
-    __device__ __forceinline__ static double d(int byte_off, int idx) {
-        return *reinterpret_cast<const double *>(qsmem + byte_off + idx * 8);
-    }
+    __device__ __forceinline__ static double d(int byte_off, int idx) { return qsmem_f64[(byte_off >> 3) + idx]; }
     __device__ __forceinline__ static double PHIN(int i) { return d(lay::PHIN, i); }
     __device__ __forceinline__ static double W1(int i) { return d(lay::W1, i); }
     __device__ __forceinline__ static double W2(int i) { return d(lay::W2, i); }
@@ -109,7 +112,7 @@ struct Tab {
     __device__ __forceinline__ static double G(int D, int i) { return d(lay::G(D), i); }
     __device__ __forceinline__ static int need(int i) { return qsmem[lay::NEED + i]; }
     __device__ __forceinline__ static int cls(int i) { return qsmem[lay::CLS + i]; }
-    __device__ __forceinline__ static int rate(int i) { return *reinterpret_cast<const int *>(qsmem + lay::RATE + i * 4); }
+    __device__ __forceinline__ static int rate(int i) { return qsmem_i32[(lay::RATE >> 2) + i]; }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -177,6 +180,8 @@ __device__ __forceinline__ uint32_t range_mask(int s, int e, int j) {
     const uint32_t upto_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
     return upto_hi & ~((1u << lo) - 1u);
 }
+
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -438,6 +443,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                 const bool prunable = (hp & 0x80) != 0;
                 const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
                 const int mycnt = lane < hops ? cnt[mylink] : 0;
+                if (lane < hops) prefetch_l1(lists + (unsigned)(mylink * dm.CAP()));  // needed by the GN sum below
                 const uint32_t av = path_available(dm, bm, hops, mylink, lane);
                 QCNT(QRMSA_CNT_LINKS_READ, hops);
                 QCNT(QRMSA_CNT_PATHS_TRIED, 1);
@@ -456,7 +462,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                         a += b;
                     }
                     const unsigned any = __ballot_sync(FULL, r != 0u);
-                    if (!any) { blk_res = 1; continue; }
+                    if (!any) {
+                        // no block of n+1 slots: the reference sets blocked_due_to_resources and tries the next
+                        // modulation (heuristics.py:938-940); when the remaining ones all need >= n slots none of
+                        // them can fit either, so the loop ends here with the same flags
+                        blk_res = 1;
+                        if (p.need_monotone) break;
+                        continue;
+                    }
                     const int fl = __ffs(any) - 1;
                     const uint32_t w = __shfl_sync(FULL, r, fl);
                     const int s = (fl << 5) + __ffs(w) - 1;
