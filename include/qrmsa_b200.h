@@ -58,6 +58,9 @@ typedef struct qrmsa_static_tables {
     double slot_bandwidth_hz;      /* Hz  (qrmsa.pyx:227)  */
     double launch_power_w;         /* W   (qrmsa.pyx:288)  */
     double margin_db;              /* dB  (qrmsa.pyx:228)  */
+    /* only read by qrmsa_observation (route-length feature, qrmsa.pyx:676-690); may be NULL otherwise */
+    const double *path_length_km;  /* [n_nodes*n_nodes*k_paths] Path.length                            */
+    const double *link_length_km;  /* [n_links] topology[u][v]["length"]                               */
 } qrmsa_static_tables;
 
 /* Counter slots returned by qrmsa_counters (per env group), all int64. */
@@ -158,6 +161,21 @@ int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream);
  */
 int qrmsa_step_action(qrmsa_ctx *ctx, const int64_t *d_action, float *d_reward, uint8_t *d_status, double *d_gsnr,
                       uint8_t *d_terminated, void *stream);
+
+/*
+ * Replaces: QRMSAEnv.observation() with gen_observation=True (envs/qrmsa.pyx:583-781, GSNR per candidate from
+ * core.osnr.calculate_osnr_observation, core/osnr.pyx:259-368) for the CURRENT request of every env:
+ *   d_obs   float [n_envs][1 + 2 + k + 12*k*M]   bit rate, source, destination, k route lengths, 12 features per
+ *                                                (path, modulation) (qrmsa.pyx:592-665, :773-779)
+ *   d_mask  uint8 [n_envs][k*M*S + 1]            1 iff the start slot is a guard-band-valid candidate AND
+ *                                                round((gsnr - minimum_osnr)/|minimum_osnr|, 10) >= 0 (threshold
+ *                                                WITHOUT margin); last entry (reject) always 1 (qrmsa.pyx:731-766)
+ * Read-only on the env state.  Stands in for the mask SB3's MaskablePPO asks the wrapper for
+ * (wrappers/qrmsa_gym.py:74-75).
+ */
+int qrmsa_observation(qrmsa_ctx *ctx, float *d_obs, uint8_t *d_mask, void *stream);
+/* Sizes of one env's observation vector and action mask. */
+int qrmsa_observation_dims(const qrmsa_ctx *ctx, int *obs_dim, int *n_actions);
 
 /*
  * Decisions of requests [first, first+count) as int32 action words, [count][n_envs] request-major:

@@ -70,7 +70,7 @@ class StaticTablesC(C.Structure):
         ("mod_se", C.c_void_p), ("mod_min_osnr", C.c_void_p), ("bit_rates", C.c_void_p),
         ("slots_needed", C.c_void_p),
         ("frequency_start", C.c_double), ("slot_bandwidth_hz", C.c_double), ("launch_power_w", C.c_double),
-        ("margin_db", C.c_double)]
+        ("margin_db", C.c_double), ("path_length_km", C.c_void_p), ("link_length_km", C.c_void_p)]
 
 
 # name -> (restype, argtypes); the symbol list is also what tests/test_abi.py checks against the header
@@ -88,6 +88,8 @@ SIGNATURES = {
     "qrmsa_load_trace_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "qrmsa_step_first_fit": (_I, [_P, _I, _P]),
     "qrmsa_step_action": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "qrmsa_observation": (_I, [_P, _P, _P, _P]),
+    "qrmsa_observation_dims": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "qrmsa_get_actions": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_actions_host": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_gsnr_host": (_I, [_P, _I, _I, _P, _P]),

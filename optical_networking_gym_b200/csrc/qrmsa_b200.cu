@@ -1,5 +1,6 @@
 // qrmsa_b200.cu -- C ABI (include/qrmsa_b200.h) over the sm_100a kernels of qrmsa_kernels.cuh.
 // Host code: context / memory management, GN-table construction, launches.  No torch types.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +28,10 @@ struct qrmsa_ctx {
     int64_t *h_counters = nullptr;  // pinned
     std::vector<uint8_t> need, cls;
     std::vector<int> cls_n;
+    const double *d_path_len_norm = nullptr;
+    double inv_max_rate = 0.0;
+    int obs_grid = 0;
+    size_t obs_smem = 0;
     std::string err;
 };
 
@@ -185,6 +190,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         W1[l] = t->link_n_spans[l] * leff[l];
         W2[l] = -(t->link_n_spans[l] * leff[l] * (5.0 / 3.0) * (leff[l] / len));  // stored negated
     }
+    for (int m = 0; m < M; m++) kp.mod_thr_nomargin[m] = t->mod_min_osnr[m];
     for (int m = 0; m < M; m++) {
         // accept iff gsnr_dB >= thr (heuristics.py:957-958)  <=>  acc = 1/GSNR <= 10^(-thr/10);
         // near-threshold flag: |gsnr_dB - thr| < 1e-3 dB
@@ -279,8 +285,26 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     CK(cudaFuncSetAttribute(k_probe_gsnr, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_build_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
 
-    // ---- uploads and state
+    // ---- observation kernel: route-length normalisation (qrmsa.pyx:676-690) and launch shape
     int rc;
+    if (t->path_length_km && t->link_length_km) {
+        double lo = t->link_length_km[0], hi = t->link_length_km[0];
+        for (int l = 1; l < E; l++) { lo = std::min(lo, t->link_length_km[l]); hi = std::max(hi, t->link_length_km[l]); }
+        std::vector<double> pln(n_paths);
+        for (size_t i = 0; i < n_paths; i++) pln[i] = hi == lo ? 0.0 : (t->path_length_km[i] - lo) / (hi - lo);
+        if ((rc = dev_upload(ctx, &ctx->d_path_len_norm, pln.data(), n_paths))) return rc;
+        double mx = 0.0;
+        for (int r = 0; r < R; r++) mx = std::max(mx, (double)rate_milli[r]);
+        ctx->inv_max_rate = mx > 0 ? 1.0 / mx : 0.0;
+        ctx->obs_smem = (size_t)kp.blob_bytes + sizeof(ObsSmem) + (size_t)D * 8 + (size_t)kp.Hmax * kp.CAP * 4;
+        if ((int)ctx->obs_smem <= ctx->smem_optin) {
+            CK(cudaFuncSetAttribute(k_observation, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->obs_smem));
+            const int per_sm = (2 * (ctx->obs_smem + 1024) <= (size_t)smem_sm) ? 2 : 1;
+            ctx->obs_grid = std::min(n_envs, ctx->sm_count * per_sm);
+        }
+    }
+
+    // ---- uploads and state
     if ((rc = dev_upload(ctx, &kp.path_hops, (const uint8_t *)hops_dev.data(), n_paths))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_links, t->path_links, n_paths * t->max_hops))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_gn, pgn.data(), n_paths))) return rc;
@@ -419,6 +443,27 @@ extern "C" int qrmsa_step_action(qrmsa_ctx *ctx, const int64_t *d_action, float 
     CK(cudaSetDevice(ctx->device));
     k_step_action<<<ctx->grid, ctx->threads, ctx->kp.blob_bytes, (cudaStream_t)stream>>>(
         ctx->kp, (const long long *)d_action, d_reward, d_status, d_gsnr, d_terminated, ctx->kp.n_req);
+    CK(cudaGetLastError());
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_observation_dims(const qrmsa_ctx *ctx, int *obs_dim, int *n_actions) {
+    if (!ctx) return QRMSA_ERR_ARG;
+    if (obs_dim) *obs_dim = 1 + 2 + ctx->kp.K + 12 * ctx->kp.K * ctx->kp.M;   // qrmsa.pyx:323-328
+    if (n_actions) *n_actions = ctx->kp.K * ctx->kp.M * ctx->kp.S + 1;        // qrmsa.pyx:319-321
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_observation(qrmsa_ctx *ctx, float *d_obs, uint8_t *d_mask, void *stream) {
+    if (!ctx || !d_obs || !d_mask) return QRMSA_ERR_ARG;
+    if (ctx->kp.n_req < 1) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
+    if (!ctx->d_path_len_norm) { ctx->err = "path_length_km / link_length_km were not given to qrmsa_create"; return QRMSA_ERR_STATE; }
+    if (!ctx->obs_grid) { ctx->err = "observation kernel needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(ctx->device));
+    int obs_dim = 0, n_actions = 0;
+    qrmsa_observation_dims(ctx, &obs_dim, &n_actions);
+    k_observation<<<ctx->obs_grid, OBS_THREADS, ctx->obs_smem, (cudaStream_t)stream>>>(
+        ctx->kp, ctx->d_path_len_norm, ctx->inv_max_rate, d_obs, d_mask, obs_dim, n_actions);
     CK(cudaGetLastError());
     return QRMSA_OK;
 }

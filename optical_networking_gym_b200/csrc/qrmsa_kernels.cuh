@@ -49,6 +49,7 @@ enum EnvError : int {
 struct KParams {
     // dimensions
     int n_envs, N, E, K, M, Mc, R, S, W, Hmax, NC, D, CAP, T, n_req, group_size;
+    double mod_thr_nomargin[8];  // Modulation.minimum_osnr (no margin): the observation's threshold (qrmsa.pyx:743-758)
     int need_monotone;  // slots_needed never decreases as the modulation index falls (true for SE-sorted tables)
     // static tables in global memory
     const uint8_t *path_hops;   // [N*N*K]
@@ -645,6 +646,232 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
             if (o_gsnr) o_gsnr[env] = g;
             if (o_term) o_term[env] = (uint8_t)term;
         }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Observation vector + GSNR-validated action mask (QRMSAEnv.observation with gen_observation=True,
+// qrmsa.pyx:583-781; calculate_osnr_observation, osnr.pyx:259-368).  One CTA per env, read-only on env state.
+//
+// The reference evaluates one GN sum per valid (path, modulation, start) -- and does it twice (features, then
+// mask).  The neighbour sum depends only on the candidate's centre c2 = 2*start + n (half-slots), so per path the
+// CTA first builds X[c2] for every c2 (thread per c2: consecutive threads read consecutive G/INV entries, so the
+// shared-memory lookups are conflict-free), then every (modulation, start) is one lookup + log10.
+// --------------------------------------------------------------------------------------------------------
+constexpr int OBS_THREADS = 640;
+constexpr int OBS_NRED = 6;
+
+struct ObsSmem {           // lives after the table blob in dynamic shared memory
+    double red[OBS_THREADS / 32][OBS_NRED];
+    double bcast[8];
+    uint32_t av[32];       // path availability words (+ the virtual slot)
+    uint32_t valid[32];    // valid-start bitmap of the current modulation
+    int link[32], cnt[32];
+    double w1[32], w2[32];
+};
+
+// sums (or max for index 4, 5) of OBS_NRED per-thread values over the CTA; result broadcast to all threads
+__device__ __forceinline__ void block_reduce6(ObsSmem *sm, double v[OBS_NRED], const unsigned max_mask) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < OBS_NRED; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(FULL, x, o);
+            x = ((max_mask >> k) & 1u) ? fmax(x, y) : x + y;
+        }
+        if (lane == 0) sm->red[warp][k] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < OBS_NRED; ++k) {
+            double x = lane < (int)(blockDim.x >> 5) ? sm->red[lane][k] : (((max_mask >> k) & 1u) ? -1e300 : 0.0);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double y = __shfl_xor_sync(FULL, x, o);
+                x = ((max_mask >> k) & 1u) ? fmax(x, y) : x + y;
+            }
+            if (lane == 0) sm->bcast[k] = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < OBS_NRED; ++k) v[k] = sm->bcast[k];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(OBS_THREADS, 1)
+    k_observation(const KParams p, const double *__restrict__ path_len_norm, const double inv_max_rate,
+                  float *__restrict__ obs_out, uint8_t *__restrict__ mask_out, const int obs_dim, const int n_actions) {
+    __shared__ uint64_t mbar;
+    stage_tables(p, &mbar);
+    const Dim<0, 0, 0> dm(p);
+    const int S = p.S, W = p.W, M = p.M, K = p.K, D = p.D, CAP = p.CAP;
+    unsigned char *extra = qsmem + p.blob_bytes;
+    ObsSmem *sm = reinterpret_cast<ObsSmem *>(extra);
+    double *X = reinterpret_cast<double *>(extra + sizeof(ObsSmem));          // [D]
+    uint32_t *rec = reinterpret_cast<uint32_t *>(X + D);                        // [Hmax][CAP]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int env = blockIdx.x; env < p.n_envs; env += gridDim.x) {
+        const int4 st = p.estate[env];
+        float *obs = obs_out + (size_t)env * obs_dim;
+        uint8_t *mask = mask_out + (size_t)env * n_actions;
+        const int cur = st.x < p.n_req ? st.x : p.n_req - 1;
+        const uint4 rq = p.trace[(size_t)env * p.T + cur];
+        const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+        const uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
+        const uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
+        const uint32_t *lists = p.lists + (size_t)env * p.E * CAP;
+        const int pbase = (src * p.N + dst) * K;
+        if (tid == 0) {
+            obs[0] = (float)((double)Tab::rate(rate) * inv_max_rate);                       // qrmsa.pyx:654-665
+            obs[1] = (float)(p.N > 1 ? (double)src / (double)(p.N - 1) : 0.0);
+            obs[2] = (float)(p.N > 1 ? (double)dst / (double)(p.N - 1) : 0.0);
+            mask[n_actions - 1] = 1;                                                        // qrmsa.pyx:766
+        }
+        for (int pi = 0; pi < K; ++pi) {
+            const int path = pbase + pi;
+            const int hops = __ldg(p.path_hops + path) & 0x7f;
+            if (tid == 0) obs[3 + pi] = hops ? (float)path_len_norm[path] : 0.f;
+            if (hops == 0) {   // fewer than k paths for this pair: features stay -1, no valid action (qrmsa.pyx:697)
+                for (int i = tid; i < M * 12; i += blockDim.x) obs[3 + K + pi * M * 12 + i] = -1.f;
+                for (int i = tid; i < M * S; i += blockDim.x) mask[(size_t)pi * M * S + i] = 0;
+                continue;
+            }
+            __syncthreads();
+            if (tid < 32) {
+                const int l = tid < hops ? __ldg(p.path_links + path * p.Hmax + tid) : 0;
+                sm->link[tid] = l;
+                sm->cnt[tid] = tid < hops ? cnt[l] : 0;
+                sm->w1[tid] = Tab::W1(l);
+                sm->w2[tid] = Tab::W2(l);
+                const uint32_t a = path_available(dm, bm, hops, l, lane);
+                sm->av[tid] = a;
+            }
+            __syncthreads();
+            // stage the channel records of the path's links
+            for (int i = 0; i < hops; ++i) {
+                const int c = sm->cnt[i];
+                const uint32_t *lst = lists + (unsigned)(sm->link[i] * CAP);
+                for (int q = tid; q < c; q += blockDim.x) rec[i * CAP + q] = lst[q];
+            }
+            __syncthreads();
+            // X[c2]: neighbour sum for a candidate centred at c2 half-slots
+            for (int c2 = tid; c2 < D; c2 += blockDim.x) {
+                double x = 0.0;
+                for (int i = 0; i < hops; ++i) {
+                    const int c = sm->cnt[i];
+                    const uint32_t *r = rec + i * CAP;
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int q = 0; q < c; ++q) {
+                        const uint32_t v = r[q];
+                        const int d = abs((int)(v & 0xfffu) - c2);
+                        s1 += Tab::G(D, (v >> 23) * D + d);
+                        s2 = fma(Tab::PHIN(v >> 20), Tab::INV(d), s2);
+                    }
+                    x = fma(sm->w1[i], s1, x);
+                    x = fma(sm->w2[i], s2, x);
+                }
+                X[c2] = x;
+            }
+            // free-block statistics of the path availability (qrmsa.pyx:631-646), thread per slot
+            double bs[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};
+            for (int s = tid; s < S; s += blockDim.x) {
+                const bool free_s = (sm->av[s >> 5] >> (s & 31)) & 1u;
+                const bool free_n = (s + 1 < S) && ((sm->av[(s + 1) >> 5] >> ((s + 1) & 31)) & 1u);
+                if (free_s) bs[0] += 1.0;                       // total available slots
+                if (free_s && !free_n) {                        // a run ends here: walk back to its start
+                    int b = s;
+                    while (b > 0 && ((sm->av[(b - 1) >> 5] >> ((b - 1) & 31)) & 1u)) --b;
+                    const double len = (double)(s - b + 1);
+                    bs[1] += 1.0; bs[2] += len; bs[3] += len * len;
+                }
+            }
+            block_reduce6(sm, bs, 0x30u);
+            const double total_av = bs[0], nb = bs[1];
+            double mean_block = 0.0, std_block = 0.0;
+            if (nb > 0.0) {
+                const double mb = bs[2] / nb;
+                const double var = fmax(bs[3] / nb - mb * mb, 0.0);
+                mean_block = ((mb - 4.0) / 4.0) / 100.0;
+                std_block = sqrt(var) / 100.0;
+            }
+            // per modulation: valid starts, GSNR per start, mask and features
+            uint32_t r = 0; int a = 1;
+            if (warp == 0) r = sm->av[lane];
+            for (int mi = 0; mi < M; ++mi) {
+                const int m = (M - 1) - mi;
+                const int n = Tab::need(rate * M + m), ncls = Tab::cls(rate * M + m);
+                if (warp == 0) {
+                    const int L = n + 1;
+                    if (L < a) { r = sm->av[lane]; a = 1; }
+                    while (a < L) { const int b = min(a, L - a); r &= shr_multi(r, b); a += b; }
+                    sm->valid[lane] = r;
+                }
+                __syncthreads();
+                double v[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};  // count, sum s, sum norm, -, max s, max norm
+                double my_norm = 0.0; bool my_valid = false; int my_s = 0;
+                for (int s = tid; s < S; s += blockDim.x) {
+                    const bool ok = (sm->valid[s >> 5] >> (s & 31)) & 1u;
+                    uint8_t bit = 0;
+                    if (ok) {
+                        const double acc = gn_base(p, path, s, n, ncls).with(X[2 * s + n]);
+                        const double g = 10.0 * log10(1.0 / acc);
+                        const double th = p.mod_thr_nomargin[m];
+                        const double nrm = rint(((g - th) / fabs(th)) * 1e10) / 1e10;     // np.round(x, 10), osnr.pyx:366
+                        bit = nrm >= 0.0 ? 1 : 0;
+                        v[0] += 1.0; v[1] += (double)s; v[2] += nrm;
+                        v[4] = fmax(v[4], (double)s); v[5] = fmax(v[5], nrm);
+                        my_norm = nrm; my_valid = true; my_s = s;
+                    }
+                    mask[(size_t)pi * M * S + (size_t)mi * S + s] = bit;
+                }
+                block_reduce6(sm, v, 0x30u);
+                const double cntv = v[0];
+                double f_avg = 0, f_std = 0, f_max = 0, best = 0, omean = 0, ovar = 0;
+                if (cntv > 0.0) {
+                    f_avg = v[1] / cntv; omean = v[2] / cntv; f_max = v[4]; best = fmax(v[5], 0.0);
+                    double w[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};
+                    if (S <= (int)blockDim.x) {
+                        if (my_valid) { const double ds = (double)my_s - f_avg, dn = my_norm - omean; w[0] = ds * ds; w[1] = dn * dn; }
+                    } else {
+                        for (int s = tid; s < S; s += blockDim.x) {
+                            if ((sm->valid[s >> 5] >> (s & 31)) & 1u) {
+                                const double acc = gn_base(p, path, s, n, ncls).with(X[2 * s + n]);
+                                const double g = 10.0 * log10(1.0 / acc);
+                                const double th = p.mod_thr_nomargin[m];
+                                const double nrm = rint(((g - th) / fabs(th)) * 1e10) / 1e10;
+                                const double ds = (double)s - f_avg, dn = nrm - omean;
+                                w[0] += ds * ds; w[1] += dn * dn;
+                            }
+                        }
+                    }
+                    block_reduce6(sm, w, 0x30u);
+                    f_std = sqrt(w[0] / cntv);
+                    ovar = w[1] / cntv;
+                }
+                if (tid == 0) {
+                    float *f = obs + 3 + K + (pi * M + mi) * 12;
+                    f[0] = (float)(cntv / (double)S);
+                    f[1] = (float)(f_avg / (double)(S - 1));
+                    f[2] = (float)(f_std / (double)(S - 1));
+                    f[3] = (float)fmax(((double)n - 5.5) / 3.5, 0.0);
+                    f[4] = (float)(2.0 * (total_av - 0.5 * (double)S) / (double)S);
+                    f[5] = (float)mean_block;
+                    f[6] = (float)std_block;
+                    f[7] = (float)best;
+                    f[8] = (float)omean;
+                    f[9] = (float)ovar;
+                    f[10] = (float)(2.0 * ((total_av / (double)S) - 0.5));
+                    f[11] = (float)(f_max / (double)(S - 1));
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -39,6 +39,8 @@ class Engine:
             mod_min_osnr=np.ascontiguousarray(tables.mod_min_osnr, np.float64),
             bit_rates=np.ascontiguousarray(tables.bit_rates, np.float64),
             slots_needed=np.ascontiguousarray(tables.slots_needed, np.uint8),
+            path_length_km=np.ascontiguousarray(tables.path_length_km, np.float64),
+            link_length_km=np.ascontiguousarray(tables.link_n_spans * tables.link_span_len_m / 1e3, np.float64),
         )
         t = _lib.StaticTablesC()
         for n in ("n_nodes", "n_links", "k_paths", "n_mods", "mods_to_consider", "n_rates", "n_slots", "max_hops"):
@@ -128,6 +130,16 @@ class Engine:
             return x.data_ptr() if x is not None else None
         check(self.lib.qrmsa_step_action(self._h, action.data_ptr(), p(reward), p(status), p(gsnr), p(terminated),
                                          self._stream(stream)), self._h)
+
+    def observation_dims(self):
+        a, b = C.c_int(0), C.c_int(0)
+        check(self.lib.qrmsa_observation_dims(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
+
+    def observation(self, obs, mask, stream=None):
+        """obs: float32 CUDA [n_envs, obs_dim]; mask: uint8 CUDA [n_envs, n_actions] (both preallocated)."""
+        check(self.lib.qrmsa_observation(self._h, obs.data_ptr(), mask.data_ptr(), self._stream(stream)), self._h)
+        return obs, mask
 
     # ------------------------------------------------------------------ results
     def actions_host(self, first: int, count: int, stream=None) -> np.ndarray:

@@ -53,6 +53,7 @@ def lib():
         _lib.orc_step_action.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int), C.c_int]
         _lib.orc_get_slots.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_observation.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         _lib.orc_get_link_list.restype = C.c_int
         _lib.orc_get_link_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_probe_gsnr.restype = C.c_double
@@ -65,6 +66,12 @@ def lib():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def link_length_range(tb):
+    """min / max LINK length in km (qrmsa.pyx:676-678), from the span tables: n_spans * span_length."""
+    km = tb.link_n_spans * tb.link_span_len_m / 1e3
+    return float(km.min()), float(km.max())
 
 
 COUNTER_NAMES = ("processed", "accepted", "ep_processed", "ep_accepted", "bl_reject", "n_gn", "n_gn_terms",
@@ -141,6 +148,16 @@ class OracleEnv:
         rw, g, term = C.c_double(0), C.c_double(0), C.c_int(0)
         st = lib().orc_step_action(self._h, int(action), C.byref(rw), C.byref(g), C.byref(term), int(episode_length))
         return st, rw.value, g.value, bool(term.value)
+
+    def observation(self):
+        """(obs float32[1+2+k+12kM], mask uint8[kMS+1]) for the current request (gen_observation=True mode)."""
+        tb = self.tables
+        obs = np.zeros(1 + 2 + tb.k_paths + 12 * tb.k_paths * tb.n_mods, np.float32)
+        mask = np.zeros(tb.k_paths * tb.n_mods * tb.n_slots + 1, np.uint8)
+        pl = np.ascontiguousarray(tb.path_length_km, np.float64)
+        lo, hi = link_length_range(tb)
+        lib().orc_observation(self._h, _ptr(pl), lo, hi, _ptr(obs), _ptr(mask))
+        return obs, mask
 
     def slots(self) -> np.ndarray:
         out = np.zeros((self.E, self.S), np.uint8)

@@ -97,3 +97,27 @@ def test_oracle_edge_cases():
     r = o.run_first_fit(n - 1)
     assert r["accepted"].all() and (r["action"] == r["action"][0]).all()
     assert o.slots().all()
+
+
+@pytest.mark.parametrize("tag,topo", [("obs_nsfnet_320_l210_s21", "nsfnet"), ("obs_nobel-eu_320_l400_s8", "nobel-eu")])
+def test_oracle_observation_and_mask_vs_reference(tag, topo):
+    """gen_observation=True: observation vector and GSNR-validated action mask, every step of the recording."""
+    import os
+    from helpers import GOLDEN
+
+    if not os.path.exists(os.path.join(GOLDEN, tag + ".npz")):
+        pytest.skip("fixture not generated")
+    g = load_golden(tag)
+    tb = load_tables(topo, 320)
+    n_req, n_act = len(g["src"]), int(g["n_actions"])
+    mask_ref = np.unpackbits(g["mask"], axis=1)[:, :n_act]
+    o = orc.OracleEnv(tb, n_req)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    for t in range(len(g["action"]) + 1):
+        obs, mask = o.observation()
+        assert np.abs(obs - g["obs"][t]).max() <= 1e-7, f"obs at step {t}"
+        assert np.array_equal(mask, mask_ref[t]), f"mask at step {t}"
+        if t < len(g["action"]):
+            st, rw, _, _ = o.step_action(int(g["action"][t]), n_req)
+            assert st in (0, 1) and rw == pytest.approx(float(g["reward"][t]), abs=1e-12)
+    assert np.array_equal(o.slots(), g["final_slots"])

@@ -50,6 +50,11 @@ MULTI = [
 RL = [
     ("nsfnet_320_l210_s11", "nsfnet", 320, 210.0, 11, 400),
 ]
+OBS = [
+    # tag, topology, S, load, seed, steps   (gen_observation=True: ~3 s per step in the reference)
+    ("nsfnet_320_l210_s21", "nsfnet", 320, 210.0, 21, 60),
+    ("nobel-eu_320_l400_s8", "nobel-eu", 320, 400.0, 8, 24),   # (ring_4 has < k paths per pair: the reference itself raises there)
+]
 
 
 def tables_for(topo, S):
@@ -115,6 +120,47 @@ def gen_rl(topo, tb, S, load, seed, n_steps):
     return out
 
 
+def gen_obs(topo, S, load, seed, n_steps):
+    """gen_observation=True (qrmsa.pyx:583-781): observation vector + GSNR-validated action mask per step,
+    driven by a seeded mix of mask-sampled and first-fit actions."""
+    heur = rh.first_fit_heuristic()
+    # a few hundred first-fit steps without observations would be faster, but the env cannot switch modes;
+    # a higher load fills the network within the recorded steps instead
+    env = rh.make_env(topo, seed, n_slots=S, load=load, episode_length=n_steps + 1, gen_observation=True)
+    node_index = {n: i for i, n in enumerate(topo.graph["node_indices"])}
+    rates = list(env.bit_rates)
+    rng = np.random.default_rng(seed)
+    obs0, info0 = env.reset()
+    rec = dict(src=[], dst=[], rate=[], arrival=[], holding=[], action=[], reward=[], obs=[obs0], mask=[info0["mask"]])
+
+    def log_req(svc):
+        rec["src"].append(node_index[svc.source]); rec["dst"].append(node_index[svc.destination])
+        rec["rate"].append(rates.index(int(svc.bit_rate)))
+        rec["arrival"].append(np.float32(svc.arrival_time)); rec["holding"].append(np.float32(svc.holding_time))
+
+    log_req(env.current_service)
+    mask = info0["mask"]
+    for t in range(n_steps):
+        valid = np.flatnonzero(mask[:-1])
+        if len(valid) and rng.integers(4) > 0:
+            a = int(rng.choice(valid))
+        elif len(valid):
+            a = int(valid[0])
+        else:
+            a = len(mask) - 1
+        obs, reward, term, _, info = env.step(a)
+        mask = info["mask"]
+        rec["action"].append(a); rec["reward"].append(reward); rec["obs"].append(obs); rec["mask"].append(mask)
+        log_req(env.current_service)
+    out = dict(src=np.array(rec["src"], np.uint8), dst=np.array(rec["dst"], np.uint8), rate=np.array(rec["rate"], np.uint8),
+               arrival=np.array(rec["arrival"], np.float32), holding=np.array(rec["holding"], np.float32),
+               action=np.array(rec["action"], np.int64), reward=np.array(rec["reward"], np.float64),
+               obs=np.array(rec["obs"], np.float32), mask=np.packbits(np.array(rec["mask"], np.uint8), axis=1),
+               n_actions=np.int64(len(mask)),
+               final_slots=np.array(env.topology.graph["available_slots"], np.uint8))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -174,6 +220,19 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, f"rl_{tag}.npz"), **out)
         st = out["status"]
         print(f"rl_{tag}: {len(st)} calls, status counts {np.bincount(st, minlength=4)}, {time.time() - t0:.1f}s")
+
+
+    for tag, name, S, load, seed, steps in OBS:
+        if args.only and args.only not in ("obs_" + tag):
+            continue
+        t0 = time.time()
+        topo = topo_of(name)
+        tables_for(topo, S).save(os.path.join(GOLDEN, f"tables_{name}_{S}.npz"))
+        out = gen_obs(topo, S, load, seed, steps)
+        out["meta_load"] = np.float64(load); out["meta_seed"] = np.int64(seed)
+        np.savez_compressed(os.path.join(GOLDEN, f"obs_{tag}.npz"), **out)
+        print(f"obs_{tag}: {steps} steps, mean valid actions {np.unpackbits(out['mask'], axis=1).sum(1).mean():.0f}, "
+              f"{time.time() - t0:.1f}s")
 
 
 if __name__ == "__main__":
