@@ -16,8 +16,12 @@ Request streams: env i replays `random.Random(base_seed + i)` exactly as the ref
 does not reach it -- so any seed reproduces *a* valid reference run; passing the same seed the oracle
 harness patches in reproduces *that* run bit for bit.
 
-Not implemented yet (SURVEY §8f "next" rows): `gen_observation=True` (observation features and the
-GSNR-validated action mask), `measure_disruptions`, `defragmentation`, `bands`; they raise.
+`gen_observation=True` returns the reference's observation vector and GSNR-validated action mask
+(qrmsa.pyx:583-781) from the device kernel `qrmsa_observation`; with `gen_observation=False` both are zeros, as in
+the reference (qrmsa.pyx:584-587).
+
+Not implemented yet (SURVEY §8f "next" rows): `measure_disruptions`, `defragmentation`, `bands`, continuous bit
+rates, per-service CSV; they raise.
 """
 from __future__ import annotations
 
@@ -97,8 +101,6 @@ def _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, 
         _unsupported("defragmentation=True")
     if bands:
         _unsupported("bands (multiband)")
-    if gen_observation:
-        _unsupported("gen_observation=True (observation features + GSNR action mask)")
     if bit_rate_selection != "discrete":
         _unsupported("bit_rate_selection='continuous'")
 
@@ -199,13 +201,21 @@ class QRMSAEnv(_Common):
         self._t_status = torch.zeros(1, dtype=torch.uint8, device=self._dev)
         self._t_gsnr = torch.zeros(1, dtype=torch.float64, device=self._dev)
         self._t_term = torch.zeros(1, dtype=torch.uint8, device=self._dev)
+        self._t_obs = torch.zeros((1, self.observation_space.shape[0]), dtype=torch.float32, device=self._dev)
+        self._t_mask = torch.zeros((1, self.action_space.n), dtype=torch.uint8, device=self._dev)
         if reset:
             self.reset()
 
     # ------------------------------------------------------------------ gym API
     def _observation(self):
-        obs = np.zeros((self.observation_space.shape[0],), dtype=np.float32)   # gen_observation=False, :584-587
-        return obs, {"mask": np.zeros((self.action_space.n,), dtype=np.uint8)}
+        if not self.gen_observation:                                           # qrmsa.pyx:584-587
+            obs = np.zeros((self.observation_space.shape[0],), dtype=np.float32)
+            return obs, {"mask": np.zeros((self.action_space.n,), dtype=np.uint8)}
+        import torch
+
+        self._eng.observation(self._t_obs, self._t_mask)
+        torch.cuda.current_stream().synchronize()
+        return self._t_obs[0].cpu().numpy(), {"mask": self._t_mask[0].cpu().numpy()}
 
     def _service_from_block(self, i: int) -> Service:
         b = self._block
@@ -461,6 +471,9 @@ class BatchedQRMSAEnv(_Common):
         self._gsnr = torch.zeros(self.n_envs, dtype=torch.float64, device=self._dev)
         self._term = torch.zeros(self.n_envs, dtype=torch.uint8, device=self._dev)
         self._obs = torch.zeros((self.n_envs, self.observation_space.shape[0]), dtype=torch.float32, device=self._dev)
+        self.gen_observation = bool(gen_observation)
+        self._mask = (torch.zeros((self.n_envs, self.action_space.n), dtype=torch.uint8, device=self._dev)
+                      if self.gen_observation else None)
         self.steps_done = 0
         if reset:
             self.reset()
@@ -475,7 +488,12 @@ class BatchedQRMSAEnv(_Common):
         self._eng.reset()
         self._eng.load_trace_host(*self._trace)
         self.steps_done = 0
-        return self._obs, {"mask": None}
+        self._observe()
+        return self._obs, {"mask": self._mask}
+
+    def _observe(self):
+        if self.gen_observation:
+            self._eng.observation(self._obs, self._mask)
 
     def current_requests(self):
         """(src, dst, rate index, arrival, holding) host arrays of the episode, [episode_length, n_envs]."""
@@ -485,7 +503,8 @@ class BatchedQRMSAEnv(_Common):
         """actions: int64 CUDA tensor [n_envs] -> (obs, reward, terminated, truncated, info) of device tensors."""
         self._eng.step_action(actions, self._reward, self._status, self._gsnr, self._term)
         self.steps_done += 1
-        info = {"status": self._status, "osnr": self._gsnr, "mask": None}
+        self._observe()
+        info = {"status": self._status, "osnr": self._gsnr, "mask": self._mask}
         return self._obs, self._reward, self._term.bool(), self._term.bool() & False, info
 
     def step_first_fit(self, n_steps: int = 1):
@@ -493,6 +512,8 @@ class BatchedQRMSAEnv(_Common):
         n_steps = min(int(n_steps), self.episode_length - 1 - self.steps_done)
         self._eng.step_first_fit(n_steps)
         self.steps_done += n_steps
+        if n_steps:
+            self._observe()
         return n_steps
 
     @property
@@ -500,7 +521,9 @@ class BatchedQRMSAEnv(_Common):
         return self.steps_done >= self.episode_length - 1
 
     def action_masks(self):
-        _unsupported("action_masks() with GSNR validation (gen_observation=True)")
+        """Last action mask, uint8 CUDA tensor [n_envs, k*M*S+1] (wrappers/qrmsa_gym.py:74-75); None when
+        gen_observation=False (the reference returns zeros there)."""
+        return self._mask
 
     def actions(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         """Decided action indices [count, n_envs] (reject = k*M*S) and near-threshold flags."""

@@ -159,3 +159,36 @@ def test_single_env_dropin_vs_live_reference():
     o1 = env.step(env.reject_action); o2 = ref.step(ref.action_space.n - 1)
     assert o1[1] == o2[1] == -6.0
     env.close()
+
+
+def test_batched_env_masks_rollout():
+    """gen_observation=True: every mask-sampled action is accepted (reward 0, never LOW_GSNR / NOT_FREE),
+    masks change with the state, reject is always allowed."""
+    import torch
+    from optical_networking_gym_b200 import _lib
+    from optical_networking_gym_b200.env import BatchedQRMSAEnv
+
+    tb = load_tables("nsfnet", 320)
+    n_envs, L = 96, 41
+    env = BatchedQRMSAEnv(tb, n_envs, num_spectrum_resources=320, episode_length=L, load=400.0,
+                          bit_rates=(10, 40, 100, 400, 1000), launch_power_dbm=1.0, gen_observation=True, seed=3)
+    obs, info = env.reset()
+    assert obs.shape == (n_envs, 368) and info["mask"].shape == (n_envs, 9601)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    first_mask_sum = int(info["mask"].sum())
+    for t in range(L - 1):
+        mask = env.action_masks()
+        assert bool((mask[:, -1] == 1).all())
+        w = mask.float()
+        w[:, -1] = 1e-6                      # prefer a real allocation whenever one exists
+        action = torch.multinomial(w, 1, generator=gen).squeeze(1)
+        obs, reward, term, trunc, info = env.step(action)
+        st = info["status"]
+        chose_reject = action == (mask.shape[1] - 1)
+        assert bool(((st == _lib.STEP_ACCEPTED) | chose_reject).all()), "a masked-valid action was refused"
+        assert bool((reward[~chose_reject] == 0).all())
+        assert bool(term.all()) == (t == L - 2)
+    assert int(env.action_masks().sum()) != first_mask_sum
+    c = env.counters()
+    assert c["errors"] == 0 and c["decided"] == n_envs * (L - 1)
+    env.close()
