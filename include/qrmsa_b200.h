@@ -142,6 +142,16 @@ int qrmsa_load_trace_host(qrmsa_ctx *ctx, const uint8_t *h_src, const uint8_t *h
                           const float *h_arrival, const float *h_holding, int n_requests, void *stream);
 
 /*
+ * Same as qrmsa_load_trace_host for a context that owns a SLICE of a larger batch: the host arrays are
+ * [n_requests][row_stride] with row_stride >= n_envs, and the pointers address this context's first env.  Fully
+ * asynchronous on `stream` (host memory must be pinned and stay alive); lets several contexts on several
+ * streams overlap their uploads with each other's kernels.
+ */
+int qrmsa_load_trace_host_strided(qrmsa_ctx *ctx, const uint8_t *h_src, const uint8_t *h_dst, const uint8_t *h_rate,
+                                  const float *h_arrival, const float *h_holding, int n_requests, int64_t row_stride,
+                                  void *stream);
+
+/*
  * Replaces: n_steps iterations of the benchmark loop
  *     action, _, _ = heuristic_shortest_available_path_first_fit_best_modulation(env)
  *     env.step(action)
@@ -184,6 +194,9 @@ int qrmsa_observation_dims(const qrmsa_ctx *ctx, int *obs_dim, int *n_actions);
  */
 int qrmsa_get_actions(qrmsa_ctx *ctx, int first, int count, int32_t *d_out, void *stream);
 int qrmsa_get_actions_host(qrmsa_ctx *ctx, int first, int count, int32_t *h_out, void *stream);
+/* Asynchronous, strided variant: h_out is [count][row_stride] int32 (pinned), this context's envs start at h_out. */
+int qrmsa_get_actions_host_strided(qrmsa_ctx *ctx, int first, int count, int32_t *h_out, int64_t row_stride,
+                                   void *stream);
 /* GSNR (dB) of the accepted candidate per request (0.0 on reject), needs qrmsa_enable_gsnr_log. */
 int qrmsa_get_gsnr_host(qrmsa_ctx *ctx, int first, int count, double *h_out, void *stream);
 

@@ -86,12 +86,14 @@ SIGNATURES = {
     "qrmsa_reset": (_I, [_P, _P]),
     "qrmsa_load_trace": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "qrmsa_load_trace_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
+    "qrmsa_load_trace_host_strided": (_I, [_P, _P, _P, _P, _P, _P, _I, C.c_int64, _P]),
     "qrmsa_step_first_fit": (_I, [_P, _I, _P]),
     "qrmsa_step_action": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "qrmsa_observation": (_I, [_P, _P, _P, _P]),
     "qrmsa_observation_dims": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "qrmsa_get_actions": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_actions_host": (_I, [_P, _I, _I, _P, _P]),
+    "qrmsa_get_actions_host_strided": (_I, [_P, _I, _I, _P, C.c_int64, _P]),
     "qrmsa_get_gsnr_host": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_counters": (_I, [_P, _P, _P]),
     "qrmsa_counters_device": (_I, [_P, C.POINTER(_P)]),

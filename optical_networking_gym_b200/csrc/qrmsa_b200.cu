@@ -418,6 +418,32 @@ extern "C" int qrmsa_load_trace_host(qrmsa_ctx *ctx, const uint8_t *h_src, const
     return qrmsa_load_trace(ctx, d_src, d_dst, d_rate, d_arr, d_hold, n_requests, stream);
 }
 
+extern "C" int qrmsa_load_trace_host_strided(qrmsa_ctx *ctx, const uint8_t *h_src, const uint8_t *h_dst,
+                                             const uint8_t *h_rate, const float *h_arrival, const float *h_holding,
+                                             int n_requests, int64_t row_stride, void *stream) {
+    if (!ctx || !h_src || !h_dst || !h_rate || !h_arrival || !h_holding || row_stride < ctx->kp.n_envs) return QRMSA_ERR_ARG;
+    if (n_requests < 1 || n_requests > ctx->kp.T) { ctx->err = "n_requests outside 1..max_requests"; return QRMSA_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ne = (size_t)ctx->kp.n_envs;
+    const size_t n = (size_t)n_requests * ne;
+    const size_t nb = round_up(n, 256);
+    // the staging buffer is sized once for the largest use of an episode so that it is never re-allocated
+    // while copies of an earlier call are still in flight
+    int rc = ensure_stage(ctx, std::max(nb * 11, (size_t)ctx->kp.T * ne * 11 + 4096));
+    if (rc) return rc;
+    unsigned char *base = (unsigned char *)ctx->stage;
+    float *d_arr = (float *)base, *d_hold = (float *)(base + nb * 4);
+    uint8_t *d_src = base + nb * 8, *d_dst = d_src + nb, *d_rate = d_dst + nb;
+    const size_t rs = (size_t)row_stride;
+    CK(cudaMemcpy2DAsync(d_arr, ne * 4, h_arrival, rs * 4, ne * 4, n_requests, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(d_hold, ne * 4, h_holding, rs * 4, ne * 4, n_requests, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(d_src, ne, h_src, rs, ne, n_requests, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(d_dst, ne, h_dst, rs, ne, n_requests, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(d_rate, ne, h_rate, rs, ne, n_requests, cudaMemcpyHostToDevice, st));
+    return qrmsa_load_trace(ctx, d_src, d_dst, d_rate, d_arr, d_hold, n_requests, stream);
+}
+
 extern "C" int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream) {
     if (!ctx || n_steps < 0) return QRMSA_ERR_ARG;
     if (ctx->kp.n_req < 2) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
@@ -488,6 +514,21 @@ extern "C" int qrmsa_get_actions_host(qrmsa_ctx *ctx, int first, int count, int3
     if (rc) return rc;
     CK(cudaMemcpyAsync(h_out, ctx->stage, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_get_actions_host_strided(qrmsa_ctx *ctx, int first, int count, int32_t *h_out, int64_t row_stride,
+                                              void *stream) {
+    if (!ctx || !h_out || first < 0 || count < 0 || first + count > ctx->kp.n_req || row_stride < ctx->kp.n_envs)
+        return QRMSA_ERR_ARG;
+    if (count == 0) return QRMSA_OK;
+    const size_t ne = (size_t)ctx->kp.n_envs;
+    int rc = ensure_stage(ctx, std::max((size_t)count * ne * 4, (size_t)ctx->kp.T * ne * 11 + 4096));
+    if (rc) return rc;
+    rc = qrmsa_get_actions(ctx, first, count, (int32_t *)ctx->stage, stream);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(h_out, (size_t)row_stride * 4, ctx->stage, ne * 4, ne * 4, count, cudaMemcpyDeviceToHost,
+                         (cudaStream_t)stream));
     return QRMSA_OK;
 }
 

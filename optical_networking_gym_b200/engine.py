@@ -111,6 +111,17 @@ class Engine:
         self._sync(stream)  # the host arrays may be pageable: keep them alive until the copies are done
         self.n_loaded = n_req
 
+    def load_trace_host_strided(self, ptrs, n_requests: int, row_stride: int, stream=None):
+        """Asynchronous upload for a context that owns an env slice of a larger pinned [n_requests, row_stride]
+        batch; `ptrs` = the five host addresses of this slice's first env (src, dst, rate, arrival, holding)."""
+        check(self.lib.qrmsa_load_trace_host_strided(self._h, *[int(p) for p in ptrs], int(n_requests), int(row_stride),
+                                                     self._stream(stream)), self._h)
+        self.n_loaded = int(n_requests)
+
+    def actions_host_strided(self, first: int, count: int, out_ptr: int, row_stride: int, stream=None):
+        check(self.lib.qrmsa_get_actions_host_strided(self._h, first, count, int(out_ptr), int(row_stride),
+                                                      self._stream(stream)), self._h)
+
     def load_trace_device(self, src, dst, rate, arrival, holding, stream=None):
         """torch CUDA tensors shaped [n_requests, n_envs] (uint8, uint8, uint8, float32, float32)."""
         n_req = src.shape[0]

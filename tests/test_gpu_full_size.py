@@ -144,3 +144,30 @@ def test_unsupported_configurations_fail_loudly():
     with pytest.raises(QRMSAError, match="no trace loaded"):
         eng.step_first_fit(1)
     eng.close()
+
+
+def test_pipelined_equals_single_context():
+    """Env slices on separate contexts/streams (upload, kernels and download overlapped) give exactly the
+    decisions of one context."""
+    import torch
+    from optical_networking_gym_b200.engine import Engine
+    from optical_networking_gym_b200.pipeline import PipelinedEpisodes
+    from optical_networking_gym_b200.tracegen import TraceGenerator
+
+    tb = load_tables("nobel-eu", 320)
+    n_envs, n_req = 3001, 180                      # deliberately not divisible by the slice count
+    pinned = [torch.empty((n_req, n_envs), dtype=dt, pin_memory=True) for dt in
+              (torch.uint8, torch.uint8, torch.uint8, torch.float32, torch.float32)]
+    TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, 300.0, base_seed=77).next(n_req, out=[p.numpy() for p in pinned])
+    out = torch.zeros((n_req - 1, n_envs), dtype=torch.int32).pin_memory()
+    pipe = PipelinedEpisodes(tb, n_envs, n_req, slices=3)
+    c_pipe = pipe.run(pinned, out, launch_steps=64)
+    c_pipe2 = pipe.run(pinned, out, launch_steps=179)      # a second episode on the same contexts
+    eng = Engine(tb, n_envs, n_req)
+    eng.reset(); eng.load_trace_host(*[p.numpy() for p in pinned])
+    eng.step_first_fit(n_req - 1)
+    ref = eng.actions_host(0, n_req - 1)
+    assert np.array_equal(out.numpy(), ref)
+    c_ref = eng.counters()
+    assert np.array_equal(c_pipe.sum(0)[:6], c_ref.sum(0)[:6]) and np.array_equal(c_pipe2.sum(0)[:6], c_ref.sum(0)[:6])
+    pipe.close(); eng.close()
