@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--e2e-slices", type=int, default=4)
     ap.add_argument("--ref-chunk", type=int, default=64, help="--impl reference: requests per env per step")
     ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--topology", default=TOPOLOGY, help="other BASELINE configs (parity cases), e.g. germany50")
+    ap.add_argument("--slots", type=int, default=N_SLOTS)
+    ap.add_argument("--load", type=float, default=LOAD)
     return ap.parse_args()
 
 
@@ -416,7 +419,9 @@ def run_b200(args, rank, local_rank, world):
 
 
 def main():
+    global TOPOLOGY, N_SLOTS, LOAD
     args = parse_args()
+    TOPOLOGY, N_SLOTS, LOAD = args.topology, args.slots, args.load
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
