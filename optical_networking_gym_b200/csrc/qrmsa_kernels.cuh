@@ -92,28 +92,48 @@ constexpr int MAX_RM = 512, MAX_E = 256, MAX_NC = 32, MAX_M = 8, MAX_R = 256;
 __host__ __device__ constexpr int G(int D) { return INV + 8 * D; }  // double[NC][D]
 }  // namespace lay
 
-// The same dynamic-shared-memory block under three element types: indexing the __shared__ arrays directly keeps
-// the accesses in the shared address space (LDS with an immediate offset, no generic-pointer conversion).
 extern __shared__ __align__(128) unsigned char qsmem[];
-extern __shared__ __align__(128) double qsmem_f64[];
-extern __shared__ __align__(128) int qsmem_i32[];
 
+// Table reads.  On sm_100a the address of a __shared__ symbol is formed from SR_CgaCtaId (shared::cluster window);
+// left to the compiler that S2R + LEA sequence is re-materialised at most uses inside the step loop.  `sb` holds
+// the window address of the dynamic shared block once per thread (volatile asm: not re-materialisable) and every
+// read is an LDS with register + immediate addressing.
 struct Tab {
-    __device__ __forceinline__ static double d(int byte_off, int idx) { return qsmem_f64[(byte_off >> 3) + idx]; }
-    __device__ __forceinline__ static double PHIN(int i) { return d(lay::PHIN, i); }
-    __device__ __forceinline__ static double W1(int i) { return d(lay::W1, i); }
-    __device__ __forceinline__ static double W2(int i) { return d(lay::W2, i); }
-    __device__ __forceinline__ static double SELF(int i) { return d(lay::SELF, i); }
-    __device__ __forceinline__ static double CN(int i) { return d(lay::CN, i); }
-    __device__ __forceinline__ static double ASEC(int i) { return d(lay::ASEC, i); }
-    __device__ __forceinline__ static double ACCT(int i) { return d(lay::ACCT, i); }
-    __device__ __forceinline__ static double ACCLO(int i) { return d(lay::ACCLO, i); }
-    __device__ __forceinline__ static double ACCHI(int i) { return d(lay::ACCHI, i); }
-    __device__ __forceinline__ static double INV(int i) { return d(lay::INV, i); }
-    __device__ __forceinline__ static double G(int D, int i) { return d(lay::G(D), i); }
-    __device__ __forceinline__ static int need(int i) { return qsmem[lay::NEED + i]; }
-    __device__ __forceinline__ static int cls(int i) { return qsmem[lay::CLS + i]; }
-    __device__ __forceinline__ static int rate(int i) { return qsmem_i32[(lay::RATE >> 2) + i]; }
+    uint32_t sb;
+    __device__ __forceinline__ void init() {
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(sb) : "l"(qsmem));
+    }
+    template <int OFF>
+    __device__ __forceinline__ double f64(int idx) const {
+        double v;
+        asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(sb + (uint32_t)idx * 8u), "n"(OFF));
+        return v;
+    }
+    template <int OFF>
+    __device__ __forceinline__ int u8(int idx) const {
+        uint32_t v;
+        asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(sb + (uint32_t)idx), "n"(OFF));
+        return (int)v;
+    }
+    __device__ __forceinline__ double PHIN(int i) const { return f64<lay::PHIN>(i); }
+    __device__ __forceinline__ double W1(int i) const { return f64<lay::W1>(i); }
+    __device__ __forceinline__ double W2(int i) const { return f64<lay::W2>(i); }
+    __device__ __forceinline__ double SELF(int i) const { return f64<lay::SELF>(i); }
+    __device__ __forceinline__ double CN(int i) const { return f64<lay::CN>(i); }
+    __device__ __forceinline__ double ASEC(int i) const { return f64<lay::ASEC>(i); }
+    __device__ __forceinline__ double ACCT(int i) const { return f64<lay::ACCT>(i); }
+    __device__ __forceinline__ double ACCLO(int i) const { return f64<lay::ACCLO>(i); }
+    __device__ __forceinline__ double ACCHI(int i) const { return f64<lay::ACCHI>(i); }
+    __device__ __forceinline__ double INV(int i) const { return f64<lay::INV>(i); }
+    // G follows INV[D]: entry i of G is entry D + i of the INV-based array
+    __device__ __forceinline__ double G(int D, int i) const { return f64<lay::INV>(D + i); }
+    __device__ __forceinline__ int need(int i) const { return u8<lay::NEED>(i); }
+    __device__ __forceinline__ int cls(int i) const { return u8<lay::CLS>(i); }
+    __device__ __forceinline__ int rate(int i) const {
+        int v;
+        asm("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(sb + (uint32_t)i * 4u), "n"(lay::RATE));
+        return v;
+    }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -221,19 +241,19 @@ struct GnBase {
     __device__ __forceinline__ double with(double x) const { return ase + cn * (selfpb + x); }
 };
 
-__device__ __forceinline__ GnBase gn_base(const KParams &p, int path, int s, int n, int ncls) {
+__device__ __forceinline__ GnBase gn_base(const KParams &p, const Tab &t, int path, int s, int n, int ncls) {
     const double2 pg = __ldg(p.path_gn + path);
     const double fc = p.f0 + (p.sb * (double)s) + (p.sb * ((double)n / 2.0));  // heuristics.py:948-951
     GnBase b;
-    b.ase = Tab::ASEC(ncls) * fc * pg.x;
-    b.cn = Tab::CN(ncls);
-    b.selfpb = Tab::SELF(ncls) * pg.y;
+    b.ase = t.ASEC(ncls) * fc * pg.x;
+    b.cn = t.CN(ncls);
+    b.selfpb = t.SELF(ncls) * pg.y;
     return b;
 }
 
 // sum over the path's links and every channel on them (same value on every lane)
 template <class DM>
-__device__ __forceinline__ double gn_neighbours(const DM &dm, const uint32_t *lists, int hops, int mylink, int mycnt,
+__device__ __forceinline__ double gn_neighbours(const DM &dm, const Tab &t, const uint32_t *lists, int hops, int mylink, int mycnt,
                                                 int c2, int lane, uint32_t &terms) {
     const int D = dm.D(), CAP = dm.CAP();
     double x = 0.0;
@@ -248,11 +268,11 @@ __device__ __forceinline__ double gn_neighbours(const DM &dm, const uint32_t *li
         for (int q = lane; q < c; q += 32, lst += 32) {
             const uint32_t rec = *lst;
             const int d = abs((int)(rec & 0xfffu) - c2);
-            s1 += Tab::G(D, (rec >> 23) * D + d);
-            s2 = fma(Tab::PHIN(rec >> 20), Tab::INV(d), s2);
+            s1 += t.G(D, (rec >> 23) * D + d);
+            s2 = fma(t.PHIN(rec >> 20), t.INV(d), s2);
         }
-        x = fma(Tab::W1(l), s1, x);
-        x = fma(Tab::W2(l), s2, x);  // W2 is stored negated
+        x = fma(t.W1(l), s1, x);
+        x = fma(t.W2(l), s2, x);  // W2 is stored negated
     }
     return warp_sum(x);
 }
@@ -299,7 +319,7 @@ __device__ __forceinline__ int commit(const DM &dm, uint32_t *bm, uint16_t *cnt,
 
 // qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record
 template <class DM>
-__device__ __forceinline__ int release_service(const DM &dm, const KParams &p, uint32_t *bm,
+__device__ __forceinline__ int release_service(const DM &dm, const KParams &p, const Tab &t, uint32_t *bm,
                                                uint16_t *cnt, uint32_t *lists, const uint4 rq, int lane) {
     const int S = dm.S(), M = dm.M(), CAP = dm.CAP();
     const uint32_t a = rq.w & QRMSA_ACTION_MASK;
@@ -308,13 +328,13 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, u
     const int rel = (a / S) % M;
     const int pi = a / (S * M);
     const int m = (M - 1) - rel;
-    const int n = Tab::need(rate * M + m);
+    const int n = t.need(rate * M + m);
     const int path = (src * p.N + dst) * dm.K() + pi;
     const int hops = __ldg(p.path_hops + path) & 0x7f;
     const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
     const int mycnt = lane < hops ? cnt[mylink] : 0;
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
-                            ((uint32_t)Tab::cls(rate * M + m) << 23);
+                            ((uint32_t)t.cls(rate * M + m) << 23);
     update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
     int err = 0;
 #pragma unroll 1
@@ -365,7 +385,7 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
 // release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
 // schedule exactly as they are absent from the reference heap.
 template <class DM>
-__device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, uint4 *tr,
+__device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
                                                    const uint16_t *perm, uint32_t *bm, uint16_t *cnt, uint32_t *lists,
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
     cur += 1;
@@ -374,7 +394,7 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];
         if (rq.w & QRMSA_FLAG_ACCEPTED) {
-            err |= release_service(dm, p, bm, cnt, lists, rq, lane);
+            err |= release_service(dm, p, t, bm, cnt, lists, rq, lane);
             n_rel += 1;
         }
         rel_ptr += 1;
@@ -387,9 +407,9 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
 
 // One QoT-checked candidate: accept iff gsnr >= threshold (heuristics.py:957-958), decided on the linear
 // value acc = 1/GSNR against ACCT[m] = 10^(-thr/10); |gsnr - thr| < 1e-3 dB <=> ACCLO[m] < acc < ACCHI[m].
-__device__ __forceinline__ bool qot_ok(int m, double acc, uint32_t &flags) {
-    if (acc > Tab::ACCLO(m) && acc < Tab::ACCHI(m)) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
-    return acc <= Tab::ACCT(m);
+__device__ __forceinline__ bool qot_ok(const Tab &t, int m, double acc, uint32_t &flags) {
+    if (acc > t.ACCLO(m) && acc < t.ACCHI(m)) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+    return acc <= t.ACCT(m);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -400,6 +420,8 @@ template <int S_, int M_, int K_>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams p, const int n_steps) {
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
+    Tab t;
+    t.init();
     const Dim<S_, M_, K_> dm(p);
     const int S = dm.S(), M = dm.M(), K = dm.K();
 
@@ -428,7 +450,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
             const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
             const int pbase = (src * p.N + dst) * K;
             // lane m holds (slots needed, slot class) of modulation m for this request's bit rate
-            const int mynd = lane < M ? (Tab::need(rate * M + lane) | (Tab::cls(rate * M + lane) << 8)) : 0;
+            const int mynd = lane < M ? (t.need(rate * M + lane) | (t.cls(rate * M + lane) << 8)) : 0;
             uint32_t flags = QRMSA_FLAG_DECIDED;
             int action = reject;
             double acc_ok = 1.0;
@@ -474,19 +496,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                     const int fl = __ffs(any) - 1;
                     const uint32_t w = __shfl_sync(FULL, r, fl);
                     const int s = (fl << 5) + __ffs(w) - 1;
-                    const GnBase gb = gn_base(p, path, s, n, ncls);
-                    if (prunable && gb.empty() >= Tab::ACCHI(m)) {  // hopeless even in an empty network
+                    const GnBase gb = gn_base(p, t, path, s, n, ncls);
+                    if (prunable && gb.empty() >= t.ACCHI(m)) {  // hopeless even in an empty network
                         QCNT(QRMSA_CNT_GN_PRUNED, 1);
                         blk_osnr = 1;
                         blk_res = 0;
                         continue;
                     }
                     uint32_t terms = 0;
-                    const double acc = gb.with(gn_neighbours(dm, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
+                    const double acc = gb.with(gn_neighbours(dm, t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
                     QCNT(QRMSA_CNT_GN_EVALS, 1);
                     QCNT(QRMSA_CNT_GN_TERMS, terms);
                     if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
-                    if (qot_ok(m, acc, flags)) {
+                    if (qot_ok(t, m, acc, flags)) {
                         found = true;
                         action = pi * M * S + ((M - 1) - m) * S + s;
                         acc_ok = acc;
@@ -496,7 +518,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                         flags |= QRMSA_FLAG_ACCEPTED;
                         accepted += 1;
                         QCNT(QRMSA_CNT_ACCEPTED, 1);
-                        QCNT(QRMSA_CNT_RATE_PROVISIONED, Tab::rate(rate));
+                        QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate(rate));
                         QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
                         QCNT(QRMSA_CNT_MOD_HIST + m, 1);
                         break;
@@ -511,7 +533,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                 QCNT(QRMSA_CNT_BLOCKED_OSNR, blk_osnr);
             }
             QCNT(QRMSA_CNT_DECIDED, 1);
-            QCNT(QRMSA_CNT_RATE_REQUESTED, Tab::rate(rate));
+            QCNT(QRMSA_CNT_RATE_REQUESTED, t.rate(rate));
             if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
             if (lane == 0) {
                 tr[cur].w = (uint32_t)action | flags;
@@ -519,7 +541,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
             }
             __syncwarp();
             uint32_t n_rel = 0;
-            if (advance_and_release(dm, p, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+            if (advance_and_release(dm, p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
         }
@@ -539,6 +561,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                   const int episode_length) {
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
+    Tab t;
+    t.init();
     const Dim<0, 0, 0> dm(p);
 
     const int lane = threadIdx.x & 31;
@@ -575,7 +599,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 const int rel = (a / p.S) % p.Mc;
                 const int pi = (a / (p.S * p.Mc)) % p.K;
                 const int m = (p.M - 1 > 1) ? (p.M - 1) - rel : (p.Mc - 1) - rel;  // qrmsa.pyx:821-829
-                const int n = Tab::need(rate * p.M + m);
+                const int n = t.need(rate * p.M + m);
                 const int path = (src * p.N + dst) * p.K + pi;
                 const int hops = __ldg(p.path_hops + path) & 0x7f;
                 const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
@@ -595,12 +619,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                     const double proc = (double)(cur + 1);
                     reward = (float)(-3.0 * (1.0 + (proc - (double)accepted) / proc));
                 } else {
-                    const int ncls = Tab::cls(rate * p.M + m);
+                    const int ncls = t.cls(rate * p.M + m);
                     uint32_t terms = 0;
-                    const double acc = gn_base(p, path, s, n, ncls).with(
-                        gn_neighbours(dm, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
+                    const double acc = gn_base(p, t, path, s, n, ncls).with(
+                        gn_neighbours(dm, t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
                     g = -10.0 * log10(acc);
-                    if (qot_ok(m, acc, flags)) {
+                    if (qot_ok(t, m, acc, flags)) {
                         const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                                              ((uint32_t)ncls << 23);
                         if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
@@ -609,7 +633,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                         status = QRMSA_STEP_ACCEPTED;
                         reward = 0.f;  // reward() falls off its end for accepted services (qrmsa.pyx:1266-1285)
                         QCNT(QRMSA_CNT_ACCEPTED, 1);
-                        QCNT(QRMSA_CNT_RATE_PROVISIONED, Tab::rate(rate));
+                        QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate(rate));
                         QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
                         QCNT(QRMSA_CNT_MOD_HIST + m, 1);
                     } else {
@@ -621,7 +645,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
             if (consume) {
                 if (status == QRMSA_STEP_REJECT_ACTION) QCNT(QRMSA_CNT_REJECTED, 1);
                 QCNT(QRMSA_CNT_DECIDED, 1);
-                QCNT(QRMSA_CNT_RATE_REQUESTED, Tab::rate(rate));
+                QCNT(QRMSA_CNT_RATE_REQUESTED, t.rate(rate));
                 if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
                 if (lane == 0) {
                     tr[cur].w = (uint32_t)(status == QRMSA_STEP_ACCEPTED ? (int)a64 : reject) | flags;
@@ -630,7 +654,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 __syncwarp();
                 Head head = load_head(p, tr, perm, rel_ptr);
                 uint32_t n_rel = 0;
-                if (advance_and_release(dm, p, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+                if (advance_and_release(dm, p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
                     err = ENV_ERR_RELEASE_NOT_FOUND;
                 QCNT(QRMSA_CNT_RELEASES, n_rel);
                 term = (cur + 1 == episode_length);  // episode_services_processed == episode_length (qrmsa.pyx:1056)
@@ -707,6 +731,8 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
                   float *__restrict__ obs_out, uint8_t *__restrict__ mask_out, const int obs_dim, const int n_actions) {
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
+    Tab t;
+    t.init();
     const Dim<0, 0, 0> dm(p);
     const int S = p.S, W = p.W, M = p.M, K = p.K, D = p.D, CAP = p.CAP;
     unsigned char *extra = qsmem + p.blob_bytes;
@@ -727,7 +753,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
         const uint32_t *lists = p.lists + (size_t)env * p.E * CAP;
         const int pbase = (src * p.N + dst) * K;
         if (tid == 0) {
-            obs[0] = (float)((double)Tab::rate(rate) * inv_max_rate);                       // qrmsa.pyx:654-665
+            obs[0] = (float)((double)t.rate(rate) * inv_max_rate);                       // qrmsa.pyx:654-665
             obs[1] = (float)(p.N > 1 ? (double)src / (double)(p.N - 1) : 0.0);
             obs[2] = (float)(p.N > 1 ? (double)dst / (double)(p.N - 1) : 0.0);
             mask[n_actions - 1] = 1;                                                        // qrmsa.pyx:766
@@ -746,8 +772,8 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
                 const int l = tid < hops ? __ldg(p.path_links + path * p.Hmax + tid) : 0;
                 sm->link[tid] = l;
                 sm->cnt[tid] = tid < hops ? cnt[l] : 0;
-                sm->w1[tid] = Tab::W1(l);
-                sm->w2[tid] = Tab::W2(l);
+                sm->w1[tid] = t.W1(l);
+                sm->w2[tid] = t.W2(l);
                 const uint32_t a = path_available(dm, bm, hops, l, lane);
                 sm->av[tid] = a;
             }
@@ -769,8 +795,8 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
                     for (int q = 0; q < c; ++q) {
                         const uint32_t v = r[q];
                         const int d = abs((int)(v & 0xfffu) - c2);
-                        s1 += Tab::G(D, (v >> 23) * D + d);
-                        s2 = fma(Tab::PHIN(v >> 20), Tab::INV(d), s2);
+                        s1 += t.G(D, (v >> 23) * D + d);
+                        s2 = fma(t.PHIN(v >> 20), t.INV(d), s2);
                     }
                     x = fma(sm->w1[i], s1, x);
                     x = fma(sm->w2[i], s2, x);
@@ -804,7 +830,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
             if (warp == 0) r = sm->av[lane];
             for (int mi = 0; mi < M; ++mi) {
                 const int m = (M - 1) - mi;
-                const int n = Tab::need(rate * M + m), ncls = Tab::cls(rate * M + m);
+                const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
                 if (warp == 0) {
                     const int L = n + 1;
                     if (L < a) { r = sm->av[lane]; a = 1; }
@@ -818,7 +844,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
                     const bool ok = (sm->valid[s >> 5] >> (s & 31)) & 1u;
                     uint8_t bit = 0;
                     if (ok) {
-                        const double acc = gn_base(p, path, s, n, ncls).with(X[2 * s + n]);
+                        const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
                         const double g = 10.0 * log10(1.0 / acc);
                         const double th = p.mod_thr_nomargin[m];
                         const double nrm = rint(((g - th) / fabs(th)) * 1e10) / 1e10;     // np.round(x, 10), osnr.pyx:366
@@ -840,7 +866,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
                     } else {
                         for (int s = tid; s < S; s += blockDim.x) {
                             if ((sm->valid[s >> 5] >> (s & 31)) & 1u) {
-                                const double acc = gn_base(p, path, s, n, ncls).with(X[2 * s + n]);
+                                const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
                                 const double g = 10.0 * log10(1.0 / acc);
                                 const double th = p.mod_thr_nomargin[m];
                                 const double nrm = rint(((g - th) / fabs(th)) * 1e10) / 1e10;
@@ -989,6 +1015,8 @@ __global__ void k_probe_gsnr(const KParams p, const int env, const int src, cons
                              const int n, double *out) {
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
+    Tab t;
+    t.init();
     const int lane = threadIdx.x & 31;
     if (threadIdx.x >= 32) return;
     const int path = (src * p.N + dst) * p.K + pi;
@@ -1000,12 +1028,12 @@ __global__ void k_probe_gsnr(const KParams p, const int env, const int src, cons
     // class of n: search the class table through NEED/CLS
     int ncls = -1;
     for (int i = 0; i < p.R * p.M; ++i)
-        if (Tab::need(i) == n) ncls = Tab::cls(i);
+        if (t.need(i) == n) ncls = t.cls(i);
     double g = nan("");
     if (ncls >= 0 && hops > 0) {
         uint32_t terms = 0;
-        g = -10.0 * log10(gn_base(p, path, s, n, ncls).with(
-            gn_neighbours(Dim<0, 0, 0>(p), lists, hops, mylink, mycnt, 2 * s + n, lane, terms)));
+        g = -10.0 * log10(gn_base(p, t, path, s, n, ncls).with(
+            gn_neighbours(Dim<0, 0, 0>(p), t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms)));
     }
     if (lane == 0) *out = g;
 }
