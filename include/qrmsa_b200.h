@@ -164,6 +164,15 @@ int qrmsa_load_trace_host_strided(qrmsa_ctx *ctx, const uint8_t *h_src, const ui
 int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream);
 
 /*
+ * Same fused loop with the heuristic chosen by id (the indices examples/JOCN_Benchmark_2024/graph_load.py:116-125
+ * selects by number):
+ *   QRMSA_POLICY_FIRST_FIT       heuristic_shortest_available_path_first_fit_best_modulation (heuristics.py:923-966)
+ *   QRMSA_POLICY_LOAD_BALANCING  load_balancing_best_modulation (heuristics.py:547-627)
+ */
+enum { QRMSA_POLICY_FIRST_FIT = 0, QRMSA_POLICY_LOAD_BALANCING = 1 };
+int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, void *stream);
+
+/*
  * Replaces: QRMSAEnv.step(action) (envs/qrmsa.pyx:838-1065) with one externally chosen action per
  * env (RL path).  d_action int64[n_envs]; outputs (nullable) d_reward float[n_envs]
  * (qrmsa.pyx:992-995, :1266-1285), d_status uint8[n_envs] (QRMSA_STEP_*), d_gsnr double[n_envs],

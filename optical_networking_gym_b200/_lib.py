@@ -28,6 +28,8 @@ ACTION_MASK = 0x00FFFFFF
 FLAG_NEAR_THRESHOLD = 0x80000000
 FLAG_DECIDED = 0x40000000
 FLAG_ACCEPTED = 0x20000000
+POLICY_FIRST_FIT, POLICY_LOAD_BALANCING = 0, 1
+POLICIES = {"first_fit": 0, "load_balancing": 1}
 STEP_ACCEPTED, STEP_REJECT_ACTION, STEP_NOT_FREE, STEP_LOW_GSNR, STEP_IDLE = range(5)
 
 
@@ -88,6 +90,7 @@ SIGNATURES = {
     "qrmsa_load_trace_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "qrmsa_load_trace_host_strided": (_I, [_P, _P, _P, _P, _P, _P, _I, C.c_int64, _P]),
     "qrmsa_step_first_fit": (_I, [_P, _I, _P]),
+    "qrmsa_step_heuristic": (_I, [_P, _I, _I, _P]),
     "qrmsa_step_action": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "qrmsa_observation": (_I, [_P, _P, _P, _P]),
     "qrmsa_observation_dims": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),

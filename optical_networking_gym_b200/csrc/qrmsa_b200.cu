@@ -278,9 +278,11 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     const int wpc = ctx->threads / 32;
     const int want = (n_envs + wpc - 1) / wpc;
     ctx->grid = want < ctx->sm_count * ctas_per_sm ? want : ctx->sm_count * ctas_per_sm;
-    CK(cudaFuncSetAttribute(k_step_first_fit<320, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_first_fit<640, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_first_fit<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_policy<640, 6, 5, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_action, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_probe_gsnr, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_build_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
@@ -444,22 +446,31 @@ extern "C" int qrmsa_load_trace_host_strided(qrmsa_ctx *ctx, const uint8_t *h_sr
     return qrmsa_load_trace(ctx, d_src, d_dst, d_rate, d_arr, d_hold, n_requests, stream);
 }
 
-extern "C" int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream) {
+extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, void *stream) {
     if (!ctx || n_steps < 0) return QRMSA_ERR_ARG;
+    if (policy != QRMSA_POLICY_FIRST_FIT && policy != QRMSA_POLICY_LOAD_BALANCING) { ctx->err = "unknown policy"; return QRMSA_ERR_ARG; }
     if (ctx->kp.n_req < 2) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
     if (n_steps == 0) return QRMSA_OK;
     CK(cudaSetDevice(ctx->device));
     const KParams &kp = ctx->kp;
     cudaStream_t st = (cudaStream_t)stream;
+    const int g = ctx->grid, th = ctx->threads, sm = kp.blob_bytes;
     // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
-    if (kp.S == 320 && kp.M == 6 && kp.K == 5)
-        k_step_first_fit<320, 6, 5><<<ctx->grid, ctx->threads, kp.blob_bytes, st>>>(kp, n_steps);
-    else if (kp.S == 640 && kp.M == 6 && kp.K == 5)
-        k_step_first_fit<640, 6, 5><<<ctx->grid, ctx->threads, kp.blob_bytes, st>>>(kp, n_steps);
-    else
-        k_step_first_fit<0, 0, 0><<<ctx->grid, ctx->threads, kp.blob_bytes, st>>>(kp, n_steps);
+    const bool c320 = kp.S == 320 && kp.M == 6 && kp.K == 5, c640 = kp.S == 640 && kp.M == 6 && kp.K == 5;
+    if (policy == QRMSA_POLICY_FIRST_FIT) {
+        if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+        else if (c640) k_step_policy<640, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+        else k_step_policy<0, 0, 0, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+    } else {
+        if (c320) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
+        else k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
+    }
     CK(cudaGetLastError());
     return QRMSA_OK;
+}
+
+extern "C" int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream) {
+    return qrmsa_step_heuristic(ctx, QRMSA_POLICY_FIRST_FIT, n_steps, stream);
 }
 
 extern "C" int qrmsa_step_action(qrmsa_ctx *ctx, const int64_t *d_action, float *d_reward, uint8_t *d_status,

@@ -413,11 +413,17 @@ __device__ __forceinline__ bool qot_ok(const Tab &t, int m, double acc, uint32_t
 }
 
 // --------------------------------------------------------------------------------------------------------
-// Fused first-fit heuristic + step, n_steps requests per env per launch.
-// heuristics.py:923-966 + qrmsa.pyx:838-1065.
+// Fused heuristic + step, n_steps requests per env per launch (qrmsa.pyx:838-1065 for the step).
+//   POLICY_FIRST_FIT       heuristic_shortest_available_path_first_fit_best_modulation (heuristics.py:923-966;
+//                          shortest_available_path_lowest_spectrum_best_modulation :431-490 decides identically)
+//   POLICY_LOAD_BALANCING  load_balancing_best_modulation (heuristics.py:547-627): among the k paths, the one
+//                          with the lowest (occupied slots of the path availability) / hops that admits a
+//                          modulation; best modulation + first-fit slot on it
 // --------------------------------------------------------------------------------------------------------
-template <int S_, int M_, int K_>
-__global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams p, const int n_steps) {
+enum { POLICY_FIRST_FIT = 0, POLICY_LOAD_BALANCING = 1 };
+
+template <int S_, int M_, int K_, int POLICY>
+__global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p, const int n_steps) {
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
     Tab t;
@@ -456,9 +462,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
             double acc_ok = 1.0;
             int blk_res = 0, blk_osnr = 0;
             bool found = false;
+            // load balancing: best candidate so far (committed after all paths have been looked at)
+            double lowest_load = 1e300;
+            int best_pi = -1, best_m = 0, best_s = 0;
 
 #pragma unroll 1
-            for (int pi = 0; pi < K && !found; ++pi) {
+            for (int pi = 0; pi < K && !(POLICY == POLICY_FIRST_FIT && found); ++pi) {
                 const int path = pbase + pi;
                 const int hp = __ldg(p.path_hops + path);  // bit 7: every neighbour term of this path is >= 0
                 const int hops = hp & 0x7f;
@@ -470,6 +479,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                 const uint32_t av = path_available(dm, bm, hops, mylink, lane);
                 QCNT(QRMSA_CNT_LINKS_READ, hops);
                 QCNT(QRMSA_CNT_PATHS_TRIED, 1);
+                double path_load = 0.0;
+                if (POLICY == POLICY_LOAD_BALANCING) {
+                    // np.sum(available == 0) / len(path.links)  (heuristics.py:569-573); the virtual slot is not a slot
+                    int free_slots = __popc(lane == (S >> 5) ? av & ~(1u << (S & 31)) : av);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) free_slots += __shfl_xor_sync(FULL, free_slots, o);
+                    path_load = (double)(S - free_slots) / (double)hops;
+                    if (path_load >= lowest_load) continue;
+                }
                 uint32_t r = av;
                 int a = 1;
                 bool counted = false;
@@ -500,7 +518,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                     if (prunable && gb.empty() >= t.ACCHI(m)) {  // hopeless even in an empty network
                         QCNT(QRMSA_CNT_GN_PRUNED, 1);
                         blk_osnr = 1;
-                        blk_res = 0;
+                        if (POLICY == POLICY_FIRST_FIT) blk_res = 0;
                         continue;
                     }
                     uint32_t terms = 0;
@@ -510,24 +528,45 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_first_fit(const KParams
                     if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
                     if (qot_ok(t, m, acc, flags)) {
                         found = true;
-                        action = pi * M * S + ((M - 1) - m) * S + s;
                         acc_ok = acc;
-                        const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
-                                             ((uint32_t)ncls << 23);
-                        if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
-                        flags |= QRMSA_FLAG_ACCEPTED;
-                        accepted += 1;
-                        QCNT(QRMSA_CNT_ACCEPTED, 1);
-                        QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate(rate));
-                        QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
-                        QCNT(QRMSA_CNT_MOD_HIST + m, 1);
+                        if (POLICY == POLICY_FIRST_FIT) {
+                            action = pi * M * S + ((M - 1) - m) * S + s;
+                            const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
+                                                 ((uint32_t)ncls << 23);
+                            if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                            QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
+                            QCNT(QRMSA_CNT_MOD_HIST + m, 1);
+                        } else {
+                            lowest_load = path_load;
+                            best_pi = pi; best_m = m; best_s = s;
+                        }
                         break;
                     }
                     blk_osnr = 1;
-                    blk_res = 0;
+                    if (POLICY == POLICY_FIRST_FIT) blk_res = 0;
                 }
             }
-            if (!found) {
+            if (POLICY == POLICY_LOAD_BALANCING && best_pi >= 0) {
+                const int path = pbase + best_pi;
+                const int hops = __ldg(p.path_hops + path) & 0x7f;
+                const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+                const int mycnt = lane < hops ? cnt[mylink] : 0;
+                const int nd = __shfl_sync(FULL, mynd, best_m);
+                const int n = nd & 0xff, ncls = nd >> 8;
+                action = best_pi * M * S + ((M - 1) - best_m) * S + best_s;
+                const uint32_t rec = (uint32_t)(2 * best_s + n) | ((uint32_t)n << 12) | ((uint32_t)best_m << 20) |
+                                     ((uint32_t)ncls << 23);
+                if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, best_s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
+                QCNT(QRMSA_CNT_MOD_HIST + best_m, 1);
+            }
+            if (found) {
+                flags |= QRMSA_FLAG_ACCEPTED;
+                accepted += 1;
+                QCNT(QRMSA_CNT_ACCEPTED, 1);
+                QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate(rate));
+            } else {
+                if (POLICY == POLICY_LOAD_BALANCING && blk_osnr) blk_res = 0;   // heuristics.py:624-626
                 QCNT(QRMSA_CNT_REJECTED, 1);
                 QCNT(QRMSA_CNT_BLOCKED_RESOURCES, blk_res);
                 QCNT(QRMSA_CNT_BLOCKED_OSNR, blk_osnr);

@@ -135,6 +135,11 @@ class Engine:
     def step_first_fit(self, n_steps: int, stream=None):
         check(self.lib.qrmsa_step_first_fit(self._h, int(n_steps), self._stream(stream)), self._h)
 
+    def step_heuristic(self, policy, n_steps: int, stream=None):
+        """policy: "first_fit" | "load_balancing" (or the integer id)."""
+        pid = _lib.POLICIES[policy] if isinstance(policy, str) else int(policy)
+        check(self.lib.qrmsa_step_heuristic(self._h, pid, int(n_steps), self._stream(stream)), self._h)
+
     def step_action(self, action, reward=None, status=None, gsnr=None, terminated=None, stream=None):
         """action: int64 CUDA tensor [n_envs]; outputs are optional preallocated CUDA tensors."""
         def p(x):

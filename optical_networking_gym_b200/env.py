@@ -516,6 +516,15 @@ class BatchedQRMSAEnv(_Common):
             self._observe()
         return n_steps
 
+    def step_heuristic(self, policy: str, n_steps: int = 1):
+        """Fused device policy + step: "first_fit" (heuristics.py:923) or "load_balancing" (heuristics.py:547)."""
+        n_steps = min(int(n_steps), self.episode_length - 1 - self.steps_done)
+        self._eng.step_heuristic(policy, n_steps)
+        self.steps_done += n_steps
+        if n_steps:
+            self._observe()
+        return n_steps
+
     @property
     def terminated(self) -> bool:
         return self.steps_done >= self.episode_length - 1

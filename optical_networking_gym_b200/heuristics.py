@@ -59,3 +59,40 @@ def heuristic_shortest_available_path_first_fit_best_modulation(env):
 
 # identical decisions in the reference (heuristics.py:431-490)
 shortest_available_path_lowest_spectrum_best_modulation = heuristic_shortest_available_path_first_fit_best_modulation
+
+
+def load_balancing_best_modulation(env):
+    """Least-loaded path (occupied slots of the path availability / hops) that admits a modulation; best
+    modulation and first-fit slot on it (heuristics.py:547-627).  Device counterpart: policy "load_balancing"."""
+    import numpy as np
+
+    sim = get_qrmsa_env(env)
+    svc = sim.current_service
+    solution, lowest = None, float("inf")
+    any_res = any_osnr = False
+    for path_idx, path in enumerate(sim.k_shortest_paths[svc.source, svc.destination]):
+        available = sim.get_available_slots(path)
+        load = np.sum(available == 0) / len(path.links)
+        if load >= lowest:
+            continue
+        for modulation_idx in range(sim.max_modulation_idx, -1, -1):
+            modulation = sim.modulations[modulation_idx]
+            n = sim.get_number_slots(svc, modulation)
+            if n <= 0:
+                continue
+            starts = sim._get_candidates(available, n, sim.num_spectrum_resources)
+            if not starts:
+                any_res = True
+                continue
+            svc.path, svc.initial_slot, svc.number_slots, svc.current_modulation = path, starts[0], n, modulation
+            osnr, _, _ = calculate_osnr(sim, svc)
+            if osnr >= modulation.minimum_osnr + sim.margin:
+                lowest = load
+                solution = get_action_index(sim, path_idx, modulation_idx, starts[0])
+                break
+            any_osnr = True
+    if solution is not None:
+        return solution, False, False
+    if any_osnr:
+        any_res = False
+    return sim.action_space.n - 1, any_res, any_osnr

@@ -49,6 +49,8 @@ def lib():
         _lib.orc_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int]
         _lib.orc_run_first_fit.restype = C.c_int
         _lib.orc_run_first_fit.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+        _lib.orc_run_heuristic.restype = C.c_int
+        _lib.orc_run_heuristic.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
         _lib.orc_step_action.restype = C.c_int
         _lib.orc_step_action.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int), C.c_int]
@@ -125,7 +127,7 @@ class OracleEnv:
         self._trace = tr
         lib().orc_reset(self._h, *[_ptr(a) for a in tr], len(tr[0]))
 
-    def run_first_fit(self, n_steps: int, log_qot: bool = True):
+    def run_first_fit(self, n_steps: int, log_qot: bool = True, policy: int = 0):
         action = np.zeros(n_steps, np.int32)
         accepted = np.zeros(n_steps, np.uint8)
         gsnr = np.zeros(n_steps, np.float64)
@@ -134,7 +136,7 @@ class OracleEnv:
         qg = np.zeros(max(cap, 1), np.float64)
         qt = np.zeros(max(cap, 1), np.float64)
         qn = C.c_int(0)
-        rc = lib().orc_run_first_fit(self._h, n_steps, _ptr(action), _ptr(accepted), _ptr(gsnr),
+        rc = lib().orc_run_heuristic(self._h, int(policy), n_steps, _ptr(action), _ptr(accepted), _ptr(gsnr),
                                      _ptr(qs) if log_qot else None, _ptr(qg) if log_qot else None,
                                      _ptr(qt) if log_qot else None, cap, C.byref(qn))
         if rc != 0:

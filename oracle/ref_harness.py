@@ -148,7 +148,8 @@ def first_fit_heuristic():
     return h.heuristic_shortest_available_path_first_fit_best_modulation
 
 
-def run_first_fit(topology, rng_seed: int, n_steps: int, record: bool = True, snapshot_every: int = 0, **kw):
+def run_first_fit(topology, rng_seed: int, n_steps: int, record: bool = True, snapshot_every: int = 0,
+                  heuristic_name: str = "heuristic_shortest_available_path_first_fit_best_modulation", **kw):
     """Run `n_steps` of heuristic+step on one reference env (one episode, no intermediate reset).
 
     Returns a dict of numpy arrays:
@@ -161,7 +162,7 @@ def run_first_fit(topology, rng_seed: int, n_steps: int, record: bool = True, sn
     kw = dict(kw)
     kw["episode_length"] = n_steps + 1
     env = make_env(topology, rng_seed, **kw)
-    heuristic = heur_mod.heuristic_shortest_available_path_first_fit_best_modulation
+    heuristic = getattr(heur_mod, heuristic_name)
     node_index = {n: i for i, n in enumerate(topology.graph["node_indices"])}
     bit_rates = list(env.bit_rates)
 

@@ -119,3 +119,28 @@ def test_snapshots_mid_episode():
         slots = unpack_bitmaps(eng.export_bitmaps(0, 1), S)[0]
         assert np.array_equal(slots, np.unpackbits(snap, axis=1)[:, :S]), f"snapshot at step {step}"
     eng.close()
+
+
+@pytest.mark.parametrize("tag", ["policy_lb_nobel-eu_320_l400_s9", "policy_lb_nsfnet_320_l300_s4"])
+def test_load_balancing_policy_vs_reference(tag):
+    """qrmsa_step_heuristic(QRMSA_POLICY_LOAD_BALANCING) against the reference's load_balancing_best_modulation."""
+    from optical_networking_gym_b200 import _lib
+    from optical_networking_gym_b200.engine import unpack_bitmaps
+
+    topo = tag.split("_")[2]
+    tb, g = load_tables(topo, 320), load_golden(tag)
+    n = len(g["action"])
+    eng = _engine(tb, 1, n + 1)
+    eng.reset(); eng.load_trace_host(*[np.ascontiguousarray(g[k][:, None]) for k in TRACE_KEYS])
+    for c in (3, 500, n - 503):
+        eng.step_heuristic("load_balancing", c)
+    words = eng.actions_host(0, n)
+    actions = (words & _lib.ACTION_MASK).astype(np.int64).T
+    flagged = ((words.view(np.uint32) & _lib.FLAG_NEAR_THRESHOLD) != 0).T
+    n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
+    if n_exc == 0:
+        assert np.abs(eng.gsnr_host(0, n).T[0] - g["gsnr"]).max() < GSNR_TOL_DB
+        assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
+        c = eng.counters_dict()
+        assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
+    eng.close()

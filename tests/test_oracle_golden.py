@@ -121,3 +121,17 @@ def test_oracle_observation_and_mask_vs_reference(tag, topo):
             st, rw, _, _ = o.step_action(int(g["action"][t]), n_req)
             assert st in (0, 1) and rw == pytest.approx(float(g["reward"][t]), abs=1e-12)
     assert np.array_equal(o.slots(), g["final_slots"])
+
+
+@pytest.mark.parametrize("tag,topo", [("policy_lb_nobel-eu_320_l400_s9", "nobel-eu"), ("policy_lb_nsfnet_320_l300_s4", "nsfnet")])
+def test_oracle_load_balancing_vs_reference(tag, topo):
+    """load_balancing_best_modulation (heuristics.py:547-627), the reference benchmark's heuristic #4."""
+    tb, g = load_tables(topo, 320), load_golden(tag)
+    n = len(g["action"])
+    o = orc.OracleEnv(tb, n + 1)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    r = o.run_first_fit(n, policy=1)
+    assert np.array_equal(r["action"], g["action"])
+    assert np.abs(r["gsnr"] - g["gsnr"]).max() < 1e-9
+    assert np.array_equal(r["qot_step"], g["qot_step"]) and np.abs(r["qot_gsnr"] - g["qot_gsnr"]).max() < 1e-9
+    assert np.array_equal(o.slots(), g["final_slots"])

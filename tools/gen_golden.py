@@ -42,6 +42,11 @@ SINGLE = [
     ("nobel-eu_320_l500_s7", "nobel-eu", 320, 500.0, 7, 1500, 500),
     ("ring4_320_l60_s3", "ring4", 320, 60.0, 3, 600, 200),
 ]
+POLICY = [
+    # tag, topology, S, load, seed, steps, reference heuristic
+    ("lb_nobel-eu_320_l400_s9", "nobel-eu", 320, 400.0, 9, 2000, "load_balancing_best_modulation"),
+    ("lb_nsfnet_320_l300_s4", "nsfnet", 320, 300.0, 4, 1500, "load_balancing_best_modulation"),
+]
 MULTI = [
     # tag, topology, S, load, base_seed, n_envs, steps
     ("nobel-eu_320_l300_b50", "nobel-eu", 320, 300.0, 50, 64, 400),
@@ -185,6 +190,17 @@ def main():
         out["meta_load"] = np.float64(load); out["meta_seed"] = np.int64(seed)
         np.savez_compressed(os.path.join(GOLDEN, f"run_{tag}.npz"), **out)
         print(f"run_{tag}: {steps} steps, accept {out['accepted'].mean():.3f}, {time.time() - t0:.1f}s")
+
+    for tag, name, S, load, seed, steps, hname in POLICY:
+        if args.only and args.only not in ("policy_" + tag):
+            continue
+        t0 = time.time()
+        topo = topo_of(name)
+        tables_for(topo, S).save(os.path.join(GOLDEN, f"tables_{name}_{S}.npz"))
+        out, _ = rh.run_first_fit(topo, seed, steps, heuristic_name=hname, n_slots=S, load=load)
+        out["meta_load"] = np.float64(load); out["meta_seed"] = np.int64(seed)
+        np.savez_compressed(os.path.join(GOLDEN, f"policy_{tag}.npz"), **out)
+        print(f"policy_{tag}: {steps} steps, accept {out['accepted'].mean():.3f}, {time.time() - t0:.1f}s")
 
     for tag, name, S, load, base, n_envs, steps in MULTI:
         if args.only and args.only not in tag:
