@@ -208,6 +208,9 @@ int qrmsa_get_actions_host_strided(qrmsa_ctx *ctx, int first, int count, int32_t
                                    void *stream);
 /* GSNR (dB) of the accepted candidate per request (0.0 on reject), needs qrmsa_enable_gsnr_log. */
 int qrmsa_get_gsnr_host(qrmsa_ctx *ctx, int first, int count, double *h_out, void *stream);
+/* ASE-only and NLI-only figures (dB) of the same candidates: the 2nd and 3rd value calculate_osnr returns
+ * (core/osnr.pyx:133-142), written to the reference's per-service CSV (envs/qrmsa.pyx:967-990). */
+int qrmsa_get_ase_nli_host(qrmsa_ctx *ctx, int first, int count, double *h_ase, double *h_nli, void *stream);
 
 /* Per-group counters, int64 [n_groups][QRMSA_N_COUNTERS]; synchronises the stream. */
 int qrmsa_counters(qrmsa_ctx *ctx, int64_t *h_out, void *stream);

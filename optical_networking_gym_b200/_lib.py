@@ -98,6 +98,7 @@ SIGNATURES = {
     "qrmsa_get_actions_host": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_actions_host_strided": (_I, [_P, _I, _I, _P, C.c_int64, _P]),
     "qrmsa_get_gsnr_host": (_I, [_P, _I, _I, _P, _P]),
+    "qrmsa_get_ase_nli_host": (_I, [_P, _I, _I, _P, _P, _P]),
     "qrmsa_counters": (_I, [_P, _P, _P]),
     "qrmsa_counters_device": (_I, [_P, C.POINTER(_P)]),
     "qrmsa_env_state_host": (_I, [_P, _P, _P]),

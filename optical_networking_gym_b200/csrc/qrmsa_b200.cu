@@ -361,9 +361,9 @@ extern "C" int qrmsa_enable_gsnr_log(qrmsa_ctx *ctx, int enable) {
     if (!ctx) return QRMSA_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     if (enable && !ctx->kp.gsnr_log) {
-        int rc = dev_alloc(ctx, &ctx->kp.gsnr_log, (size_t)ctx->kp.n_envs * ctx->kp.T);
+        int rc = dev_alloc(ctx, &ctx->kp.gsnr_log, (size_t)ctx->kp.n_envs * ctx->kp.T * 3);
         if (rc) return rc;
-        CK(cudaMemset(ctx->kp.gsnr_log, 0, sizeof(double) * (size_t)ctx->kp.n_envs * ctx->kp.T));
+        CK(cudaMemset(ctx->kp.gsnr_log, 0, sizeof(double) * (size_t)ctx->kp.n_envs * ctx->kp.T * 3));
     }
     return QRMSA_OK;
 }
@@ -543,7 +543,7 @@ extern "C" int qrmsa_get_actions_host_strided(qrmsa_ctx *ctx, int first, int cou
     return QRMSA_OK;
 }
 
-extern "C" int qrmsa_get_gsnr_host(qrmsa_ctx *ctx, int first, int count, double *h_out, void *stream) {
+static int get_qot_component(qrmsa_ctx *ctx, int first, int count, int comp, double *h_out, void *stream) {
     if (!ctx || !h_out || first < 0 || count < 0 || first + count > ctx->kp.n_req) return QRMSA_ERR_ARG;
     if (!ctx->kp.gsnr_log) { ctx->err = "GSNR log not enabled"; return QRMSA_ERR_STATE; }
     if (count == 0) return QRMSA_OK;
@@ -551,11 +551,20 @@ extern "C" int qrmsa_get_gsnr_host(qrmsa_ctx *ctx, int first, int count, double 
     const size_t bytes = (size_t)count * ctx->kp.n_envs * 8;
     int rc = ensure_stage(ctx, bytes);
     if (rc) return rc;
-    k_gather_gsnr<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(ctx->kp, first, count, (double *)ctx->stage);
+    k_gather_gsnr<<<ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(ctx->kp, first, count, comp, (double *)ctx->stage);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_out, ctx->stage, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return QRMSA_OK;
+}
+
+extern "C" int qrmsa_get_gsnr_host(qrmsa_ctx *ctx, int first, int count, double *h_out, void *stream) {
+    return get_qot_component(ctx, first, count, 0, h_out, stream);
+}
+
+extern "C" int qrmsa_get_ase_nli_host(qrmsa_ctx *ctx, int first, int count, double *h_ase, double *h_nli, void *stream) {
+    int rc = get_qot_component(ctx, first, count, 1, h_ase, stream);
+    return rc ? rc : get_qot_component(ctx, first, count, 2, h_nli, stream);
 }
 
 extern "C" int qrmsa_counters(qrmsa_ctx *ctx, int64_t *h_out, void *stream) {

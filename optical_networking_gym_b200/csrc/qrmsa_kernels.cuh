@@ -66,7 +66,7 @@ struct KParams {
     uint16_t *perm;
     int4 *estate;
     unsigned long long *counters;  // [n_groups][QRMSA_N_COUNTERS]
-    double *gsnr_log;              // nullable, [n_envs][T]
+    double *gsnr_log;              // nullable, [n_envs][T][3] = GSNR, ASE-only, NLI-only in dB (osnr.pyx:138-140)
     size_t bm_stride;              // uint32 words per env
     size_t cnt_stride;             // uint16 per env
 };
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
         uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
         uint32_t *lists = p.lists + (size_t)env * p.E * dm.CAP();
-        double *glog = p.gsnr_log ? p.gsnr_log + (size_t)env * p.T : nullptr;
+        double *glog = p.gsnr_log ? p.gsnr_log + (size_t)env * p.T * 3 : nullptr;
         Head head = load_head(p, tr, perm, rel_ptr);
         uint32_t cnt_reg = 0;
 
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             const int mynd = lane < M ? (t.need(rate * M + lane) | (t.cls(rate * M + lane) << 8)) : 0;
             uint32_t flags = QRMSA_FLAG_DECIDED;
             int action = reject;
-            double acc_ok = 1.0;
+            double acc_ok = 1.0, ase_ok = 0.5;
             int blk_res = 0, blk_osnr = 0;
             bool found = false;
             // load balancing: best candidate so far (committed after all paths have been looked at)
@@ -529,6 +529,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                     if (qot_ok(t, m, acc, flags)) {
                         found = true;
                         acc_ok = acc;
+                        ase_ok = gb.ase;
                         if (POLICY == POLICY_FIRST_FIT) {
                             action = pi * M * S + ((M - 1) - m) * S + s;
                             const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
@@ -576,7 +577,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
             if (lane == 0) {
                 tr[cur].w = (uint32_t)action | flags;
-                if (glog) glog[cur] = found ? -10.0 * log10(acc_ok) : 0.0;  // 10*log10(1/acc), osnr.pyx:138
+                if (glog) {   // 10*log10(1/acc) for the total, ASE-only and NLI-only accumulators (osnr.pyx:133-140)
+                    glog[3 * cur + 0] = found ? -10.0 * log10(acc_ok) : 0.0;
+                    glog[3 * cur + 1] = found ? -10.0 * log10(ase_ok) : 0.0;
+                    glog[3 * cur + 2] = found ? -10.0 * log10(acc_ok - ase_ok) : 0.0;
+                }
             }
             __syncwarp();
             uint32_t n_rel = 0;
@@ -615,7 +620,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
         int cur = st.x, rel_ptr = st.y, accepted = st.z, err = st.w;
         int status = QRMSA_STEP_IDLE;
         float reward = 0.f;
-        double g = 0.0;
+        double g = 0.0, g_ase = 0.0, g_nli = 0.0;
         int term = 0;
         uint32_t cnt_reg = 0;
         if (err == ENV_OK && cur + 1 < p.n_req) {
@@ -660,9 +665,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 } else {
                     const int ncls = t.cls(rate * p.M + m);
                     uint32_t terms = 0;
-                    const double acc = gn_base(p, t, path, s, n, ncls).with(
-                        gn_neighbours(dm, t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
+                    const GnBase gb = gn_base(p, t, path, s, n, ncls);
+                    const double acc = gb.with(gn_neighbours(dm, t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
                     g = -10.0 * log10(acc);
+                    g_ase = -10.0 * log10(gb.ase);
+                    g_nli = -10.0 * log10(acc - gb.ase);
                     if (qot_ok(t, m, acc, flags)) {
                         const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                                              ((uint32_t)ncls << 23);
@@ -688,7 +695,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
                 if (lane == 0) {
                     tr[cur].w = (uint32_t)(status == QRMSA_STEP_ACCEPTED ? (int)a64 : reject) | flags;
-                    if (p.gsnr_log) p.gsnr_log[(size_t)env * p.T + cur] = g;
+                    if (p.gsnr_log) {
+                        double *gl = p.gsnr_log + ((size_t)env * p.T + cur) * 3;
+                        const bool acc_ = status == QRMSA_STEP_ACCEPTED;
+                        gl[0] = acc_ ? g : 0.0; gl[1] = acc_ ? g_ase : 0.0; gl[2] = acc_ ? g_nli : 0.0;
+                    }
                 }
                 __syncwarp();
                 Head head = load_head(p, tr, perm, rel_ptr);
@@ -1041,11 +1052,12 @@ __global__ void k_gather_actions(const KParams p, const int first, const int cou
     }
 }
 
-__global__ void k_gather_gsnr(const KParams p, const int first, const int count, double *__restrict__ out) {
+__global__ void k_gather_gsnr(const KParams p, const int first, const int count, const int comp,
+                              double *__restrict__ out) {
     const size_t n = (size_t)count * p.n_envs;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / p.n_envs), e = (int)(i % p.n_envs);
-        out[i] = p.gsnr_log[(size_t)e * p.T + first + r];
+        out[i] = p.gsnr_log[((size_t)e * p.T + first + r) * 3 + comp];
     }
 }
 

@@ -175,6 +175,12 @@ class Engine:
         check(self.lib.qrmsa_get_gsnr_host(self._h, first, count, _np_ptr(out), self._stream(stream)), self._h)
         return out
 
+    def ase_nli_host(self, first: int, count: int, stream=None):
+        ase = np.empty((count, self.n_envs), np.float64)
+        nli = np.empty((count, self.n_envs), np.float64)
+        check(self.lib.qrmsa_get_ase_nli_host(self._h, first, count, _np_ptr(ase), _np_ptr(nli), self._stream(stream)), self._h)
+        return ase, nli
+
     def counters(self, stream=None) -> np.ndarray:
         out = np.zeros((self.n_groups, _lib.N_COUNTERS), np.int64)
         check(self.lib.qrmsa_counters(self._h, _np_ptr(out), self._stream(stream)), self._h)

@@ -192,3 +192,41 @@ def test_batched_env_masks_rollout():
     c = env.counters()
     assert c["errors"] == 0 and c["decided"] == n_envs * (L - 1)
     env.close()
+
+
+def test_per_service_csv_matches_reference_file():
+    """reporting.service_csv_lines reproduces the per-service CSV the reference itself wrote (qrmsa.pyx:967-990):
+    ids, endpoints, path, modulation and active-service counts exactly, OSNR/ASE/NLI to 1e-6 dB."""
+    from optical_networking_gym_b200 import reporting
+    from optical_networking_gym_b200.engine import Engine
+
+    g = load_golden("csv_nsfnet_320_l300_s77")
+    tb = load_tables("nsfnet", 320)
+    tr = [np.ascontiguousarray(g[k][:, None]) for k in TRACE_KEYS]
+    n = len(g["src"]) - 1
+    eng = Engine(tb, 1, n + 1)
+    eng.enable_gsnr_log(True)
+    eng.reset(); eng.load_trace_host(*tr)
+    eng.step_first_fit(n)
+    words = eng.actions_host(0, n)
+    gsnr = eng.gsnr_host(0, n)
+    ase, nli = eng.ase_nli_host(0, n)
+    lines = reporting.service_csv_lines(tb, tr, words, 0, gsnr, ase, nli)
+    ref_lines = str(g["csv"]).splitlines()
+    assert reporting.SERVICE_HEADER.splitlines() == ref_lines[:2]
+    assert len(lines) == len(ref_lines) - 2 == n
+    n_acc = 0
+    for got, ref in zip(lines, ref_lines[2:]):
+        a, b = got.strip().split(","), ref.split(",")
+        assert len(a) == len(b) == 13
+        for i in (0, 1, 2, 4, 6, 11, 12):
+            assert int(float(a[i])) == int(float(b[i])), (got, ref)
+        for i in (3, 5, 7):
+            assert float(a[i]) == float(b[i]), (got, ref)
+        for i in (8, 9, 10):
+            assert float(a[i]) == pytest.approx(float(b[i]), abs=1e-6), (got, ref)
+        n_acc += b[4] != "-1"
+    assert n_acc == eng.counters_dict()["accepted"]
+    rows = reporting.episode_rows(tb, tr, words, gsnr)
+    assert rows[0]["episode_service_blocking_rate"] == pytest.approx((n + 1 - n_acc) / (n + 1))
+    eng.close()

@@ -251,5 +251,35 @@ def main():
               f"{time.time() - t0:.1f}s")
 
 
+    if not args.only or args.only in "csv_nsfnet":
+        # per-service CSV written by the reference itself (qrmsa.pyx:387-406, :967-990)
+        import glob, tempfile
+        topo = topo_of("nsfnet")
+        tmp = tempfile.mkdtemp()
+        rh_kw = dict(n_slots=320, load=300.0)
+        kw = rh.env_kwargs(topo, episode_length=401, **rh_kw)
+        kw["file_name"] = os.path.join(tmp, "svc")
+        _, ref_qrmsa, _, _ = rh.import_reference()
+        with rh.seeded_random(77):
+            env = ref_qrmsa.QRMSAEnv(**kw)
+        heur = rh.first_fit_heuristic()
+        node_index = {n: i for i, n in enumerate(topo.graph["node_indices"])}
+        rates = list(env.bit_rates)
+        tr = []
+        def req(svc):
+            return (node_index[svc.source], node_index[svc.destination], rates.index(int(svc.bit_rate)),
+                    np.float32(svc.arrival_time), np.float32(svc.holding_time))
+        tr.append(req(env.current_service))
+        for t in range(400):
+            a, _, _ = heur(env)
+            env.step(a)
+            tr.append(req(env.current_service))
+        text = open(glob.glob(os.path.join(tmp, "*.csv"))[0]).read()
+        arr = np.array(tr, dtype=[("src", "u1"), ("dst", "u1"), ("rate", "u1"), ("arrival", "f4"), ("holding", "f4")])
+        np.savez_compressed(os.path.join(GOLDEN, "csv_nsfnet_320_l300_s77.npz"), csv=np.array(text),
+                            **{k: arr[k].copy() for k in arr.dtype.names})
+        print("csv_nsfnet_320_l300_s77:", len(text.splitlines()), "lines")
+
+
 if __name__ == "__main__":
     main()
