@@ -52,6 +52,7 @@ def main():
                           bit_rates=(10, 40, 100, 400, 1000), launch_power_dbm=1.0, bandwidth=args.slots * 12.5e9,
                           seed=args.seed + rank * 10_000_019, n_groups=L, device=local, reset=False)
     env.reset()
+    sharding.allreduce_counters(np.zeros((L, 32), np.int64))   # NCCL communicator set-up is not part of the episode
     t_setup = time.time() - t0
     torch.cuda.synchronize()
     t0 = time.time()
