@@ -13,7 +13,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libqrmsa_b200.so")
+LIB_PATH = os.environ.get("QRMSA_LIB") or os.path.join(HERE, "libqrmsa_b200.so")
 SOURCES = ("qrmsa_b200.cu", "tracegen.cpp")
 HEADERS = ("qrmsa_kernels.cuh", os.path.join("..", "..", "include", "qrmsa_b200.h"))
 
@@ -45,6 +45,8 @@ def _nvcc() -> str:
 
 
 def needs_build() -> bool:
+    if os.environ.get("QRMSA_LIB"):
+        return False   # an explicitly selected prebuilt library (kernel experiments)
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

@@ -269,7 +269,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     // 228 KB for L1 (env state is re-read from L1/L2 across the steps of a launch); QRMSA_CTAS_PER_SM=2 selects
     // two 512-thread CTAs instead (same warps, two table copies) for experiments
     int ctas_per_sm = 1;
-    ctx->threads = 1024;
+    ctx->threads = MAX_THREADS;
     const char *env_ctas = getenv("QRMSA_CTAS_PER_SM");
     if (env_ctas && atoi(env_ctas) == 2 && 2 * (size_t)(kp.blob_bytes + 1024 + 64) <= (size_t)smem_sm) {
         ctas_per_sm = 2;

@@ -37,7 +37,10 @@
 namespace qrmsa {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int MAX_THREADS = 1024;
+#ifndef QRMSA_STEP_THREADS
+#define QRMSA_STEP_THREADS 1024
+#endif
+constexpr int MAX_THREADS = QRMSA_STEP_THREADS;  // threads per CTA of the step kernels (one CTA per SM)
 
 enum EnvError : int {
     ENV_OK = 0,
