@@ -298,7 +298,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         double mx = 0.0;
         for (int r = 0; r < R; r++) mx = std::max(mx, (double)rate_milli[r]);
         ctx->inv_max_rate = mx > 0 ? 1.0 / mx : 0.0;
-        ctx->obs_smem = (size_t)kp.blob_bytes + sizeof(ObsSmem) + (size_t)D * 8 + (size_t)kp.Hmax * kp.CAP * 4;
+        ctx->obs_smem = (size_t)kp.blob_bytes + sizeof(ObsSmem) + (size_t)D * 8 + (size_t)S * 8 + (size_t)kp.Hmax * kp.CAP * 4;
         if ((int)ctx->obs_smem <= ctx->smem_optin) {
             CK(cudaFuncSetAttribute(k_observation, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->obs_smem));
             const int per_sm = (2 * (ctx->obs_smem + 1024) <= (size_t)smem_sm) ? 2 : 1;

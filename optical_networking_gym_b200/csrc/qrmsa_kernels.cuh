@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
 // CTA first builds X[c2] for every c2 (thread per c2: consecutive threads read consecutive G/INV entries, so the
 // shared-memory lookups are conflict-free), then every (modulation, start) is one lookup + log10.
 // --------------------------------------------------------------------------------------------------------
-constexpr int OBS_THREADS = 640;
+constexpr int OBS_THREADS = 320;   // 10 warps; two CTAs per SM overlap each other's barrier waits
 constexpr int OBS_NRED = 6;
 
 struct ObsSmem {           // lives after the table blob in dynamic shared memory
@@ -779,7 +779,7 @@ __device__ __forceinline__ void block_reduce6(ObsSmem *sm, double v[OBS_NRED], c
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(OBS_THREADS, 1)
+__global__ void __launch_bounds__(OBS_THREADS, 2)
     k_observation(const KParams p, const double *__restrict__ path_len_norm, const double inv_max_rate,
                   float *__restrict__ obs_out, uint8_t *__restrict__ mask_out, const int obs_dim, const int n_actions) {
     __shared__ uint64_t mbar;
@@ -791,7 +791,8 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
     unsigned char *extra = qsmem + p.blob_bytes;
     ObsSmem *sm = reinterpret_cast<ObsSmem *>(extra);
     double *X = reinterpret_cast<double *>(extra + sizeof(ObsSmem));          // [D]
-    uint32_t *rec = reinterpret_cast<uint32_t *>(X + D);                        // [Hmax][CAP]
+    double *NRM = X + D;                                                        // [S] normalised GSNR per start
+    uint32_t *rec = reinterpret_cast<uint32_t *>(NRM + p.S);                    // [Hmax][CAP]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int env = blockIdx.x; env < p.n_envs; env += gridDim.x) {
@@ -891,8 +892,9 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
                     sm->valid[lane] = r;
                 }
                 __syncthreads();
-                double v[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};  // count, sum s, sum norm, -, max s, max norm
-                double my_norm = 0.0; bool my_valid = false; int my_s = 0;
+                // count, sum s, sum s^2, sum norm, max s, max norm -- then one more reduction for sum (norm - mean)^2.
+                // Positions are small integers (their sums are exact in FP64), so their variance comes from one pass.
+                double v[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};
                 for (int s = tid; s < S; s += blockDim.x) {
                     const bool ok = (sm->valid[s >> 5] >> (s & 31)) & 1u;
                     uint8_t bit = 0;
@@ -902,9 +904,9 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
                         const double th = p.mod_thr_nomargin[m];
                         const double nrm = rint(((g - th) / fabs(th)) * 1e10) / 1e10;     // np.round(x, 10), osnr.pyx:366
                         bit = nrm >= 0.0 ? 1 : 0;
-                        v[0] += 1.0; v[1] += (double)s; v[2] += nrm;
+                        v[0] += 1.0; v[1] += (double)s; v[2] += (double)s * (double)s; v[3] += nrm;
                         v[4] = fmax(v[4], (double)s); v[5] = fmax(v[5], nrm);
-                        my_norm = nrm; my_valid = true; my_s = s;
+                        NRM[s] = nrm;
                     }
                     mask[(size_t)pi * M * S + (size_t)mi * S + s] = bit;
                 }
@@ -912,25 +914,13 @@ __global__ void __launch_bounds__(OBS_THREADS, 1)
                 const double cntv = v[0];
                 double f_avg = 0, f_std = 0, f_max = 0, best = 0, omean = 0, ovar = 0;
                 if (cntv > 0.0) {
-                    f_avg = v[1] / cntv; omean = v[2] / cntv; f_max = v[4]; best = fmax(v[5], 0.0);
+                    f_avg = v[1] / cntv; omean = v[3] / cntv; f_max = v[4]; best = fmax(v[5], 0.0);
+                    f_std = sqrt(fmax(v[2] / cntv - f_avg * f_avg, 0.0));
                     double w[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};
-                    if (S <= (int)blockDim.x) {
-                        if (my_valid) { const double ds = (double)my_s - f_avg, dn = my_norm - omean; w[0] = ds * ds; w[1] = dn * dn; }
-                    } else {
-                        for (int s = tid; s < S; s += blockDim.x) {
-                            if ((sm->valid[s >> 5] >> (s & 31)) & 1u) {
-                                const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
-                                const double g = 10.0 * log10(1.0 / acc);
-                                const double th = p.mod_thr_nomargin[m];
-                                const double nrm = rint(((g - th) / fabs(th)) * 1e10) / 1e10;
-                                const double ds = (double)s - f_avg, dn = nrm - omean;
-                                w[0] += ds * ds; w[1] += dn * dn;
-                            }
-                        }
-                    }
+                    for (int s = tid; s < S; s += blockDim.x)
+                        if ((sm->valid[s >> 5] >> (s & 31)) & 1u) { const double dn = NRM[s] - omean; w[0] += dn * dn; }
                     block_reduce6(sm, w, 0x30u);
-                    f_std = sqrt(w[0] / cntv);
-                    ovar = w[1] / cntv;
+                    ovar = w[0] / cntv;
                 }
                 if (tid == 0) {
                     float *f = obs + 3 + K + (pi * M + mi) * 12;
