@@ -91,6 +91,8 @@ enum {
 #define QRMSA_FLAG_NEAR_THRESHOLD 0x80000000u /* some evaluated GSNR within 1e-3 dB of its threshold */
 #define QRMSA_FLAG_DECIDED 0x40000000u        /* the request has been decided                        */
 #define QRMSA_FLAG_ACCEPTED 0x20000000u
+#define QRMSA_FLAG_BLOCKED_RESOURCES 0x01000000u /* rejected: the heuristic's blocked_due_to_resources (heuristics.py:966) */
+#define QRMSA_FLAG_BLOCKED_OSNR 0x02000000u      /* rejected: blocked_due_to_osnr                                     */
 
 /* step_action status per env (qrmsa.pyx:838-1065) */
 enum {

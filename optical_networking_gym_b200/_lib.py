@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("QRMSA_LIB") or os.path.join(HERE, "libqrmsa_b200.so")
 SOURCES = ("qrmsa_b200.cu", "tracegen.cpp")
-HEADERS = ("qrmsa_kernels.cuh", os.path.join("..", "..", "include", "qrmsa_b200.h"))
+HEADERS = ("qrmsa_kernels.cuh", "qrmsa_step_sub.cuh", os.path.join("..", "..", "include", "qrmsa_b200.h"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "qrmsa_kernels.cuh"
+#include "qrmsa_step_sub.cuh"
 
 using namespace qrmsa;
 
@@ -18,6 +19,10 @@ struct qrmsa_ctx {
     int smem_optin = 0;
     int threads = 512;
     int grid = 0;
+    int sub_threads = 0;   // k_step_sub: threads per CTA (one CTA per SM)
+    int sub_grid = 0;
+    bool use_warp_kernel = false;
+    size_t sub_smem = 0;
     int n_groups = 1;
     int max_need = 1;
     KParams kp{};
@@ -112,6 +117,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     const int N = t->n_nodes, E = t->n_links, K = t->k_paths, M = t->n_mods, R = t->n_rates, S = t->n_slots;
     kp.n_envs = n_envs; kp.N = N; kp.E = E; kp.K = K; kp.M = M; kp.Mc = t->mods_to_consider; kp.R = R; kp.S = S;
     kp.W = (S + 31) / 32;
+    kp.RW = row_words(S);
     kp.Hmax = t->max_hops;
     kp.D = 2 * S;
     kp.CAP = (int)round_up((size_t)(S + 1) / 2, 32);
@@ -147,8 +153,9 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         for (size_t j = i + 1; j < cls_n.size(); j++)
             if (cls_n[j] < cls_n[i]) std::swap(cls_n[i], cls_n[j]);
     const int NC = (int)cls_n.size();
-    if (NC > 32) { ctx->err = "more than 32 distinct slot counts"; return QRMSA_ERR_UNSUPPORTED; }
+    if (NC > 31) { ctx->err = "more than 31 distinct slot counts"; return QRMSA_ERR_UNSUPPORTED; }
     kp.NC = NC;
+    kp.sentinel = (uint32_t)NC << 23;   // class NC: G row of zeros, PHIN 0
     ctx->cls_n = cls_n;
     ctx->cls.resize((size_t)R * M);
     for (size_t i = 0; i < ctx->need.size(); i++)
@@ -166,7 +173,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     const double alpha = t->link_alpha[0], sb = t->slot_bandwidth_hz, P = t->launch_power_w;
     const double l_eff_a = 1.0 / (2.0 * alpha);
     const int D = kp.D;
-    std::vector<double> G((size_t)NC * D), INV(D), PHIN(256, 0.0), W1(E), W2(E), SELF(NC), CN(NC), ASEC(NC), ACCT(M), ACCLO(M), ACCHI(M);
+    std::vector<double> G((size_t)(NC + 1) * D, 0.0), INV(D), PHIN(256, 0.0), W1(E), W2(E), SELF(NC), CN(NC), ASEC(NC), ACCT(M), ACCLO(M), ACCHI(M);
     for (int c = 0; c < NC; c++) {
         const double bw_r = sb * cls_n[c];
         for (int d = 0; d < D; d++) {
@@ -238,7 +245,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         ctx->err = "table dimension exceeds the shared-memory layout capacity";
         return QRMSA_ERR_UNSUPPORTED;
     }
-    std::vector<unsigned char> blob((size_t)round_up(lay::G(D) + (size_t)NC * D * 8, 16), 0);
+    std::vector<unsigned char> blob((size_t)round_up(lay::G(D) + (size_t)(NC + 1) * D * 8, 16), 0);
     auto put = [&](int off, const void *src, size_t n) { memcpy(blob.data() + off, src, n); };
     put(lay::PHIN, PHIN.data(), PHIN.size() * 8);
     put(lay::W1, W1.data(), W1.size() * 8);
@@ -283,6 +290,29 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_sub<4, 320, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2)));
+    CK(cudaFuncSetAttribute(k_step_sub<8, 640, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2)));
+    CK(cudaFuncSetAttribute(k_step_sub<4, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2)));
+    CK(cudaFuncSetAttribute(k_step_sub<8, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2)));
+    {
+        // k_step_sub: one CTA per SM, env groups (32/LPE envs per warp) handed out by a ticket counter.  The CTA
+        // size is the smallest that keeps the number of rounds: e.g. 65,536 envs / 8 per warp / 148 SMs = 55.4
+        // groups per SM -> 2 rounds of 28 warps rather than 2 rounds of 32 with the second one 73 % full.
+        const int lpe = kp.RW / 4, epw = 32 / lpe;
+        const int groups = (n_envs + epw - 1) / epw;
+        const int wmax = QRMSA_SUB_THREADS / 32;
+        int per_sm = (groups + ctx->sm_count - 1) / ctx->sm_count;
+        int rounds = (per_sm + wmax - 1) / wmax;
+        int w = (per_sm + rounds - 1) / rounds;
+        const char *env_w = getenv("QRMSA_SUB_WARPS");
+        if (env_w && atoi(env_w) >= 1 && atoi(env_w) <= wmax) w = atoi(env_w);
+        ctx->sub_threads = 32 * (w < 1 ? 1 : w);
+        ctx->sub_grid = groups < ctx->sm_count ? groups : ctx->sm_count;
+        const char *impl = getenv("QRMSA_STEP_IMPL");
+        // default: warp per env (k_step_policy); QRMSA_STEP_IMPL=sub selects the lanes-per-env experiment (k_step_sub)
+        ctx->use_warp_kernel = !(impl && !strcmp(impl, "sub")) || t->max_hops > SUB_HCAP;
+        ctx->sub_smem = (size_t)kp.blob_bytes + (size_t)(ctx->sub_threads / 32) * epw * SUB_HCAP * sizeof(uint2);
+    }
     CK(cudaFuncSetAttribute(k_step_action, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_probe_gsnr, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_build_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
@@ -310,12 +340,46 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     if ((rc = dev_upload(ctx, &kp.path_hops, (const uint8_t *)hops_dev.data(), n_paths))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_links, t->path_links, n_paths * t->max_hops))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_gn, pgn.data(), n_paths))) return rc;
+    {
+        // 64-byte path records for k_step_sub: one line holds everything a path needs
+        std::vector<uint32_t> prec(n_paths * 16, 0u);
+        for (size_t pi_ = 0; pi_ < n_paths; pi_++) {
+            uint8_t *b = reinterpret_cast<uint8_t *>(&prec[pi_ * 16]);
+            for (int h = 0; h < t->path_hops[pi_]; h++) b[h] = t->path_links[pi_ * t->max_hops + h];
+            memcpy(&prec[pi_ * 16 + 8], &pgn[pi_].x, 8);
+            memcpy(&prec[pi_ * 16 + 10], &pgn[pi_].y, 8);
+            prec[pi_ * 16 + 12] = hops_dev[pi_];
+            // per bit rate r < 6: bit m = modulation m is refused on the empty-network bound for EVERY start slot,
+            // bit 8+m = for none (the bound is monotone in the centre frequency; the slack covers FMA contraction)
+            const bool prun = (hops_dev[pi_] & 0x80) != 0;
+            for (int r = 0; r < R && r < 6 && t->path_hops[pi_] > 0; r++) {
+                uint32_t mask = 0;
+                for (int m = 0; m < M; m++) {
+                    const int n = ctx->need[(size_t)r * M + m], c = ctx->cls[(size_t)r * M + m];
+                    if (n > S) continue;
+                    auto empty = [&](int s_) {
+                        const double fc = kp.f0 + (kp.sb * (double)s_) + (kp.sb * ((double)n / 2.0));
+                        return ASEC[c] * fc * pgn[pi_].x + CN[c] * (SELF[c] * pgn[pi_].y);
+                    };
+                    if (!prun || empty(S - n) < ACCHI[m] * (1.0 - 1e-12)) mask |= 1u << (8 + m);
+                    else if (empty(0) >= ACCHI[m] * (1.0 + 1e-12)) mask |= 1u << m;
+                }
+                prec[pi_ * 16 + 13 + (r >> 1)] |= mask << ((r & 1) * 16);
+            }
+        }
+        const uint32_t *d = nullptr;
+        if ((rc = dev_upload(ctx, &d, prec.data(), prec.size()))) return rc;
+        kp.prec = reinterpret_cast<const uint4 *>(d);
+        if ((rc = dev_alloc(ctx, &kp.work, 4))) return rc;
+        if ((rc = dev_alloc(ctx, &kp.counted, (size_t)n_envs))) return rc;
+    }
     if ((rc = dev_upload(ctx, &kp.blob, (const unsigned char *)blob.data(), blob.size()))) return rc;
-    kp.bm_stride = round_up((size_t)E * kp.W, 32);
-    kp.cnt_stride = round_up((size_t)E, 64);
+    kp.bm_stride = (size_t)E * kp.RW;
     if ((rc = dev_alloc(ctx, &kp.bm, (size_t)n_envs * kp.bm_stride))) return rc;
-    if ((rc = dev_alloc(ctx, &kp.cnt, (size_t)n_envs * kp.cnt_stride))) return rc;
     if ((rc = dev_alloc(ctx, &kp.lists, (size_t)n_envs * E * kp.CAP))) return rc;
+    kp.pos_bytes = kp.RW == 16 ? 1 : 2;   // k_step_sub<4>: u8, k_step_sub<8>: u16
+    kp.pos_stride = (size_t)E * kp.CAP * kp.pos_bytes;
+    if ((rc = dev_alloc(ctx, &kp.pos, (size_t)n_envs * kp.pos_stride))) return rc;
     if ((rc = dev_alloc(ctx, &kp.trace, (size_t)n_envs * kp.T))) return rc;
     if ((rc = dev_alloc(ctx, &kp.perm, (size_t)n_envs * kp.T))) return rc;
     if ((rc = dev_alloc(ctx, &kp.estate, (size_t)n_envs))) return rc;
@@ -457,13 +521,27 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
     const int g = ctx->grid, th = ctx->threads, sm = kp.blob_bytes;
     // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
     const bool c320 = kp.S == 320 && kp.M == 6 && kp.K == 5, c640 = kp.S == 640 && kp.M == 6 && kp.K == 5;
-    if (policy == QRMSA_POLICY_FIRST_FIT) {
+    if (policy == QRMSA_POLICY_FIRST_FIT && !ctx->use_warp_kernel) {
+        CK(cudaMemsetAsync(kp.work, 0, 4, st));
+        const int sg = ctx->sub_grid, sth = ctx->sub_threads;
+        const size_t ssm = ctx->sub_smem;
+        if (c320) k_step_sub<4, 320, 6, 5><<<sg, sth, ssm, st>>>(kp, n_steps);
+        else if (c640) k_step_sub<8, 640, 6, 5><<<sg, sth, ssm, st>>>(kp, n_steps);
+        else if (kp.RW == 16) k_step_sub<4, 0, 0, 0><<<sg, sth, ssm, st>>>(kp, n_steps);
+        else k_step_sub<8, 0, 0, 0><<<sg, sth, ssm, st>>>(kp, n_steps);
+        CK(cudaGetLastError());
+        k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
+    } else if (policy == QRMSA_POLICY_FIRST_FIT) {
         if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else if (c640) k_step_policy<640, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else {
         if (c320) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
+    }
+    if (policy != QRMSA_POLICY_FIRST_FIT || ctx->use_warp_kernel) {
+        CK(cudaGetLastError());
+        k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
     }
     CK(cudaGetLastError());
     return QRMSA_OK;
@@ -604,9 +682,9 @@ extern "C" int qrmsa_export_bitmaps(qrmsa_ctx *ctx, int first, int count, uint32
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     const KParams &kp = ctx->kp;
-    const size_t row = (size_t)kp.E * kp.W;
-    CK(cudaMemcpy2D(h_out, row * 4, kp.bm + (size_t)first * kp.bm_stride, kp.bm_stride * 4, row * 4, count,
-                    cudaMemcpyDeviceToHost));
+    // rows are RW words apart on the device (bitmap words + padding + the count word); the export is dense
+    CK(cudaMemcpy2D(h_out, (size_t)kp.W * 4, kp.bm + (size_t)first * kp.bm_stride, (size_t)kp.RW * 4, (size_t)kp.W * 4,
+                    (size_t)count * kp.E, cudaMemcpyDeviceToHost));
     return QRMSA_OK;
 }
 
@@ -626,12 +704,12 @@ extern "C" int qrmsa_export_link_list(qrmsa_ctx *ctx, int env, int link, int32_t
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     const KParams &kp = ctx->kp;
-    uint16_t c = 0;
-    CK(cudaMemcpy(&c, kp.cnt + (size_t)env * kp.cnt_stride + link, 2, cudaMemcpyDeviceToHost));
+    uint32_t c = 0;
+    CK(cudaMemcpy(&c, kp.bm + (size_t)env * kp.bm_stride + (size_t)link * kp.RW + kp.RW - 1, 4, cudaMemcpyDeviceToHost));
     std::vector<uint32_t> recs(kp.CAP);
     CK(cudaMemcpy(recs.data(), kp.lists + ((size_t)env * kp.E + link) * kp.CAP, (size_t)kp.CAP * 4, cudaMemcpyDeviceToHost));
-    *n = c;
-    for (int i = 0; i < c && i < cap; i++) {
+    *n = (int)c;
+    for (int i = 0; i < (int)c && i < cap; i++) {
         const uint32_t r = recs[i];
         const int nn = (r >> 12) & 0xff;
         h_out3[3 * i + 0] = ((int)(r & 0xfff) - nn) / 2;

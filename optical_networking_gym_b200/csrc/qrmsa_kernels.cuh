@@ -51,7 +51,8 @@ enum EnvError : int {
 
 struct KParams {
     // dimensions
-    int n_envs, N, E, K, M, Mc, R, S, W, Hmax, NC, D, CAP, T, n_req, group_size;
+    int n_envs, N, E, K, M, Mc, R, S, W, RW, Hmax, NC, D, CAP, T, n_req, group_size;
+    uint32_t sentinel;          // list filler record: class NC (all-zero G row, PHIN 0) -> contributes exactly 0
     double mod_thr_nomargin[8];  // Modulation.minimum_osnr (no margin): the observation's threshold (qrmsa.pyx:743-758)
     int need_monotone;  // slots_needed never decreases as the modulation index falls (true for SE-sorted tables)
     // static tables in global memory
@@ -59,19 +60,24 @@ struct KParams {
     const uint8_t *path_links;  // [N*N*K*Hmax]
     const double2 *path_gn;     // [N*N*K] {PA, PB}
     const unsigned char *blob;  // shared-memory image, 16-byte multiple
+    const uint4 *prec;          // [N*N*K][4] path records (64 B): link ids u8[32] | {PA, PB} | hops (bit 7: prunable)
+    int *work;                  // env-group ticket counter of k_step_sub (zeroed before each launch)
+    uint8_t *pos;               // [n_envs][E][CAP] (u8 if CAP <= 256, else u16): list position of the channel that starts in
+                                // slot pair s>>1 of the link -- lets a release drop its record without searching
+    int pos_bytes;              // 1 or 2
+    size_t pos_stride;          // bytes per env
+    uint32_t *counted;          // [n_envs] requests already covered by k_count_decisions (or counted in-kernel)
     int blob_bytes;
     double f0, sb;
     // per-env state
     uint32_t *bm;
-    uint16_t *cnt;
     uint32_t *lists;
     uint4 *trace;
     uint16_t *perm;
     int4 *estate;
     unsigned long long *counters;  // [n_groups][QRMSA_N_COUNTERS]
     double *gsnr_log;              // nullable, [n_envs][T][3] = GSNR, ASE-only, NLI-only in dB (osnr.pyx:138-140)
-    size_t bm_stride;              // uint32 words per env
-    size_t cnt_stride;             // uint16 per env
+    size_t bm_stride;              // uint32 words per env (= E * RW)
 };
 
 // Shared-memory image of the static tables (byte offsets).  The layout is FIXED (capacities, not sizes) so
@@ -173,6 +179,22 @@ __device__ __forceinline__ void stage_tables(const KParams &p, uint64_t *mbar) {
     }
 }
 
+// Words per link row: bitmap words 0..W-1 (1 = free), word RW-1 = number of channels on the link.  16 words
+// (one 64-byte line, 4 lanes x 16 B) up to 479 slots, 32 words (8 lanes x 16 B) up to 991: the virtual slot at
+// index S must fall before the count word.
+__host__ __device__ constexpr int row_words(int S) { return S <= 479 ? 16 : 32; }
+__device__ __forceinline__ uint32_t *cnt_word(uint32_t *bm, int l, int RW) { return bm + (unsigned)(l * RW + RW - 1); }
+__device__ __forceinline__ const uint32_t *cnt_word(const uint32_t *bm, int l, int RW) { return bm + (unsigned)(l * RW + RW - 1); }
+
+// pos[link][s >> 1] = index of the channel record in the link's list.  A service and its guard slot cover at least
+// one aligned slot pair exclusively, so the pair index identifies the service on that link.
+__device__ __forceinline__ void pos_store(const KParams &p, uint8_t *pos, int l, int pair, int v) {
+    const unsigned i = (unsigned)(l * p.CAP + pair);
+    if (p.pos_bytes == 1) pos[i] = (uint8_t)v;
+    else reinterpret_cast<uint16_t *>(pos)[i] = (uint16_t)v;
+}
+__device__ __forceinline__ int rec_pair(uint32_t rec) { return (int)(((rec & 0xfffu) - ((rec >> 12) & 0xffu)) >> 2); }
+
 // Compile-time problem dimensions (0 = take them from KParams at run time).  Fixing S/M/K removes the
 // integer divisions of the action decode and most address arithmetic from the per-step instruction stream.
 template <int S_, int M_, int K_>
@@ -181,6 +203,7 @@ struct Dim {
     __device__ __forceinline__ explicit Dim(const KParams &kp) : p(kp) {}
     __device__ __forceinline__ int S() const { return S_ ? S_ : p.S; }
     __device__ __forceinline__ int W() const { return S_ ? (S_ + 31) / 32 : p.W; }
+    __device__ __forceinline__ int RW() const { return S_ ? row_words(S_) : p.RW; }
     __device__ __forceinline__ int D() const { return S_ ? 2 * S_ : p.D; }
     __device__ __forceinline__ int CAP() const { return S_ ? ((S_ + 1) / 2 + 31) / 32 * 32 : p.CAP; }
     __device__ __forceinline__ int M() const { return M_ ? M_ : p.M; }
@@ -218,7 +241,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // "n+1 consecutive free slots".  32/W link rows are fetched per pass (3 at W=10), then folded with shuffles.
 template <class DM>
 __device__ __forceinline__ uint32_t path_available(const DM &dm, const uint32_t *bm, int hops, int mylink, int lane) {
-    const int W = dm.W(), S = dm.S();
+    const int W = dm.W(), S = dm.S(), RW = dm.RW();
     const int G = 32 / W;            // link rows per pass
     const int grp = lane / W, j = lane - grp * W;
     uint32_t av = 0xffffffffu;
@@ -226,7 +249,7 @@ __device__ __forceinline__ uint32_t path_available(const DM &dm, const uint32_t 
     for (int i0 = 0; i0 < hops; i0 += G) {
         const int i = i0 + grp;
         const int l = __shfl_sync(FULL, mylink, i & 31);
-        if (grp < G && i < hops) av &= bm[(unsigned)(l * W + j)];  // mutable state: plain (coherent) load
+        if (grp < G && i < hops) av &= bm[(unsigned)(l * RW + j)];  // mutable state: plain (coherent) load
     }
     for (int g = 1; g < G; ++g) av &= __shfl_down_sync(FULL, av, g * W);
     if (lane >= W) av = 0u;
@@ -254,28 +277,47 @@ __device__ __forceinline__ GnBase gn_base(const KParams &p, const Tab &t, int pa
     return b;
 }
 
-// sum over the path's links and every channel on them (same value on every lane)
+// one channel record against a candidate centred at c2 half-slots (core/osnr.pyx:64-94, table form)
+__device__ __forceinline__ void gn_term(const Tab &t, const int D, const uint32_t rec, const int c2, double &s1, double &s2) {
+    const int d = abs((int)(rec & 0xfffu) - c2);
+    s1 += t.G(D, (rec >> 23) * D + d);
+    s2 = fma(t.PHIN(rec >> 20), t.INV(d), s2);
+}
+
+// sum over the path's links and every channel on them (same value on every lane).
+// Lane = (link slot ls = lane >> 3, chunk ck = lane & 7): one pass covers 4 links x 32 records with one 16-byte
+// load per lane.  Lists are padded with the zero-contribution filler record, so a pass needs no bounds test; a
+// link with more than 32 channels takes further passes.
 template <class DM>
 __device__ __forceinline__ double gn_neighbours(const DM &dm, const Tab &t, const uint32_t *lists, int hops, int mylink, int mycnt,
                                                 int c2, int lane, uint32_t &terms) {
     const int D = dm.D(), CAP = dm.CAP();
+    const int ls = lane >> 3, ck = lane & 7;
     double x = 0.0;
+    terms += (uint32_t)__reduce_add_sync(FULL, lane < hops ? mycnt : 0);
 #pragma unroll 1
-    for (int i = 0; i < hops; ++i) {
-        const int l = __shfl_sync(FULL, mylink, i);
-        const int c = __shfl_sync(FULL, mycnt, i);
-        const uint32_t *lst = lists + (unsigned)(l * CAP) + lane;
+    for (int i0 = 0; i0 < hops; i0 += 4) {
+        const int i = i0 + ls;
+        const int l = __shfl_sync(FULL, mylink, i & 31);
+        const int c_any = __shfl_sync(FULL, mycnt, i & 31);   // (every lane takes part in the shuffle)
+        const int c = i < hops ? c_any : 0;
+        const int cmax = __reduce_max_sync(FULL, c);
+        const uint32_t *lp = lists + (unsigned)(l * CAP) + 4 * ck;
         double s1 = 0.0, s2 = 0.0;
-        terms += c;
 #pragma unroll 1
-        for (int q = lane; q < c; q += 32, lst += 32) {
-            const uint32_t rec = *lst;
-            const int d = abs((int)(rec & 0xfffu) - c2);
-            s1 += t.G(D, (rec >> 23) * D + d);
-            s2 = fma(t.PHIN(rec >> 20), t.INV(d), s2);
+        for (int q = 0; q < cmax; q += 32) {
+            if (q < c) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(lp + q);
+                gn_term(t, D, v.x, c2, s1, s2);
+                gn_term(t, D, v.y, c2, s1, s2);
+                gn_term(t, D, v.z, c2, s1, s2);
+                gn_term(t, D, v.w, c2, s1, s2);
+            }
         }
-        x = fma(t.W1(l), s1, x);
-        x = fma(t.W2(l), s2, x);  // W2 is stored negated
+        if (c > 0) {
+            x = fma(t.W1(l), s1, x);
+            x = fma(t.W2(l), s2, x);  // W2 is stored negated
+        }
     }
     return warp_sum(x);
 }
@@ -285,7 +327,7 @@ __device__ __forceinline__ double gn_neighbours(const DM &dm, const Tab &t, cons
 template <bool SET, class DM>
 __device__ __forceinline__ void update_bitmaps(const DM &dm, uint32_t *bm, int hops, int mylink, int s, int e,
                                                int lane) {
-    const int W = dm.W();
+    const int W = dm.W(), RW = dm.RW();
     const int w0 = s >> 5;
     const int k = lane & 3;
     const int j = w0 + k;
@@ -295,7 +337,7 @@ __device__ __forceinline__ void update_bitmaps(const DM &dm, uint32_t *bm, int h
         const int i = i0 + (lane >> 2);
         const int l = __shfl_sync(FULL, mylink, i & 31);
         if (i < hops && mask) {
-            uint32_t *wp = bm + (unsigned)(l * W + j);
+            uint32_t *wp = bm + (unsigned)(l * RW + j);
             *wp = SET ? (*wp | mask) : (*wp & ~mask);
         }
     }
@@ -303,7 +345,7 @@ __device__ __forceinline__ void update_bitmaps(const DM &dm, uint32_t *bm, int h
 
 // qrmsa.pyx:1288-1325 (the release key of :1327-1330 is implicit in the precomputed schedule)
 template <class DM>
-__device__ __forceinline__ int commit(const DM &dm, uint32_t *bm, uint16_t *cnt, uint32_t *lists, int hops,
+__device__ __forceinline__ int commit(const DM &dm, const KParams &p, uint32_t *bm, uint32_t *lists, uint8_t *pos, int hops,
                                       int mylink, int mycnt, int s, int n, uint32_t rec, int lane) {
     int e = s + n;
     if (e < dm.S()) e += 1;
@@ -314,16 +356,18 @@ __device__ __forceinline__ int commit(const DM &dm, uint32_t *bm, uint16_t *cnt,
             err = 1;
         } else {
             lists[(unsigned)(mylink * dm.CAP() + mycnt)] = rec;
-            cnt[mylink] = (uint16_t)(mycnt + 1);
+            pos_store(p, pos, mylink, s >> 1, mycnt);
+            *cnt_word(bm, mylink, dm.RW()) = (uint32_t)(mycnt + 1);
         }
     }
     return __any_sync(FULL, err);
 }
 
-// qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record
+// qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record.
+// Lane i handles hop i: the record's place in the link's list comes from the position table, so there is no search.
 template <class DM>
 __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, const Tab &t, uint32_t *bm,
-                                               uint16_t *cnt, uint32_t *lists, const uint4 rq, int lane) {
+                                               uint32_t *lists, uint8_t *pos, const uint4 rq, int lane) {
     const int S = dm.S(), M = dm.M(), CAP = dm.CAP();
     const uint32_t a = rq.w & QRMSA_ACTION_MASK;
     const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
@@ -335,34 +379,27 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int path = (src * p.N + dst) * dm.K() + pi;
     const int hops = __ldg(p.path_hops + path) & 0x7f;
     const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
-    const int mycnt = lane < hops ? cnt[mylink] : 0;
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                             ((uint32_t)t.cls(rate * M + m) << 23);
     update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
     int err = 0;
-#pragma unroll 1
-    for (int i = 0; i < hops; ++i) {
-        const int l = __shfl_sync(FULL, mylink, i);
-        const int c = __shfl_sync(FULL, mycnt, i);
-        uint32_t *lst = lists + (unsigned)(l * CAP);
-        int found = -1;
-#pragma unroll 1
-        for (int q0 = 0; q0 < c; q0 += 32) {
-            const int q = q0 + lane;
-            const uint32_t v = q < c ? lst[q] : 0xffffffffu;
-            const unsigned hit = __ballot_sync(FULL, v == target);
-            if (hit) {
-                found = q0 + __ffs(hit) - 1;
-                break;
-            }
-        }
-        if (found < 0) {
+    if (lane < hops) {
+        uint32_t *cw = cnt_word(bm, mylink, dm.RW());
+        const int c = (int)*cw;
+        uint32_t *lst = lists + (unsigned)(mylink * CAP);
+        const unsigned pidx = (unsigned)(mylink * CAP + (s >> 1));
+        const int fpos = p.pos_bytes == 1 ? (int)pos[pidx] : (int)reinterpret_cast<const uint16_t *>(pos)[pidx];
+        if (fpos >= c || lst[fpos] != target) {
             err = 1;
-        } else if (lane == 0) {
-            lst[found] = lst[c - 1];
+        } else {
+            const uint32_t last = lst[c - 1];
+            lst[fpos] = last;
+            lst[c - 1] = p.sentinel;   // entries past the count are always the zero-contribution filler
+            pos_store(p, pos, mylink, rec_pair(last), fpos);
+            *cw = (uint32_t)(c - 1);
         }
     }
-    if (lane < hops && mycnt > 0) cnt[mylink] = (uint16_t)(mycnt - 1);
+    err = __any_sync(FULL, err);
     __syncwarp();
     return err;
 }
@@ -389,7 +426,7 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
 // schedule exactly as they are absent from the reference heap.
 template <class DM>
 __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
-                                                   const uint16_t *perm, uint32_t *bm, uint16_t *cnt, uint32_t *lists,
+                                                   const uint16_t *perm, uint32_t *bm, uint32_t *lists, uint8_t *pos,
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
     cur += 1;
     const float now = __uint_as_float(tr[cur].x);
@@ -397,7 +434,7 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];
         if (rq.w & QRMSA_FLAG_ACCEPTED) {
-            err |= release_service(dm, p, t, bm, cnt, lists, rq, lane);
+            err |= release_service(dm, p, t, bm, lists, pos, rq, lane);
             n_rel += 1;
         }
         rel_ptr += 1;
@@ -447,8 +484,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         uint4 *tr = p.trace + (size_t)env * p.T;
         const uint16_t *perm = p.perm + (size_t)env * p.T;
         uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
-        uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
         uint32_t *lists = p.lists + (size_t)env * p.E * dm.CAP();
+        uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
         double *glog = p.gsnr_log ? p.gsnr_log + (size_t)env * p.T * 3 : nullptr;
         Head head = load_head(p, tr, perm, rel_ptr);
         uint32_t cnt_reg = 0;
@@ -477,7 +514,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 if (hops == 0) continue;
                 const bool prunable = (hp & 0x80) != 0;
                 const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
-                const int mycnt = lane < hops ? cnt[mylink] : 0;
+                const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, dm.RW()) : 0;
                 if (lane < hops) prefetch_l1(lists + (unsigned)(mylink * dm.CAP()));  // needed by the GN sum below
                 const uint32_t av = path_available(dm, bm, hops, mylink, lane);
                 QCNT(QRMSA_CNT_LINKS_READ, hops);
@@ -537,9 +574,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                             action = pi * M * S + ((M - 1) - m) * S + s;
                             const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                                                  ((uint32_t)ncls << 23);
-                            if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
-                            QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
-                            QCNT(QRMSA_CNT_MOD_HIST + m, 1);
+                            if (commit(dm, p, bm, lists, pos, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
                         } else {
                             lowest_load = path_load;
                             best_pi = pi; best_m = m; best_s = s;
@@ -554,30 +589,23 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 const int path = pbase + best_pi;
                 const int hops = __ldg(p.path_hops + path) & 0x7f;
                 const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
-                const int mycnt = lane < hops ? cnt[mylink] : 0;
+                const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, dm.RW()) : 0;
                 const int nd = __shfl_sync(FULL, mynd, best_m);
                 const int n = nd & 0xff, ncls = nd >> 8;
                 action = best_pi * M * S + ((M - 1) - best_m) * S + best_s;
                 const uint32_t rec = (uint32_t)(2 * best_s + n) | ((uint32_t)n << 12) | ((uint32_t)best_m << 20) |
                                      ((uint32_t)ncls << 23);
-                if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, best_s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
-                QCNT(QRMSA_CNT_HOPS_ACCEPTED, hops);
-                QCNT(QRMSA_CNT_MOD_HIST + best_m, 1);
+                if (commit(dm, p, bm, lists, pos, hops, mylink, mycnt, best_s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
             }
+            // decided / accepted / rejected / bit rates / hops / modulation histogram / flags are counted from the
+            // decision log by k_count_decisions after the launch (it also maintains the env's accepted total)
             if (found) {
                 flags |= QRMSA_FLAG_ACCEPTED;
-                accepted += 1;
-                QCNT(QRMSA_CNT_ACCEPTED, 1);
-                QCNT(QRMSA_CNT_RATE_PROVISIONED, t.rate(rate));
             } else {
                 if (POLICY == POLICY_LOAD_BALANCING && blk_osnr) blk_res = 0;   // heuristics.py:624-626
-                QCNT(QRMSA_CNT_REJECTED, 1);
-                QCNT(QRMSA_CNT_BLOCKED_RESOURCES, blk_res);
-                QCNT(QRMSA_CNT_BLOCKED_OSNR, blk_osnr);
+                if (blk_res) flags |= QRMSA_FLAG_BLOCKED_RESOURCES;
+                if (blk_osnr) flags |= QRMSA_FLAG_BLOCKED_OSNR;
             }
-            QCNT(QRMSA_CNT_DECIDED, 1);
-            QCNT(QRMSA_CNT_RATE_REQUESTED, t.rate(rate));
-            if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
             if (lane == 0) {
                 tr[cur].w = (uint32_t)action | flags;
                 if (glog) {   // 10*log10(1/acc) for the total, ASE-only and NLI-only accumulators (osnr.pyx:133-140)
@@ -588,11 +616,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             }
             __syncwarp();
             uint32_t n_rel = 0;
-            if (advance_and_release(dm, p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+            if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
         }
-        if (err) QCNT(QRMSA_CNT_ERRORS, 1);
         if (lane == 0) p.estate[env] = make_int4(cur, rel_ptr, accepted, err);
         if (cnt_reg) atomicAdd(p.counters + (size_t)(env / p.group_size) * QRMSA_N_COUNTERS + lane,
                                (unsigned long long)cnt_reg);
@@ -630,8 +657,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
             uint4 *tr = p.trace + (size_t)env * p.T;
             const uint16_t *perm = p.perm + (size_t)env * p.T;
             uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
-            uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
             uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
+            uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
             const uint4 rq = tr[cur];
             const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
             const long long a64 = ext_action[env];
@@ -650,7 +677,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 const int path = (src * p.N + dst) * p.K + pi;
                 const int hops = __ldg(p.path_hops + path) & 0x7f;
                 const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
-                const int mycnt = lane < hops ? cnt[mylink] : 0;
+                const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, dm.RW()) : 0;
                 // is_path_free (qrmsa.pyx:1248-1264): [s, s+n (+1 guard if it ends before S)) free on every link
                 bool free_ok = hops > 0 && s + n <= p.S;
                 if (free_ok) {
@@ -676,7 +703,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                     if (qot_ok(t, m, acc, flags)) {
                         const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                                              ((uint32_t)ncls << 23);
-                        if (commit(dm, bm, cnt, lists, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                        if (commit(dm, p, bm, lists, pos, hops, mylink, mycnt, s, n, rec, lane)) err = ENV_ERR_LIST_OVERFLOW;
                         flags |= QRMSA_FLAG_ACCEPTED;
                         accepted += 1;
                         status = QRMSA_STEP_ACCEPTED;
@@ -707,13 +734,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 __syncwarp();
                 Head head = load_head(p, tr, perm, rel_ptr);
                 uint32_t n_rel = 0;
-                if (advance_and_release(dm, p, t, tr, perm, bm, cnt, lists, cur, rel_ptr, head, lane, n_rel))
+                if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel))
                     err = ENV_ERR_RELEASE_NOT_FOUND;
                 QCNT(QRMSA_CNT_RELEASES, n_rel);
                 term = (cur + 1 == episode_length);  // episode_services_processed == episode_length (qrmsa.pyx:1056)
             }
             if (err) QCNT(QRMSA_CNT_ERRORS, 1);
-            if (lane == 0) p.estate[env] = make_int4(cur, rel_ptr, accepted, err);
+            if (lane == 0) { p.estate[env] = make_int4(cur, rel_ptr, accepted, err); p.counted[env] = (uint32_t)cur; }
             if (cnt_reg) atomicAdd(p.counters + (size_t)(env / p.group_size) * QRMSA_N_COUNTERS + lane,
                                    (unsigned long long)cnt_reg);
         }
@@ -803,7 +830,6 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
         const uint4 rq = p.trace[(size_t)env * p.T + cur];
         const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
         const uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
-        const uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
         const uint32_t *lists = p.lists + (size_t)env * p.E * CAP;
         const int pbase = (src * p.N + dst) * K;
         if (tid == 0) {
@@ -825,7 +851,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
             if (tid < 32) {
                 const int l = tid < hops ? __ldg(p.path_links + path * p.Hmax + tid) : 0;
                 sm->link[tid] = l;
-                sm->cnt[tid] = tid < hops ? cnt[l] : 0;
+                sm->cnt[tid] = tid < hops ? (int)bm[(unsigned)(l * p.RW + p.RW - 1)] : 0;
                 sm->w1[tid] = t.W1(l);
                 sm->w2[tid] = t.W2(l);
                 const uint32_t a = path_available(dm, bm, hops, l, lane);
@@ -951,20 +977,18 @@ __global__ void k_reset(const KParams p) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t words = (size_t)p.n_envs * p.bm_stride;
-    const int rowwords = p.E * p.W;
     for (size_t i = tid; i < words; i += nthreads) {
-        const int k = (int)(i % p.bm_stride);
+        const int j = (int)(i % p.RW);   // word of the link row; the count word (RW-1) and the padding start at 0
         uint32_t v = 0u;
-        if (k < rowwords) {
-            const int j = k % p.W;
+        if (j < p.W) {
             const int left = p.S - (j << 5);
             v = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
         }
         p.bm[i] = v;
     }
-    const size_t ncnt = (size_t)p.n_envs * p.cnt_stride;
-    for (size_t i = tid; i < ncnt; i += nthreads) p.cnt[i] = 0;
-    for (size_t i = tid; i < (size_t)p.n_envs; i += nthreads) p.estate[i] = make_int4(0, 0, 0, 0);
+    const size_t nrec = (size_t)p.n_envs * p.E * p.CAP;
+    for (size_t i = tid; i < nrec; i += nthreads) p.lists[i] = p.sentinel;
+    for (size_t i = tid; i < (size_t)p.n_envs; i += nthreads) { p.estate[i] = make_int4(0, 0, 0, 0); p.counted[i] = 0u; }
 }
 
 // Request-major SoA [n_req][n_envs] -> per-env AoS records, through a shared-memory tile so that both the
@@ -1065,10 +1089,10 @@ __global__ void k_probe_gsnr(const KParams p, const int env, const int src, cons
     if (threadIdx.x >= 32) return;
     const int path = (src * p.N + dst) * p.K + pi;
     const int hops = __ldg(p.path_hops + path) & 0x7f;
-    const uint16_t *cnt = p.cnt + (size_t)env * p.cnt_stride;
     const uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
+    const uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
     const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
-    const int mycnt = lane < hops ? cnt[mylink] : 0;
+    const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, p.RW) : 0;
     // class of n: search the class table through NEED/CLS
     int ncls = -1;
     for (int i = 0; i < p.R * p.M; ++i)

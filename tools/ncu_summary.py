@@ -76,18 +76,19 @@ def main():
 
     src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
     ops, lines, text = collections.Counter(), collections.Counter(), {}
+    fname = ''
     stall = collections.Counter()
     infile, cur, tot, hdr_row = False, None, 0, None
     for r in src:
         if len(r) >= 2 and r[0] == "File Path":
-            infile = r[1].endswith("qrmsa_kernels.cuh"); cur = None; continue
+            infile = r[1].endswith(".cuh"); fname = os.path.basename(r[1]); cur = None; continue
         if len(r) >= 8 and r[0] == "Line No":
             hdr_row = r; continue
         if len(r) < 8:
             continue
         if r[0] != "":
             try:
-                cur = int(r[0]); text[cur] = r[1].strip()
+                cur = (fname, int(r[0])); text[cur] = r[1].strip()
             except ValueError:
                 cur = None
             continue
@@ -108,9 +109,9 @@ def main():
         f.write(f"warp-instructions per launch {tot:.4g}" + (f" = {tot / per:.0f} per env-step" if env_steps else "") + "\n\n")
         f.write("## SASS opcode mix (per env-step)\n\n" if env_steps else "## SASS opcode mix\n\n")
         f.write(", ".join(f"{o} {n / per:.1f}" for o, n in ops.most_common(30)) + "\n\n")
-        f.write("## hottest source lines (warp-instructions per env-step, qrmsa_kernels.cuh)\n\n| line | instr | source |\n|---|---|---|\n")
-        for ln, n in lines.most_common(45):
-            f.write(f"| {ln} | {n / per:.1f} | `{text[ln][:110]}` |\n")
+        f.write("## hottest source lines (warp-instructions per env-step, csrc/*.cuh)\n\n| line | instr | source |\n|---|---|---|\n")
+        for ln, n in lines.most_common(70):
+            f.write(f"| {ln[0].replace('qrmsa_', '').replace('.cuh', '')}:{ln[1]} | {n / per:.1f} | `{text[ln][:110]}` |\n")
     print(json.dumps(traffic))
 
 
