@@ -285,36 +285,45 @@ __device__ __forceinline__ void gn_term(const Tab &t, const int D, const uint32_
 }
 
 // sum over the path's links and every channel on them (same value on every lane).
-// Lane = (link slot ls = lane >> 3, chunk ck = lane & 7): one pass covers 4 links x 32 records with one 16-byte
-// load per lane.  Lists are padded with the zero-contribution filler record, so a pass needs no bounds test; a
-// link with more than 32 channels takes further passes.
+// The path's lists are cut into groups of 4 records (one 16-byte load) and the groups of ALL links are dealt out
+// to the lanes in one flat sequence: lane t of pass b takes group b + t, which belongs to the hop whose group range
+// [start, end) contains it.  A typical path (4 hops x 28 channels = 30 groups) is one pass with every lane busy.
+// Lists are padded with the zero-contribution filler record, so the last group of a link needs no bounds test.
 template <class DM>
 __device__ __forceinline__ double gn_neighbours(const DM &dm, const Tab &t, const uint32_t *lists, int hops, int mylink, int mycnt,
                                                 int c2, int lane, uint32_t &terms) {
     const int D = dm.D(), CAP = dm.CAP();
-    const int ls = lane >> 3, ck = lane & 7;
+    const int cnt = lane < hops ? mycnt : 0;
+    terms += (uint32_t)__reduce_add_sync(FULL, cnt);
+    // groups of this lane's hop (an empty link still gets one group of fillers, so that every hop owns a distinct
+    // start), then an inclusive prefix sum over the hops
+    const int mine = lane < hops ? max((cnt + 3) >> 2, 1) : 0;
+    int end = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, end, o);
+        if (lane >= o) end += v;
+    }
+    const int total = __shfl_sync(FULL, end, 31);
+    const int start = end - mine;
     double x = 0.0;
-    terms += (uint32_t)__reduce_add_sync(FULL, lane < hops ? mycnt : 0);
 #pragma unroll 1
-    for (int i0 = 0; i0 < hops; i0 += 4) {
-        const int i = i0 + ls;
-        const int l = __shfl_sync(FULL, mylink, i & 31);
-        const int c_any = __shfl_sync(FULL, mycnt, i & 31);   // (every lane takes part in the shuffle)
-        const int c = i < hops ? c_any : 0;
-        const int cmax = __reduce_max_sync(FULL, c);
-        const uint32_t *lp = lists + (unsigned)(l * CAP) + 4 * ck;
-        double s1 = 0.0, s2 = 0.0;
-#pragma unroll 1
-        for (int q = 0; q < cmax; q += 32) {
-            if (q < c) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(lp + q);
-                gn_term(t, D, v.x, c2, s1, s2);
-                gn_term(t, D, v.y, c2, s1, s2);
-                gn_term(t, D, v.z, c2, s1, s2);
-                gn_term(t, D, v.w, c2, s1, s2);
-            }
-        }
-        if (c > 0) {
+    for (int b = 0; b < total; b += 32) {
+        // hop of group g = b + lane: number of hops that start at or before g, minus one.  The starts inside this
+        // pass are marked in a 32-bit mask (OR over the hop lanes), the ones before it are counted by a ballot.
+        const int rel = start - b;
+        const uint32_t mark = __reduce_or_sync(FULL, (lane < hops && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+        const int before = __popc(__ballot_sync(FULL, lane < hops && rel < 0));
+        const int hop = before + __popc(mark & (0xffffffffu >> (31 - lane))) - 1;
+        const int l = __shfl_sync(FULL, mylink, hop & 31);
+        const int off = b + lane - __shfl_sync(FULL, start, hop & 31);
+        if (b + lane < total) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(lists + (unsigned)(l * CAP) + 4 * off);
+            double s1 = 0.0, s2 = 0.0;
+            gn_term(t, D, v.x, c2, s1, s2);
+            gn_term(t, D, v.y, c2, s1, s2);
+            gn_term(t, D, v.z, c2, s1, s2);
+            gn_term(t, D, v.w, c2, s1, s2);
             x = fma(t.W1(l), s1, x);
             x = fma(t.W2(l), s2, x);  // W2 is stored negated
         }
