@@ -9,7 +9,8 @@ k=5, 6 modulations, first-fit heuristic, load 300 Erlang, launch power 1 dBm, bi
 (10,40,100,400,1000), env i replaying the request stream random.Random(50 + i).
 
 A bench "step" = one pass of the fused hot path over one batch of synthetic input = ONE kernel
-launch that advances every env by `chunk` requests (default 128).  Before the timed region every
+launch of the step kernel (followed by the small decision-log counting kernel) that advances every env by
+`chunk` requests (default 128).  Before the timed region every
 env is brought to steady state by an untimed prefill of 1000 requests from the empty network
 (SURVEY §8d C2).  `value` = env-steps/s with the trace resident in HBM; `e2e` = the same metric
 through the host-buffer C-ABI calls for a whole episode (reset + H2D of the trace from pinned memory
@@ -65,53 +66,68 @@ def workload_name(n_envs):
 # clocks: sample nvidia-smi DURING the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    """SM clock, power and throttle reasons sampled every few ms by an NVML thread while the timed region runs
+    (nvidia-smi -lms takes longer to start than the region lasts); falls back to one nvidia-smi query."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.proc = None
+        self.gpu = gpu_index
+        self.sm, self.power, self.reasons, self.mx = [], [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        try:
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(get(self.h))
+            for bit, name in self.BITS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.004)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.tmp.flush()
-        self.tmp.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
-        for line in self.tmp.read().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(self.NAMES, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.tmp.name)
-        except OSError:
-            pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(power))
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        elif self.nv is None:
+            try:   # no NVML binding: one nvidia-smi query right after the region
+                q = "clocks.sm,clocks.max.sm,power.draw"
+                f = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                self.sm, self.mx, self.power = [float(f[0])], float(f[1]), [float(f[2])]
+            except Exception:
+                pass
+        if self.sm:
+            sm = sorted(self.sm)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.mx, reasons=sorted(self.reasons), samples=len(sm),
+                       power_w_max=max(self.power) if self.power else None)
         return out
 
 
@@ -349,7 +365,7 @@ def run_b200(args, rank, local_rank, world):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_step_first_fit", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "k_step_policy<320,6,5,first_fit> (+ k_count_decisions, <1 % of the launch)", "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": bytes_step, "env_steps_per_launch": n_envs * chunk,
                 "avg_launch_ms": avg_launch_s * 1e3, "workload_params": params}
 
@@ -408,9 +424,9 @@ def run_b200(args, rank, local_rank, world):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n_envs), "chunk_requests_per_env_per_step": chunk,
                        "episode_requests": n_req, "l2_policy": "inputs larger than L2 (per-GPU env state + trace "
-                       f"touched per step >= {n_envs * (tb.n_links * 40 + 16 * chunk) / 1e6:.0f} MB)",
+                       f"touched per step >= {n_envs * (tb.n_links * 64 + 16 * chunk) / 1e6:.0f} MB)",
                        "trace": f"CPython-random-exact streams, seeds {BASE_SEED}+i, generated on host in {t_gen:.1f}s"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     eng.close()

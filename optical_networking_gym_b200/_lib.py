@@ -28,6 +28,8 @@ ACTION_MASK = 0x00FFFFFF
 FLAG_NEAR_THRESHOLD = 0x80000000
 FLAG_DECIDED = 0x40000000
 FLAG_ACCEPTED = 0x20000000
+FLAG_BLOCKED_RESOURCES = 0x01000000   # rejected requests: the heuristic's blocked_due_to_resources
+FLAG_BLOCKED_OSNR = 0x02000000        # rejected requests: blocked_due_to_osnr
 POLICY_FIRST_FIT, POLICY_LOAD_BALANCING = 0, 1
 POLICIES = {"first_fit": 0, "load_balancing": 1}
 STEP_ACCEPTED, STEP_REJECT_ACTION, STEP_NOT_FREE, STEP_LOW_GSNR, STEP_IDLE = range(5)

@@ -144,3 +144,71 @@ def test_load_balancing_policy_vs_reference(tag):
         c = eng.counters_dict()
         assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("tag", ["multi_nobel-eu_320_l300_b50", "multi_germany50_640_l800_b50"])
+def test_lanes_per_env_experiment_matches_product_kernel(tag, monkeypatch):
+    """k_step_sub (QRMSA_STEP_IMPL=sub, csrc/qrmsa_step_sub.cuh) must reproduce the product kernel word for word:
+    action words including every flag, bitmaps, channel lists, env state and counters."""
+    from optical_networking_gym_b200.engine import Engine
+
+    topo, S = parse_tag(tag)
+    tb = load_tables(topo, S)
+    g = load_golden(tag)
+    tr = [np.ascontiguousarray(g[k].T) for k in TRACE_KEYS]
+    n_req, n_envs = tr[0].shape
+    out = {}
+    for impl in ("warp", "sub"):
+        monkeypatch.setenv("QRMSA_STEP_IMPL", impl)   # read by qrmsa_create
+        eng = Engine(tb, n_envs, n_req)
+        eng.reset()
+        eng.load_trace_host(*tr)
+        for c in (3, 50, n_req - 1 - 53):
+            eng.step_first_fit(c)
+        lists = [eng.export_link_list(e, l) for e in (0, n_envs - 1) for l in range(tb.n_links)]
+        out[impl] = (eng.actions_host(0, n_req - 1).copy(), eng.export_bitmaps(0, n_envs).copy(), eng.env_state().copy(),
+                     eng.counters().copy(), [sorted(map(tuple, x)) for x in lists])
+        eng.close()
+    a, b = out["warp"], out["sub"]
+    assert np.array_equal(a[0], b[0]), "action words differ"
+    assert np.array_equal(a[1], b[1]), "bitmaps differ"
+    assert np.array_equal(a[2], b[2]), "env state differs"
+    assert np.array_equal(a[3], b[3]), "counters differ"
+    assert a[4] == b[4], "channel lists differ"
+
+
+def test_blocked_by_flags_and_log_counters():
+    """Rejected requests carry the heuristic's (blocked_due_to_resources, blocked_due_to_osnr) pair in the action word
+    (heuristics.py:966); the counters k_count_decisions derives from the log must equal a recount on the host."""
+    from optical_networking_gym_b200 import _lib
+    from optical_networking_gym_b200.engine import Engine
+
+    tag = "multi_nobel-eu_320_l300_b50"
+    topo, S = parse_tag(tag)
+    tb = load_tables(topo, S)
+    g = load_golden(tag)
+    tr = [np.ascontiguousarray(g[k].T) for k in TRACE_KEYS]
+    n_req, n_envs = tr[0].shape
+    eng = Engine(tb, n_envs, n_req)
+    eng.reset()
+    eng.load_trace_host(*tr)
+    for c in (100, n_req - 1 - 100):
+        eng.step_first_fit(c)
+    w = eng.actions_host(0, n_req - 1).view(np.uint32)
+    acc = (w & _lib.FLAG_ACCEPTED) != 0
+    res = (w & _lib.FLAG_BLOCKED_RESOURCES) != 0
+    osn = (w & _lib.FLAG_BLOCKED_OSNR) != 0
+    assert ((w & _lib.FLAG_DECIDED) != 0).all()
+    assert not (acc & (res | osn)).any()          # the pair is only reported with the reject action
+    assert ((res | osn) | acc).all()              # a reject always has a cause
+    c = eng.counters_dict()
+    assert c["decided"] == w.size and c["accepted"] == int(acc.sum()) and c["rejected"] == int((~acc).sum())
+    assert c["blocked_resources"] == int(res.sum()) and c["blocked_osnr"] == int(osn.sum())
+    assert c["near_threshold"] == int(((w & _lib.FLAG_NEAR_THRESHOLD) != 0).sum())
+    rates = np.asarray(tb.bit_rates)[tr[2][: n_req - 1]]
+    assert c["rate_requested_milli"] == int(np.rint(rates * 1000).sum())
+    assert c["rate_provisioned_milli"] == int(np.rint(rates[acc] * 1000).sum())
+    m_idx = (tb.n_mods - 1) - ((w & _lib.ACTION_MASK) // tb.n_slots) % tb.n_mods
+    assert np.array_equal(c["mod_hist"][: tb.n_mods], np.bincount(m_idx[acc], minlength=tb.n_mods))
+    assert np.array_equal(eng.env_state()[:, 1], acc.sum(0))
+    eng.close()
