@@ -154,6 +154,23 @@ int qrmsa_load_trace_host_strided(qrmsa_ctx *ctx, const uint8_t *h_src, const ui
                                   void *stream);
 
 /*
+ * Replaces: the same draws of QRMSAEnv._next_service / _get_node_pair (envs/qrmsa.pyx:1079-1099, :1134-1148) made ON
+ * THE DEVICE for the next n_requests requests of every env: exponential inter-arrival and holding times
+ * rounded to float32, the float32 clock, source / destination / bit rate by bisecting the cumulative-weight tables
+ * (built by the caller exactly as for qrmsa_tracegen_create), drawn from a Philox4x32-10 stream keyed by
+ * (seed, env_offset + env, request index).  The streams do not depend on how envs are split over contexts / GPUs;
+ * they are not CPython's MT19937 streams (for replay parity with the reference use qrmsa_tracegen_* +
+ * qrmsa_load_trace_host).  restart != 0 zeroes the clocks and the request counter; otherwise the streams continue
+ * where the previous call stopped.  Also builds the release schedule, like qrmsa_load_trace.
+ */
+int qrmsa_generate_trace(qrmsa_ctx *ctx, uint64_t seed, int restart, int64_t env_offset, const double *h_load,
+                         double mean_holding_time, const double *h_src_cum, const double *h_dst_cum,
+                         const double *h_rate_cum, int n_requests, void *stream);
+/* The loaded / generated request stream, requests [first, first+count), arrays [count][n_envs]; synchronises. */
+int qrmsa_get_trace_host(qrmsa_ctx *ctx, int first, int count, uint8_t *h_src, uint8_t *h_dst, uint8_t *h_rate,
+                         float *h_arrival, float *h_holding, void *stream);
+
+/*
  * Replaces: n_steps iterations of the benchmark loop
  *     action, _, _ = heuristic_shortest_available_path_first_fit_best_modulation(env)
  *     env.step(action)

@@ -93,6 +93,8 @@ SIGNATURES = {
     "qrmsa_load_trace": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "qrmsa_load_trace_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "qrmsa_load_trace_host_strided": (_I, [_P, _P, _P, _P, _P, _P, _I, C.c_int64, _P]),
+    "qrmsa_generate_trace": (_I, [_P, _U64, _I, C.c_int64, _P, C.c_double, _P, _P, _P, _I, _P]),
+    "qrmsa_get_trace_host": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "qrmsa_step_first_fit": (_I, [_P, _I, _P]),
     "qrmsa_step_heuristic": (_I, [_P, _I, _I, _P]),
     "qrmsa_step_action": (_I, [_P, _P, _P, _P, _P, _P, _P]),

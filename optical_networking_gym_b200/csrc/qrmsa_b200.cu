@@ -23,6 +23,10 @@ struct qrmsa_ctx {
     int sub_grid = 0;
     bool use_warp_kernel = false;
     size_t sub_smem = 0;
+    // on-device request generator
+    float *gen_clock = nullptr;
+    double *gen_tables = nullptr;   // load[n_envs] | src_cum[N] | dst_cum[N*N] | rate_cum[R]
+    unsigned long long gen_pos = 0;
     int n_groups = 1;
     int max_need = 1;
     KParams kp{};
@@ -443,6 +447,8 @@ extern "C" int qrmsa_reset(qrmsa_ctx *ctx, void *stream) {
     return QRMSA_OK;
 }
 
+static int build_schedule(qrmsa_ctx *ctx, int n_requests, cudaStream_t st);
+
 extern "C" int qrmsa_load_trace(qrmsa_ctx *ctx, const uint8_t *d_src, const uint8_t *d_dst, const uint8_t *d_rate,
                                 const float *d_arrival, const float *d_holding, int n_requests, void *stream) {
     if (!ctx || !d_src || !d_dst || !d_rate || !d_arrival || !d_holding) return QRMSA_ERR_ARG;
@@ -454,13 +460,7 @@ extern "C" int qrmsa_load_trace(qrmsa_ctx *ctx, const uint8_t *d_src, const uint
     dim3 grid((kp.n_envs + 31) / 32, (n_requests + 31) / 32);
     k_ingest_trace<<<grid, 256, 0, st>>>(kp, d_src, d_dst, d_rate, d_arrival, d_holding, n_requests);
     CK(cudaGetLastError());
-    int n_pad = 2;
-    while (n_pad < n_requests) n_pad <<= 1;
-    int threads = n_pad / 2 < 1024 ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : 1024;
-    int blocks = kp.n_envs < ctx->sm_count * 8 ? kp.n_envs : ctx->sm_count * 8;
-    k_build_schedule<<<blocks, threads, (size_t)n_pad * 8, st>>>(kp, n_requests, n_pad);
-    CK(cudaGetLastError());
-    return QRMSA_OK;
+    return build_schedule(ctx, n_requests, st);
 }
 
 extern "C" int qrmsa_load_trace_host(qrmsa_ctx *ctx, const uint8_t *h_src, const uint8_t *h_dst, const uint8_t *h_rate,
@@ -508,6 +508,80 @@ extern "C" int qrmsa_load_trace_host_strided(qrmsa_ctx *ctx, const uint8_t *h_sr
     CK(cudaMemcpy2DAsync(d_dst, ne, h_dst, rs, ne, n_requests, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpy2DAsync(d_rate, ne, h_rate, rs, ne, n_requests, cudaMemcpyHostToDevice, st));
     return qrmsa_load_trace(ctx, d_src, d_dst, d_rate, d_arr, d_hold, n_requests, stream);
+}
+
+static int build_schedule(qrmsa_ctx *ctx, int n_requests, cudaStream_t st) {
+    const KParams &kp = ctx->kp;
+    int n_pad = 2;
+    while (n_pad < n_requests) n_pad <<= 1;
+    int threads = n_pad / 2 < 1024 ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : 1024;
+    int blocks = kp.n_envs < ctx->sm_count * 8 ? kp.n_envs : ctx->sm_count * 8;
+    k_build_schedule<<<blocks, threads, (size_t)n_pad * 8, st>>>(kp, n_requests, n_pad);
+    CK(cudaGetLastError());
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_generate_trace(qrmsa_ctx *ctx, uint64_t seed, int restart, int64_t env_offset, const double *h_load,
+                                    double mean_holding_time, const double *h_src_cum, const double *h_dst_cum,
+                                    const double *h_rate_cum, int n_requests, void *stream) {
+    if (!ctx || !h_load || !h_src_cum || !h_dst_cum || !h_rate_cum || !(mean_holding_time > 0) || env_offset < 0) return QRMSA_ERR_ARG;
+    if (n_requests < 1 || n_requests > ctx->kp.T) { ctx->err = "n_requests outside 1..max_requests"; return QRMSA_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    KParams &kp = ctx->kp;
+    const size_t ne = (size_t)kp.n_envs, N = (size_t)kp.N, R = (size_t)kp.R;
+    for (size_t i = 0; i < ne; i++)
+        if (!(h_load[i] > 0)) { ctx->err = "load must be positive"; return QRMSA_ERR_ARG; }
+    if (!ctx->gen_clock) {
+        int rc = dev_alloc(ctx, &ctx->gen_clock, ne);
+        if (rc) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->gen_tables, ne + N + N * N + R))) return rc;
+        restart = 1;
+    }
+    if (restart) {
+        CK(cudaMemsetAsync(ctx->gen_clock, 0, ne * sizeof(float), st));
+        ctx->gen_pos = 0;
+    }
+    double *d_load = ctx->gen_tables, *d_src = d_load + ne, *d_dst = d_src + N, *d_rate = d_dst + N * N;
+    CK(cudaMemcpyAsync(d_load, h_load, ne * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_src, h_src_cum, N * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_dst, h_dst_cum, N * N * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_rate, h_rate_cum, R * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // the host tables may be pageable and short-lived
+    kp.n_req = n_requests;
+    // set_load takes the holding time as a C float (qrmsa.pyx:1124)
+    k_generate_trace<<<(kp.n_envs + 127) / 128, 128, 0, st>>>(kp, seed, ctx->gen_pos, env_offset, d_load,
+                                                              (double)(float)mean_holding_time, d_src, d_dst, d_rate,
+                                                              ctx->gen_clock, n_requests);
+    CK(cudaGetLastError());
+    ctx->gen_pos += (unsigned long long)n_requests;
+    return build_schedule(ctx, n_requests, st);
+}
+
+extern "C" int qrmsa_get_trace_host(qrmsa_ctx *ctx, int first, int count, uint8_t *h_src, uint8_t *h_dst, uint8_t *h_rate,
+                                    float *h_arrival, float *h_holding, void *stream) {
+    if (!ctx || !h_src || !h_dst || !h_rate || !h_arrival || !h_holding || first < 0 || count < 0 ||
+        first + count > ctx->kp.n_req)
+        return QRMSA_ERR_ARG;
+    if (count == 0) return QRMSA_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)count * ctx->kp.n_envs, nb = round_up(n, 256);
+    int rc = ensure_stage(ctx, nb * 11);
+    if (rc) return rc;
+    unsigned char *base = (unsigned char *)ctx->stage;
+    float *d_arr = (float *)base, *d_hold = (float *)(base + nb * 4);
+    uint8_t *d_src = base + nb * 8, *d_dst = d_src + nb, *d_rate = d_dst + nb;
+    dim3 grid((ctx->kp.n_envs + 31) / 32, (count + 31) / 32);
+    k_gather_trace<<<grid, 256, 0, st>>>(ctx->kp, first, count, d_src, d_dst, d_rate, d_arr, d_hold);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_arrival, d_arr, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_holding, d_hold, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_src, d_src, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_dst, d_dst, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_rate, d_rate, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return QRMSA_OK;
 }
 
 extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, void *stream) {

@@ -1027,6 +1027,92 @@ __global__ void k_ingest_trace(const KParams p, const uint8_t *__restrict__ src,
     }
 }
 
+// --------------------------------------------------------------------------------------------------------
+// On-device request generation: the draws of QRMSAEnv._next_service / _get_node_pair
+// (qrmsa.pyx:1079-1099, :1134-1148) in the same order and arithmetic -- exponential inter-arrival and holding
+// times rounded to float32, the float32 clock, source / destination / bit rate by bisecting cumulative weights --
+// but from a counter-based Philox4x32-10 stream keyed by (seed, global env index, request index) instead of
+// CPython's MT19937.  Streams are reproducible and independent of how envs are sharded over GPUs; they are NOT
+// the reference's streams (use the host generator + qrmsa_load_trace for replay parity).
+// --------------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c.x, p1 = (uint64_t)0xCD9E8D57u * c.z;
+        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k.y, (uint32_t)p0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// 53-bit uniform in [0, 1) from two words, as CPython's random() builds it
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ int bisect_right_dev(const double *__restrict__ a, double x, int hi) {
+    int lo = 0;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (x < a[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void k_generate_trace(const KParams p, const unsigned long long seed, const unsigned long long pos0,
+                                 const long long env_offset, const double *__restrict__ load, const double mean_holding,
+                                 const double *__restrict__ src_cum, const double *__restrict__ dst_cum,
+                                 const double *__restrict__ rate_cum, float *__restrict__ clock, const int n_req) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_envs) return;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const unsigned long long ge = (unsigned long long)(env_offset + e);
+    const double mean_iat = 1.0 / (load[e] / mean_holding);   // qrmsa.pyx:1130 (holding time as float32, set by the host)
+    const double lam = 1.0 / mean_iat, lam_hold = 1.0 / mean_holding;
+    const int N = p.N, R = p.R;
+    double now = (double)clock[e];
+    uint4 *tr = p.trace + (size_t)e * p.T;
+    for (int k = 0; k < n_req; ++k) {
+        const unsigned long long c = pos0 + (unsigned long long)k;
+        const uint4 a = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)ge, (uint32_t)(ge >> 32) * 2u), key);
+        const uint4 b = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)ge, (uint32_t)(ge >> 32) * 2u + 1u), key);
+        const float at = (float)(now + (-log(1.0 - u53(a.x, a.y)) / lam));       // qrmsa.pyx:1079-1081
+        now = (double)at;
+        const float ht = (float)(-log(1.0 - u53(a.z, a.w)) / lam_hold);          // qrmsa.pyx:1083-1084
+        const int src = bisect_right_dev(src_cum, ((double)b.x * (1.0 / 4294967296.0)) * src_cum[N - 1], N - 1);
+        const double *dc = dst_cum + (size_t)src * N;
+        const int dst = bisect_right_dev(dc, ((double)b.y * (1.0 / 4294967296.0)) * dc[N - 1], N - 1);
+        const int rate = bisect_right_dev(rate_cum, ((double)b.z * (1.0 / 4294967296.0)) * rate_cum[R - 1], R - 1);
+        tr[k] = make_uint4(__float_as_uint(at), __float_as_uint(ht), (uint32_t)src | ((uint32_t)dst << 8) | ((uint32_t)rate << 16), 0u);
+    }
+    clock[e] = (float)now;
+}
+
+// request records [first, first+count) -> request-major SoA [count][n_envs] (the inverse of k_ingest_trace)
+__global__ void k_gather_trace(const KParams p, const int first, const int count, uint8_t *__restrict__ src,
+                               uint8_t *__restrict__ dst, uint8_t *__restrict__ rate, float *__restrict__ arrival,
+                               float *__restrict__ holding) {
+    __shared__ uint4 tile[32][33];
+    const int e0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int ee = ty; ee < 32; ee += 8) {
+        const int e = e0 + ee, r = r0 + tx;
+        if (r < count && e < p.n_envs) tile[ee][tx] = p.trace[(size_t)e * p.T + first + r];
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int r = r0 + rr, e = e0 + tx;
+        if (r < count && e < p.n_envs) {
+            const uint4 v = tile[tx][rr];
+            const size_t o = (size_t)r * p.n_envs + e;
+            arrival[o] = __uint_as_float(v.x);
+            holding[o] = __uint_as_float(v.y);
+            src[o] = (uint8_t)(v.z & 0xff); dst[o] = (uint8_t)((v.z >> 8) & 0xff); rate[o] = (uint8_t)((v.z >> 16) & 0xff);
+        }
+    }
+}
+
 // Release schedule: per env, request ids sorted by (float32(arrival + holding), id) -- the key of the
 // reference's heap (qrmsa.pyx:1327-1330).  One CTA per env, bitonic sort of 64-bit keys in shared memory.
 __global__ void __launch_bounds__(1024) k_build_schedule(const KParams p, const int n_req, const int n_pad) {

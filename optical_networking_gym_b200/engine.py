@@ -111,6 +111,31 @@ class Engine:
         self._sync(stream)  # the host arrays may be pageable: keep them alive until the copies are done
         self.n_loaded = n_req
 
+    def generate_trace(self, n_requests: int, load, seed: int = 0, restart: bool = True, env_offset: int = 0,
+                       mean_holding_time: float = 10800.0, node_request_probabilities=None,
+                       bit_rate_probabilities=None, stream=None):
+        """Draw the next n_requests requests of every env ON THE DEVICE (Philox streams keyed by seed and global env
+        index; the draws of qrmsa.pyx:1079-1099, :1134-1148) instead of uploading a host trace."""
+        from .tracegen import choice_tables
+
+        ld = np.broadcast_to(np.asarray(load, np.float64), (self.n_envs,)).copy()
+        src_cum, dst_cum, rate_cum = choice_tables(self.tables.n_nodes, self.tables.n_rates, node_request_probabilities,
+                                                   bit_rate_probabilities)
+        check(self.lib.qrmsa_generate_trace(self._h, int(seed), int(bool(restart)), int(env_offset), _np_ptr(ld),
+                                            float(mean_holding_time), _np_ptr(src_cum), _np_ptr(dst_cum),
+                                            _np_ptr(rate_cum), int(n_requests), self._stream(stream)), self._h)
+        self.n_loaded = int(n_requests)
+
+    def trace_host(self, first: int = 0, count: Optional[int] = None, stream=None):
+        """The loaded / generated request stream as (src, dst, rate, arrival, holding), each [count, n_envs]."""
+        count = self.n_loaded - first if count is None else int(count)
+        shape = (count, self.n_envs)
+        out = (np.empty(shape, np.uint8), np.empty(shape, np.uint8), np.empty(shape, np.uint8),
+               np.empty(shape, np.float32), np.empty(shape, np.float32))
+        check(self.lib.qrmsa_get_trace_host(self._h, int(first), count, *[_np_ptr(a) for a in out],
+                                            self._stream(stream)), self._h)
+        return out
+
     def load_trace_host_strided(self, ptrs, n_requests: int, row_stride: int, stream=None):
         """Asynchronous upload for a context that owns an env slice of a larger pinned [n_requests, row_stride]
         batch; `ptrs` = the five host addresses of this slice's first env (src, dst, rate, arrival, holding)."""

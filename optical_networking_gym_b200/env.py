@@ -435,8 +435,13 @@ def calculate_osnr(env, service):
 
 # ========================================================================================================
 class BatchedQRMSAEnv(_Common):
-    """n_envs environments on one GPU, stepped together.  Env i replays random.Random(base_seed + i);
-    `load` may be a scalar or one value per env (load sweeps: set n_groups for per-load counters)."""
+    """n_envs environments on one GPU, stepped together.  `load` may be a scalar or one value per env (load sweeps:
+    set n_groups for per-load counters).
+
+    request_source="replay" (default): env i replays random.Random(base_seed + i), generated on the host draw for
+    draw as the reference does (qrmsa.pyx:1079-1099) and uploaded each episode.
+    request_source="device": the same traffic model drawn on the GPU from Philox streams keyed by
+    (seed, env_offset + i) -- no host generation or upload; not the reference's streams."""
 
     def __init__(self, topology, n_envs: int, num_spectrum_resources: int = 320, episode_length: int = 1000,
                  load=10.0, mean_service_holding_time: float = 10800.0, bit_rate_selection: str = "discrete",
@@ -445,12 +450,21 @@ class BatchedQRMSAEnv(_Common):
                  frequency_slot_bandwidth: float = 12.5e9, margin: float = 0.0, measure_disruptions: bool = False,
                  seed: int = 50, allow_rejection: bool = True, reset: bool = True, channel_width: float = 12.5,
                  k_paths: int = 5, modulations_to_consider: int = 6, defragmentation: bool = False,
-                 gen_observation: bool = False, bands=None, device: int = 0, n_groups: int = 1, n_threads: int = 0):
+                 gen_observation: bool = False, bands=None, device: int = 0, n_groups: int = 1, n_threads: int = 0,
+                 request_source: str = "replay", env_offset: int = 0):
         _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, bit_rate_selection)
         self._setup(topology, num_spectrum_resources, bit_rates, launch_power_dbm, margin, frequency_start,
                     frequency_slot_bandwidth, channel_width, k_paths, modulations_to_consider, bandwidth)
         import torch
 
+        if request_source not in ("replay", "device"):
+            raise ValueError("request_source must be 'replay' or 'device'")
+        self.request_source = request_source
+        self.env_offset = int(env_offset)
+        self._traffic = dict(load=load, mean_holding_time=mean_service_holding_time,
+                             node_request_probabilities=node_request_probabilities,
+                             bit_rate_probabilities=bit_rate_probabilities)
+        self._episodes = 0
         self.n_envs = int(n_envs)
         self.episode_length = int(episode_length)
         self.base_seed = int(seed)
@@ -484,9 +498,19 @@ class BatchedQRMSAEnv(_Common):
 
     def reset(self, seed=None, options=None):
         """Every env: network wiped, next `episode_length` requests of its stream attached (qrmsa.pyx:427-504)."""
-        self._gen.next(self.episode_length, out=self._trace)
         self._eng.reset()
-        self._eng.load_trace_host(*self._trace)
+        if self.request_source == "device":
+            self._eng.generate_trace(self.episode_length, self._traffic["load"], seed=self.base_seed,
+                                     restart=self._episodes == 0, env_offset=self.env_offset,
+                                     mean_holding_time=self._traffic["mean_holding_time"],
+                                     node_request_probabilities=self._traffic["node_request_probabilities"],
+                                     bit_rate_probabilities=self._traffic["bit_rate_probabilities"])
+            self._trace_valid = False
+        else:
+            self._gen.next(self.episode_length, out=self._trace)
+            self._eng.load_trace_host(*self._trace)
+            self._trace_valid = True
+        self._episodes += 1
         self.steps_done = 0
         self._observe()
         return self._obs, {"mask": self._mask}
@@ -497,6 +521,10 @@ class BatchedQRMSAEnv(_Common):
 
     def current_requests(self):
         """(src, dst, rate index, arrival, holding) host arrays of the episode, [episode_length, n_envs]."""
+        if not self._trace_valid:   # device-generated: fetched on demand
+            for dst_arr, a in zip(self._trace, self._eng.trace_host()):
+                dst_arr[...] = a
+            self._trace_valid = True
         return self._trace
 
     def step(self, actions):

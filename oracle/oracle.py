@@ -222,3 +222,51 @@ def generate_trace_python(n_nodes: int, n_rates: int, load: float, mean_holding:
         r = rng.choices(list(range(n_rates)), probs, k=1)[0]
         src[i], dst[i], rate[i], arrival[i], holding[i] = s, d, r, at, ht
     return dict(src=src, dst=dst, rate=rate, arrival=arrival, holding=holding), rng, now
+
+
+def philox4x32_10(c, k):
+    """Philox4x32-10 (Salmon et al., SC'11; Random123 constants) on numpy uint32 arrays: c = 4 counter words,
+    k = 2 key words.  Restates philox4x32_10 of csrc/qrmsa_kernels.cuh for the tests."""
+    c = [np.asarray(x, np.uint64) for x in c]
+    k = [np.uint64(k[0]), np.uint64(k[1])]
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k[0]) & MASK, p1 & MASK, ((p0 >> np.uint64(32)) ^ c[3] ^ k[1]) & MASK, p0 & MASK]
+        k = [(k[0] + W0) & MASK, (k[1] + W1) & MASK]
+    return c
+
+
+def generate_trace_philox(n_envs: int, n_requests: int, load, seed: int, src_cum, dst_cum, rate_cum,
+                          mean_holding: float = 10800.0, env_offset: int = 0, pos0: int = 0):
+    """numpy restatement of k_generate_trace (the on-device request generator): the draws of qrmsa.pyx:1079-1099,
+    :1134-1148 from Philox streams keyed by (seed, env_offset + env, request index).  Arrays are [n_requests, n_envs]."""
+    load = np.broadcast_to(np.asarray(load, np.float64), (n_envs,))
+    mh = float(np.float32(mean_holding))
+    lam = 1.0 / (1.0 / (load / mh))
+    lam_hold = 1.0 / mh
+    ge = np.arange(n_envs, dtype=np.uint64) + np.uint64(env_offset)
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    N, R = len(src_cum), len(rate_cum)
+    src = np.zeros((n_requests, n_envs), np.uint8); dst = np.zeros_like(src); rate = np.zeros_like(src)
+    arrival = np.zeros((n_requests, n_envs), np.float32); holding = np.zeros_like(arrival)
+    now = np.zeros(n_envs, np.float64)
+
+    def u53(a, b):
+        return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) * (1.0 / 9007199254740992.0)
+
+    for kk in range(n_requests):
+        c = np.uint64(pos0 + kk)
+        lo, hi = np.full(n_envs, c & np.uint64(0xFFFFFFFF)), np.full(n_envs, c >> np.uint64(32))
+        gl, gh = ge & np.uint64(0xFFFFFFFF), (ge >> np.uint64(32)) * np.uint64(2)
+        a = philox4x32_10((lo, hi, gl, gh), key)
+        b = philox4x32_10((lo, hi, gl, gh + np.uint64(1)), key)
+        at = (now + (-np.log(1.0 - u53(a[0], a[1])) / lam)).astype(np.float32)
+        now = at.astype(np.float64)
+        ht = (-np.log(1.0 - u53(a[2], a[3])) / lam_hold).astype(np.float32)
+        s = np.minimum(np.searchsorted(src_cum[: N - 1], (b[0].astype(np.float64) / 4294967296.0) * src_cum[N - 1], side="right"), N - 1)
+        xd = (b[1].astype(np.float64) / 4294967296.0) * dst_cum[s, N - 1]
+        d = np.array([np.searchsorted(dst_cum[si, : N - 1], x, side="right") for si, x in zip(s, xd)])
+        r = np.searchsorted(rate_cum[: R - 1], (b[2].astype(np.float64) / 4294967296.0) * rate_cum[R - 1], side="right")
+        src[kk], dst[kk], rate[kk], arrival[kk], holding[kk] = s, d, r, at, ht
+    return src, dst, rate, arrival, holding

@@ -56,3 +56,24 @@ def test_properties():
     assert (src != dst).all() and src.max() < 28 and dst.max() < 28 and rate.max() < 5
     assert (np.diff(arr, axis=0) >= 0).all() and (hold >= 0).all()
     assert abs(np.diff(arr, axis=0).mean() - 10800.0 / 300.0) < 1.5
+
+
+def test_philox_known_answers_and_restatement_properties():
+    """The numpy restatement of the on-device generator: Philox4x32-10 against the Random123 known-answer vectors
+    (kat_vectors: philox4x32 10), then determinism / shard independence of the request streams built on it."""
+    from oracle import oracle as orc
+    from optical_networking_gym_b200.tracegen import choice_tables
+
+    kat = [((0, 0, 0, 0), (0, 0), "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+           ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for c, k, want in kat:
+        out = orc.philox4x32_10([np.array([x]) for x in c], k)
+        assert " ".join("%08x" % int(o[0]) for o in out) == want
+    tabs = choice_tables(14, 5)
+    a = orc.generate_trace_philox(12, 40, 210.0, 77, *tabs)
+    b = orc.generate_trace_philox(4, 40, 210.0, 77, *tabs, env_offset=8)
+    assert np.array_equal(a[0][:, 8:], b[0]) and np.array_equal(a[3][:, 8:], b[3])   # streams follow the global env index
+    c = orc.generate_trace_philox(12, 15, 210.0, 77, *tabs, pos0=25)
+    assert np.array_equal(a[1][25:], c[1])                                               # and the request index
+    assert (a[0] != a[1]).all() and (np.diff(a[3].astype(np.float64), axis=0) >= 0).all()
