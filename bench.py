@@ -398,6 +398,32 @@ def run_b200(args, rank, local_rank, world):
                        "C-ABI calls on env slices overlapped over CUDA streams; bytes are per bench step of "
                        "`chunk` requests per env"}
 
+    # ---- phase C (informational): the same episode with the requests drawn on the device (qrmsa_generate_trace,
+    # Philox streams) instead of uploaded: no host generation, no H2D; decisions still downloaded
+    e2e_dev = None
+    if not args.no_e2e:
+        out_words = torch.empty((n_req - 1, n_envs), dtype=torch.int32, pin_memory=True)
+        def episode():
+            eng.reset()
+            eng.generate_trace(n_req, LOAD, seed=BASE_SEED, env_offset=rank * n_envs)
+            done = 0
+            while done < n_req - 1:
+                c = min(512, n_req - 1 - done)
+                eng.step_first_fit(c)
+                done += c
+            eng.actions_host_strided(0, n_req - 1, out_words.data_ptr(), n_envs)
+            return eng.counters().sum(0)
+        episode()
+        barrier()
+        t0 = time.perf_counter()
+        cnt = episode()
+        barrier()
+        t_dev = max_over_ranks(time.perf_counter() - t0)
+        assert int(cnt[0]) == n_envs * (n_req - 1)
+        e2e_dev = {"value": world * n_envs * (n_req - 1) / t_dev, "unit": UNIT, "seconds": t_dev,
+                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * n_envs * chunk,
+                   "note": "requests generated on the device (Philox), decisions downloaded; not the contract's e2e"}
+
     # ---- CPU baseline: the reference's Cython path on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -426,7 +452,8 @@ def run_b200(args, rank, local_rank, world):
                        "episode_requests": n_req, "l2_policy": "inputs larger than L2 (per-GPU env state + trace "
                        f"touched per step >= {n_envs * (tb.n_links * 64 + 16 * chunk) / 1e6:.0f} MB)",
                        "trace": f"CPython-random-exact streams, seeds {BASE_SEED}+i, generated on host in {t_gen:.1f}s"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_device_requests": e2e_dev,
+            "gpu_launches": 2 * K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     eng.close()
