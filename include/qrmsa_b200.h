@@ -93,6 +93,7 @@ enum {
 #define QRMSA_FLAG_ACCEPTED 0x20000000u
 #define QRMSA_FLAG_BLOCKED_RESOURCES 0x01000000u /* rejected: the heuristic's blocked_due_to_resources (heuristics.py:966) */
 #define QRMSA_FLAG_BLOCKED_OSNR 0x02000000u      /* rejected: blocked_due_to_osnr                                     */
+#define QRMSA_FLAG_NEAR_TIE 0x04000000u          /* highest-SNR policy: a runner-up within 1e-6 dB of the chosen candidate */
 
 /* step_action status per env (qrmsa.pyx:838-1065) */
 enum {
@@ -187,8 +188,10 @@ int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream);
  * selects by number):
  *   QRMSA_POLICY_FIRST_FIT       heuristic_shortest_available_path_first_fit_best_modulation (heuristics.py:923-966)
  *   QRMSA_POLICY_LOAD_BALANCING  load_balancing_best_modulation (heuristics.py:547-627)
+ *   QRMSA_POLICY_HIGHEST_SNR     heuristic_highest_snr (heuristics.py:272-328): every valid start of every (path,
+ *                                modulation) is QoT-checked, the acceptable candidate with the highest GSNR wins
  */
-enum { QRMSA_POLICY_FIRST_FIT = 0, QRMSA_POLICY_LOAD_BALANCING = 1 };
+enum { QRMSA_POLICY_FIRST_FIT = 0, QRMSA_POLICY_LOAD_BALANCING = 1, QRMSA_POLICY_HIGHEST_SNR = 2 };
 int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, void *stream);
 
 /*

@@ -30,8 +30,9 @@ FLAG_DECIDED = 0x40000000
 FLAG_ACCEPTED = 0x20000000
 FLAG_BLOCKED_RESOURCES = 0x01000000   # rejected requests: the heuristic's blocked_due_to_resources
 FLAG_BLOCKED_OSNR = 0x02000000        # rejected requests: blocked_due_to_osnr
-POLICY_FIRST_FIT, POLICY_LOAD_BALANCING = 0, 1
-POLICIES = {"first_fit": 0, "load_balancing": 1}
+FLAG_NEAR_TIE = 0x04000000            # highest-SNR policy: runner-up within 1e-6 dB of the chosen candidate
+POLICY_FIRST_FIT, POLICY_LOAD_BALANCING, POLICY_HIGHEST_SNR = 0, 1, 2
+POLICIES = {"first_fit": 0, "load_balancing": 1, "highest_snr": 2}
 STEP_ACCEPTED, STEP_REJECT_ACTION, STEP_NOT_FREE, STEP_LOW_GSNR, STEP_IDLE = range(5)
 
 

@@ -23,6 +23,8 @@ struct qrmsa_ctx {
     int sub_grid = 0;
     bool use_warp_kernel = false;
     size_t sub_smem = 0;
+    size_t cta_smem = 0;   // k_step_highest_snr (and k_observation): one CTA per env
+    int cta_grid = 0;
     // on-device request generator
     float *gen_clock = nullptr;
     double *gen_tables = nullptr;   // load[n_envs] | src_cum[N] | dst_cum[N*N] | rate_cum[R]
@@ -321,8 +323,15 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     CK(cudaFuncSetAttribute(k_probe_gsnr, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_build_schedule, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
 
-    // ---- observation kernel: route-length normalisation (qrmsa.pyx:676-690) and launch shape
+    // ---- CTA-per-env kernels (observation, highest-SNR policy): shared memory = tables + X[c2] + staged records
     int rc;
+    ctx->cta_smem = (size_t)kp.blob_bytes + sizeof(ObsSmem) + (size_t)D * 8 + (size_t)S * 8 + (size_t)kp.Hmax * kp.CAP * 4;
+    if ((int)ctx->cta_smem <= ctx->smem_optin) {
+        CK(cudaFuncSetAttribute(k_step_highest_snr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->cta_smem));
+        const int per_sm = (2 * (ctx->cta_smem + 1024) <= (size_t)smem_sm) ? 2 : 1;
+        ctx->cta_grid = std::min(n_envs, ctx->sm_count * per_sm);
+    }
+    // ---- observation kernel: route-length normalisation (qrmsa.pyx:676-690) and launch shape
     if (t->path_length_km && t->link_length_km) {
         double lo = t->link_length_km[0], hi = t->link_length_km[0];
         for (int l = 1; l < E; l++) { lo = std::min(lo, t->link_length_km[l]); hi = std::max(hi, t->link_length_km[l]); }
@@ -586,7 +595,7 @@ extern "C" int qrmsa_get_trace_host(qrmsa_ctx *ctx, int first, int count, uint8_
 
 extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, void *stream) {
     if (!ctx || n_steps < 0) return QRMSA_ERR_ARG;
-    if (policy != QRMSA_POLICY_FIRST_FIT && policy != QRMSA_POLICY_LOAD_BALANCING) { ctx->err = "unknown policy"; return QRMSA_ERR_ARG; }
+    if (policy != QRMSA_POLICY_FIRST_FIT && policy != QRMSA_POLICY_LOAD_BALANCING && policy != QRMSA_POLICY_HIGHEST_SNR) { ctx->err = "unknown policy"; return QRMSA_ERR_ARG; }
     if (ctx->kp.n_req < 2) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
     if (n_steps == 0) return QRMSA_OK;
     CK(cudaSetDevice(ctx->device));
@@ -609,6 +618,9 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else if (c640) k_step_policy<640, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+    } else if (policy == QRMSA_POLICY_HIGHEST_SNR) {
+        if (!ctx->cta_grid) { ctx->err = "highest-SNR policy needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
+        k_step_highest_snr<<<ctx->cta_grid, OBS_THREADS, ctx->cta_smem, st>>>(kp, n_steps);
     } else {
         if (c320) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);

@@ -980,6 +980,225 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
 }
 
 // --------------------------------------------------------------------------------------------------------
+// heuristic_highest_snr (heuristics.py:272-328, benchmark heuristic #2) + env.step, n_steps requests per env.
+// The reference QoT-checks EVERY valid start of every (path, modulation) and takes the acceptable candidate with
+// the highest GSNR.  One CTA per env: per path the neighbour sum X[c2] is built once for every centre frequency
+// (as in k_observation), after which a candidate is one lookup; the winner is the smallest acc = 1/GSNR, found by
+// block reductions, and warp 0 commits it with the warp-level commit / release code of the first-fit kernel.
+// Order of the search = order of the reference's loops (path, modulation descending, start ascending); the first
+// candidate wins a tie.  The reference compares GSNR in dB, several 1/GSNR values share one dB value, so a
+// runner-up within 1e-6 dB of the winner raises QRMSA_FLAG_NEAR_TIE (reported like the near-threshold flag).
+// --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long *red, unsigned long long *bc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(FULL, v, o);
+        v = y < v ? y : v;
+    }
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long x = lane < (int)(blockDim.x >> 5) ? red[lane] : ~0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(FULL, x, o);
+            x = y < x ? y : x;
+        }
+        if (lane == 0) *bc = x;
+    }
+    __syncthreads();
+    const unsigned long long r = *bc;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KParams p, const int n_steps) {
+    __shared__ uint64_t mbar;
+    __shared__ unsigned long long red64[OBS_THREADS / 32], bc64;
+    __shared__ unsigned int s_checks, s_terms;
+    __shared__ int s_cur, s_err;
+    stage_tables(p, &mbar);
+    Tab t;
+    t.init();
+    const Dim<0, 0, 0> dm(p);
+    const int S = p.S, M = p.M, K = p.K, D = p.D, CAP = p.CAP;
+    unsigned char *extra = qsmem + p.blob_bytes;
+    ObsSmem *sm = reinterpret_cast<ObsSmem *>(extra);
+    double *X = reinterpret_cast<double *>(extra + sizeof(ObsSmem));          // [D]
+    uint32_t *rec = reinterpret_cast<uint32_t *>(X + D + p.S);                  // [Hmax][CAP]  (same carve-up as k_observation)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int reject = K * M * S;
+    const double TIE = 1.0000002302585359;   // 10^(1e-6 / 10): 1e-6 dB on the linear value
+
+    for (int env = blockIdx.x; env < p.n_envs; env += gridDim.x) {
+        int4 st = p.estate[env];
+        if (st.w != ENV_OK) continue;   // (uniform over the CTA)
+        int cur = st.x, rel_ptr = st.y, err = 0;
+        uint4 *tr = p.trace + (size_t)env * p.T;
+        const uint16_t *perm = p.perm + (size_t)env * p.T;
+        uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
+        uint32_t *lists = p.lists + (size_t)env * p.E * CAP;
+        uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
+        Head head = load_head(p, tr, perm, rel_ptr);
+        unsigned long long *cglob = p.counters + (size_t)(env / p.group_size) * QRMSA_N_COUNTERS;
+        if (tid == 0) { s_checks = 0u; s_terms = 0u; }
+
+#pragma unroll 1
+        for (int step = 0; step < n_steps && cur + 1 < p.n_req && !err; ++step) {
+            const uint4 rq = tr[cur];
+            const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+            const int pbase = (src * p.N + dst) * K;
+            // per-thread best / runner-up over the candidates this thread evaluates (acc > 0: its bit pattern orders it)
+            unsigned long long best = ~0ull, second = ~0ull, near = ~0ull;   // near: smallest acc within 1e-3 dB of its threshold
+            int best_idx = 0x7fffffff, best_phys = -1;   // phys: (path, start, slots) -- the same channel under another modulation
+            int any_res = 0, any_osnr = 0;
+            uint32_t n_checks = 0, n_terms = 0;
+
+            for (int pi = 0; pi < K; ++pi) {
+                const int path = pbase + pi;
+                const int hops = __ldg(p.path_hops + path) & 0x7f;
+                if (hops == 0) continue;
+                __syncthreads();
+                if (tid < 32) {
+                    const int l = tid < hops ? __ldg(p.path_links + path * p.Hmax + tid) : 0;
+                    sm->link[tid] = l;
+                    sm->cnt[tid] = tid < hops ? (int)bm[(unsigned)(l * p.RW + p.RW - 1)] : 0;
+                    sm->w1[tid] = t.W1(l);
+                    sm->w2[tid] = t.W2(l);
+                    sm->av[tid] = path_available(dm, bm, hops, l, lane);
+                }
+                __syncthreads();
+                for (int i = 0; i < hops; ++i) {
+                    const int c = sm->cnt[i];
+                    const uint32_t *lst = lists + (unsigned)(sm->link[i] * CAP);
+                    for (int q = tid; q < c; q += blockDim.x) rec[i * CAP + q] = lst[q];
+                }
+                __syncthreads();
+                for (int c2 = tid; c2 < D; c2 += blockDim.x) {   // X[c2]: neighbour sum for a candidate centred at c2
+                    double x = 0.0;
+                    for (int i = 0; i < hops; ++i) {
+                        const int c = sm->cnt[i];
+                        const uint32_t *r = rec + i * CAP;
+                        double s1 = 0.0, s2 = 0.0;
+                        for (int q = 0; q < c; ++q) gn_term(t, D, r[q], c2, s1, s2);
+                        n_terms += (uint32_t)c;
+                        x = fma(sm->w1[i], s1, x);
+                        x = fma(sm->w2[i], s2, x);
+                    }
+                    X[c2] = x;
+                }
+                uint32_t r = 0;
+                int a = 1;
+                if (warp == 0) r = sm->av[lane];
+                for (int mi = 0; mi < M; ++mi) {
+                    const int m = (M - 1) - mi;
+                    const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
+                    __syncthreads();   // X complete / previous valid[] consumed
+                    if (warp == 0) {
+                        const int L = n + 1;
+                        if (L < a) { r = sm->av[lane]; a = 1; }
+                        while (a < L) { const int b = min(a, L - a); r &= shr_multi(r, b); a += b; }
+                        sm->valid[lane] = r;
+                    }
+                    __syncthreads();
+                    int here = 0;
+                    for (int s = tid; s < S; s += blockDim.x) {
+                        if (!((sm->valid[s >> 5] >> (s & 31)) & 1u)) continue;
+                        here = 1;
+                        const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
+                        n_checks += 1;
+                        const unsigned long long k = (unsigned long long)__double_as_longlong(acc);
+                        if (acc > t.ACCLO(m) && acc < t.ACCHI(m) && k < near) near = k;
+                        if (acc <= t.ACCT(m)) {                       // gsnr >= threshold (heuristics.py:312-313)
+                            const int idx = (pi * M + mi) * S + s;     // = the action index
+                            const int phys = (pi << 20) | (s << 8) | n;
+                            if (k == best && phys == best_phys) {
+                                // identical channel (same path, slots) met again under a lower modulation: same GSNR by
+                                // construction, the first one keeps the tie (heuristics.py:314) and it is no runner-up
+                            } else if (k < best) { second = best; best = k; best_idx = idx; best_phys = phys; }
+                            else if (k < second) second = k;
+                        } else {
+                            any_osnr = 1;
+                        }
+                    }
+                    if (!__syncthreads_or(here)) any_res = 1;         // no valid start: blocked_resources (heuristics.py:295-297)
+                }
+            }
+            // ---- winner: smallest acc, first in search order among equals
+            const unsigned long long gbest = block_min_u64(best, red64, &bc64);
+            const int widx = (int)block_min_u64(best == gbest ? (unsigned long long)(unsigned)best_idx : ~0ull, red64, &bc64);
+            const unsigned long long gsecond = block_min_u64((best == gbest && best_idx == widx) ? second : best, red64, &bc64);
+            const unsigned long long gnear = block_min_u64(near, red64, &bc64);
+            const int g_osnr = __syncthreads_or(any_osnr);
+            const bool found = gbest != ~0ull;
+            uint32_t flags = QRMSA_FLAG_DECIDED;
+            // a check within 1e-3 dB of its threshold matters when flipping it could change the outcome: no acceptable
+            // candidate at all, or its GSNR is at least the winner's
+            if (gnear != ~0ull && (!found || __longlong_as_double((long long)gnear) <= __longlong_as_double((long long)gbest) * TIE))
+                flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+            int action = reject;
+            if (found) {
+                flags |= QRMSA_FLAG_ACCEPTED;
+                action = widx;
+                if (gsecond != ~0ull && __longlong_as_double((long long)gsecond) <= __longlong_as_double((long long)gbest) * TIE)
+                    flags |= QRMSA_FLAG_NEAR_TIE;
+            } else {
+                if (any_res && !g_osnr) flags |= QRMSA_FLAG_BLOCKED_RESOURCES;   // heuristics.py:324-326
+                if (g_osnr) flags |= QRMSA_FLAG_BLOCKED_OSNR;
+            }
+            // work counters: block totals
+            {
+                uint32_t v0 = n_checks, v1 = n_terms;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(FULL, v0, o); v1 += __shfl_xor_sync(FULL, v1, o); }
+                if (lane == 0) { atomicAdd(&s_checks, v0); atomicAdd(&s_terms, v1); }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                if (found) {
+                    const int s = widx % S, mi = (widx / S) % M, pi = widx / (S * M), m = (M - 1) - mi;
+                    const int path = pbase + pi;
+                    const int hops = __ldg(p.path_hops + path) & 0x7f;
+                    const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+                    const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, p.RW) : 0;
+                    const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
+                    const uint32_t rec_w = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) | ((uint32_t)ncls << 23);
+                    if (commit(dm, p, bm, lists, pos, hops, mylink, mycnt, s, n, rec_w, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                    if (lane == 0 && p.gsnr_log) {
+                        const double acc = __longlong_as_double((long long)gbest), ase = gn_base(p, t, path, s, n, ncls).ase;
+                        double *gl = p.gsnr_log + ((size_t)env * p.T + cur) * 3;
+                        gl[0] = -10.0 * log10(acc); gl[1] = -10.0 * log10(ase); gl[2] = -10.0 * log10(acc - ase);
+                    }
+                } else if (lane == 0 && p.gsnr_log) {
+                    double *gl = p.gsnr_log + ((size_t)env * p.T + cur) * 3;
+                    gl[0] = gl[1] = gl[2] = 0.0;
+                }
+                if (lane == 0) tr[cur].w = (uint32_t)action | flags;
+                __syncwarp();
+                uint32_t n_rel = 0;
+                if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel))
+                    err = ENV_ERR_RELEASE_NOT_FOUND;
+                if (lane == 0) {
+                    atomicAdd(cglob + QRMSA_CNT_GN_EVALS, (unsigned long long)s_checks);
+                    atomicAdd(cglob + QRMSA_CNT_GN_TERMS, (unsigned long long)s_terms);
+                    atomicAdd(cglob + QRMSA_CNT_PATHS_TRIED, (unsigned long long)K);
+                    if (n_rel) atomicAdd(cglob + QRMSA_CNT_RELEASES, (unsigned long long)n_rel);
+                    s_checks = 0u; s_terms = 0u;
+                    s_cur = cur; s_err = err;
+                }
+            }
+            __syncthreads();
+            cur = s_cur;
+            err = s_err;
+            __syncthreads();
+        }
+        if (tid == 0) p.estate[env] = make_int4(cur, rel_ptr, st.z, err);
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
 // reset (qrmsa.pyx:427-504): every slot free, lists empty, release pointer / request index / episode counters 0
 // --------------------------------------------------------------------------------------------------------
 __global__ void k_reset(const KParams p) {

@@ -96,3 +96,41 @@ def load_balancing_best_modulation(env):
     if any_osnr:
         any_res = False
     return sim.action_space.n - 1, any_res, any_osnr
+
+
+def heuristic_highest_snr(env):
+    """Every valid start of every (path, modulation) is QoT-checked; the acceptable candidate with the highest GSNR
+    wins, the first one met keeps a tie (heuristics.py:272-328, the benchmark's heuristic #2).  This Python form makes
+    one device probe per candidate (thousands per request); the batched path runs the same search fused in one kernel:
+    `BatchedQRMSAEnv.step_heuristic("highest_snr", n)` / `qrmsa_step_heuristic(QRMSA_POLICY_HIGHEST_SNR)`."""
+    sim = get_qrmsa_env(env)
+    svc = sim.current_service
+    best_osnr, best_action = float("-inf"), None
+    any_res = any_osnr = False
+    for path_idx, path in enumerate(sim.k_shortest_paths[svc.source, svc.destination]):
+        for modulation_idx in range(sim.max_modulation_idx, -1, -1):
+            modulation = sim.modulations[modulation_idx]
+            n = sim.get_number_slots(svc, modulation)
+            if n <= 0:
+                continue
+            starts = sim._get_candidates(sim.get_available_slots(path), n, sim.num_spectrum_resources)
+            if not starts:
+                any_res = True
+                continue
+            for start in starts:
+                svc.path, svc.initial_slot, svc.number_slots, svc.current_modulation = path, start, n, modulation
+                svc.center_frequency = (sim.frequency_start + (sim.frequency_slot_bandwidth * start)
+                                        + (sim.frequency_slot_bandwidth * (n / 2)))
+                svc.bandwidth = sim.frequency_slot_bandwidth * n
+                svc.launch_power = sim.launch_power
+                osnr, _, _ = calculate_osnr(sim, svc)
+                if osnr >= modulation.minimum_osnr + sim.margin:
+                    if osnr > best_osnr:
+                        best_osnr, best_action = osnr, get_action_index(sim, path_idx, modulation_idx, start)
+                else:
+                    any_osnr = True
+    if best_action is not None:
+        return best_action, False, False
+    if any_osnr:
+        any_res = False
+    return sim.action_space.n - 1, any_res, any_osnr

@@ -131,7 +131,8 @@ class OracleEnv:
         action = np.zeros(n_steps, np.int32)
         accepted = np.zeros(n_steps, np.uint8)
         gsnr = np.zeros(n_steps, np.float64)
-        cap = n_steps * self.tables.k_paths * self.tables.n_mods if log_qot else 0
+        per_step = self.tables.k_paths * self.tables.n_mods * (self.tables.n_slots if policy == 2 else 1)   # 2: every start
+        cap = n_steps * per_step if log_qot else 0
         qs = np.zeros(max(cap, 1), np.int32)
         qg = np.zeros(max(cap, 1), np.float64)
         qt = np.zeros(max(cap, 1), np.float64)

@@ -135,3 +135,22 @@ def test_oracle_load_balancing_vs_reference(tag, topo):
     assert np.abs(r["gsnr"] - g["gsnr"]).max() < 1e-9
     assert np.array_equal(r["qot_step"], g["qot_step"]) and np.abs(r["qot_gsnr"] - g["qot_gsnr"]).max() < 1e-9
     assert np.array_equal(o.slots(), g["final_slots"])
+
+
+@pytest.mark.parametrize("tag,topo", [("policy_hsnr_nsfnet_320_l300_s21", "nsfnet"), ("policy_hsnr_nobel-eu_320_l400_s5", "nobel-eu")])
+def test_oracle_highest_snr_vs_reference(tag, topo):
+    """heuristic_highest_snr (heuristics.py:272-328), the reference benchmark's heuristic #2: every valid start of every
+    (path, modulation) is QoT-checked; the recording keeps the number of checks per step instead of the full log."""
+    import os
+    from helpers import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, tag + ".npz")):
+        pytest.skip("recording not generated")
+    tb, g = load_tables(topo, 320), load_golden(tag)
+    n = len(g["action"])
+    o = orc.OracleEnv(tb, n + 1)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    r = o.run_first_fit(n, policy=2)
+    assert np.array_equal(r["action"], g["action"])
+    assert np.abs(r["gsnr"] - g["gsnr"]).max() < 1e-9
+    assert np.array_equal(np.bincount(r["qot_step"], minlength=n), g["n_checks"])
+    assert np.array_equal(o.slots(), g["final_slots"])

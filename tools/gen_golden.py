@@ -47,6 +47,13 @@ POLICY = [
     ("lb_nobel-eu_320_l400_s9", "nobel-eu", 320, 400.0, 9, 2000, "load_balancing_best_modulation"),
     ("lb_nsfnet_320_l300_s4", "nsfnet", 320, 300.0, 4, 1500, "load_balancing_best_modulation"),
 ]
+EXHAUSTIVE = [
+    # tag, topology, S, load, seed, steps, reference heuristic: every valid start of every (path, modulation) is QoT-checked
+    # (about 2 s of reference time per step), so the recordings are short; per step they keep the number of checks
+    # and the gap between the best and the second-best acceptable GSNR instead of the full QoT log
+    ("hsnr_nsfnet_320_l300_s21", "nsfnet", 320, 300.0, 21, 150, "heuristic_highest_snr"),
+    ("hsnr_nobel-eu_320_l400_s5", "nobel-eu", 320, 400.0, 5, 90, "heuristic_highest_snr"),
+]
 MULTI = [
     # tag, topology, S, load, base_seed, n_envs, steps
     ("nobel-eu_320_l300_b50", "nobel-eu", 320, 300.0, 50, 64, 400),
@@ -201,6 +208,31 @@ def main():
         out["meta_load"] = np.float64(load); out["meta_seed"] = np.int64(seed)
         np.savez_compressed(os.path.join(GOLDEN, f"policy_{tag}.npz"), **out)
         print(f"policy_{tag}: {steps} steps, accept {out['accepted'].mean():.3f}, {time.time() - t0:.1f}s")
+
+    for tag, name, S, load, seed, steps, hname in EXHAUSTIVE:
+        if args.only and args.only not in ("policy_" + tag):
+            continue
+        t0 = time.time()
+        topo = topo_of(name)
+        tables_for(topo, S).save(os.path.join(GOLDEN, f"tables_{name}_{S}.npz"))
+        out, _ = rh.run_first_fit(topo, seed, steps, heuristic_name=hname, n_slots=S, load=load)
+        qs, qg, qt = out.pop("qot_step"), out.pop("qot_gsnr"), out.pop("qot_thr")
+        n_checks = np.bincount(qs, minlength=steps).astype(np.int32)
+        gap = np.full(steps, np.inf)
+        thr_margin = np.full(steps, np.inf)
+        for t in range(steps):
+            sel = qs == t
+            g, th = qg[sel], qt[sel]
+            if len(g):
+                thr_margin[t] = np.abs(g - th).min()
+            ok = np.sort(g[g >= th])[::-1]
+            if len(ok) >= 2:
+                gap[t] = ok[0] - ok[1]
+        out.update(n_checks=n_checks, best_gap_db=gap, thr_margin_db=thr_margin,
+                   meta_load=np.float64(load), meta_seed=np.int64(seed))
+        np.savez_compressed(os.path.join(GOLDEN, f"policy_{tag}.npz"), **out)
+        print(f"policy_{tag}: {steps} steps, accept {out['accepted'].mean():.3f}, min gap {gap.min():.3e} dB, "
+              f"{time.time() - t0:.1f}s")
 
     for tag, name, S, load, base, n_envs, steps in MULTI:
         if args.only and args.only not in tag:
