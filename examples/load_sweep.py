@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--topology", default="nobel-eu")
     ap.add_argument("--slots", type=int, default=320)
     ap.add_argument("--seed", type=int, default=50)
+    ap.add_argument("--requests", choices=["replay", "device"], default="replay",
+                    help="replay: CPython-exact host streams (reference parity); device: Philox streams drawn on the GPU")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -50,7 +52,8 @@ def main():
     t0 = time.time()
     env = BatchedQRMSAEnv(tb, L * per, num_spectrum_resources=args.slots, episode_length=args.episode_length, load=loads,
                           bit_rates=(10, 40, 100, 400, 1000), launch_power_dbm=1.0, bandwidth=args.slots * 12.5e9,
-                          seed=args.seed + rank * 10_000_019, n_groups=L, device=local, reset=False)
+                          seed=args.seed + (rank * 10_000_019 if args.requests == "replay" else 0), n_groups=L, device=local,
+                          reset=False, request_source=args.requests, env_offset=rank * L * per)
     env.reset()
     sharding.allreduce_counters(np.zeros((L, 32), np.int64))   # NCCL communicator set-up is not part of the episode
     t_setup = time.time() - t0
@@ -64,7 +67,7 @@ def main():
     if rank == 0:
         n_total = args.envs_per_load * L * (args.episode_length - 1)
         print(f"{args.topology}/{args.slots}: {args.envs_per_load * L} envs x {args.episode_length - 1} steps on {world} GPU(s): "
-              f"{dt:.2f}s = {n_total / dt:,.0f} env-steps/s (setup incl. host trace generation {t_setup:.1f}s)")
+              f"{dt:.2f}s = {n_total / dt:,.0f} env-steps/s (setup incl. {args.requests} request generation {t_setup:.1f}s)")
         print("load,episodes,service_blocking_rate,ci95,bit_rate_blocking_rate,near_threshold_decisions")
         for i, load in enumerate(args.loads):
             c = counters[i]
