@@ -364,10 +364,23 @@ def run_b200(args, rank, local_rank, world):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # what actually binds the kernel (profiles/README.md): warp-instruction issue.  Instructions per env-step come from
+    # the committed ncu capture of this kernel, the rate and the clock from this run.
+    issue = None
+    try:
+        tj = json.load(open(tp))
+        ipe = float(tj["warp_instructions_per_env_step"])
+        sm_clock = float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        issue = {"bound": "issue", "achieved": ipe * (n_envs * chunk) / avg_launch_s, "peak": n_sm * 4 * sm_clock,
+                 "unit": "warp-instructions/s", "frac": ipe * (n_envs * chunk) / avg_launch_s / (n_sm * 4 * sm_clock),
+                 "warp_instructions_per_env_step": ipe, "source": tj.get("source")}
+    except Exception:
+        issue = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_step_policy<320,6,5,first_fit> (+ k_count_decisions, <1 % of the launch)", "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": bytes_step, "env_steps_per_launch": n_envs * chunk,
-                "avg_launch_ms": avg_launch_s * 1e3, "workload_params": params}
+                "avg_launch_ms": avg_launch_s * 1e3, "workload_params": params, "issue_roofline": issue}
 
     # ---- phase B: end to end through the host-buffer C-ABI calls, one whole episode.  The public call is
     # PipelinedEpisodes.run: env slices on separate contexts/streams so that upload, kernels and download overlap.

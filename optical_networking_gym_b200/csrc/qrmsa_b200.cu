@@ -296,10 +296,12 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_sub<4, 320, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2)));
-    CK(cudaFuncSetAttribute(k_step_sub<8, 640, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2)));
-    CK(cudaFuncSetAttribute(k_step_sub<4, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2)));
-    CK(cudaFuncSetAttribute(k_step_sub<8, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2)));
+    const int sub_smem_max = kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2);
+    const bool sub_fits = sub_smem_max <= ctx->smem_optin;   // the experiment kernel keeps a per-env link scratch after the tables
+    if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<4, 320, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
+    if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<8, 640, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
+    if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<4, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
+    if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<8, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
     {
         // k_step_sub: one CTA per SM, env groups (32/LPE envs per warp) handed out by a ticket counter.  The CTA
         // size is the smallest that keeps the number of rounds: e.g. 65,536 envs / 8 per warp / 148 SMs = 55.4
@@ -316,7 +318,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         ctx->sub_grid = groups < ctx->sm_count ? groups : ctx->sm_count;
         const char *impl = getenv("QRMSA_STEP_IMPL");
         // default: warp per env (k_step_policy); QRMSA_STEP_IMPL=sub selects the lanes-per-env experiment (k_step_sub)
-        ctx->use_warp_kernel = !(impl && !strcmp(impl, "sub")) || t->max_hops > SUB_HCAP;
+        ctx->use_warp_kernel = !(impl && !strcmp(impl, "sub")) || t->max_hops > SUB_HCAP || !sub_fits;
         ctx->sub_smem = (size_t)kp.blob_bytes + (size_t)(ctx->sub_threads / 32) * epw * SUB_HCAP * sizeof(uint2);
     }
     CK(cudaFuncSetAttribute(k_step_action, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
