@@ -540,41 +540,58 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 uint32_t r = av;
                 int a = 1;
                 bool counted = false;
+                // Modulations that need the same number of slots share the candidate (same first-fit start, same
+                // centre frequency, same bandwidth), hence the same GSNR: the search and the GN sum are done once per
+                // slot count and the following modulations only compare against their own threshold.
+                int n_seen = -1, s = 0;
+                bool have_x = false;
+                double x = 0.0;
+                GnBase gb;
+                gb.ase = gb.cn = gb.selfpb = 0.0;
 #pragma unroll 1
                 for (int m = M - 1; m >= 0; --m) {
                     const int nd = __shfl_sync(FULL, mynd, m);
                     const int n = nd & 0xff, ncls = nd >> 8;
-                    const int L = n + 1;
-                    if (L < a) { r = av; a = 1; }
-                    while (a < L) {
-                        const int b = min(a, L - a);
-                        r &= shr_multi(r, b);
-                        a += b;
+                    if (n != n_seen) {
+                        n_seen = -1;
+                        const int L = n + 1;
+                        if (L < a) { r = av; a = 1; }
+                        while (a < L) {
+                            const int b = min(a, L - a);
+                            r &= shr_multi(r, b);
+                            a += b;
+                        }
+                        const unsigned any = __ballot_sync(FULL, r != 0u);
+                        if (!any) {
+                            // no block of n+1 slots: the reference sets blocked_due_to_resources and tries the next
+                            // modulation (heuristics.py:938-940); when the remaining ones all need >= n slots none of
+                            // them can fit either, so the loop ends here with the same flags
+                            blk_res = 1;
+                            if (p.need_monotone) break;
+                            continue;
+                        }
+                        const int fl = __ffs(any) - 1;
+                        const uint32_t w = __shfl_sync(FULL, r, fl);
+                        s = (fl << 5) + __ffs(w) - 1;
+                        gb = gn_base(p, t, path, s, n, ncls);
+                        have_x = false;
+                        n_seen = n;
                     }
-                    const unsigned any = __ballot_sync(FULL, r != 0u);
-                    if (!any) {
-                        // no block of n+1 slots: the reference sets blocked_due_to_resources and tries the next
-                        // modulation (heuristics.py:938-940); when the remaining ones all need >= n slots none of
-                        // them can fit either, so the loop ends here with the same flags
-                        blk_res = 1;
-                        if (p.need_monotone) break;
-                        continue;
-                    }
-                    const int fl = __ffs(any) - 1;
-                    const uint32_t w = __shfl_sync(FULL, r, fl);
-                    const int s = (fl << 5) + __ffs(w) - 1;
-                    const GnBase gb = gn_base(p, t, path, s, n, ncls);
                     if (prunable && gb.empty() >= t.ACCHI(m)) {  // hopeless even in an empty network
                         QCNT(QRMSA_CNT_GN_PRUNED, 1);
                         blk_osnr = 1;
                         if (POLICY == POLICY_FIRST_FIT) blk_res = 0;
                         continue;
                     }
-                    uint32_t terms = 0;
-                    const double acc = gb.with(gn_neighbours(dm, t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
+                    if (!have_x) {
+                        uint32_t terms = 0;
+                        x = gn_neighbours(dm, t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms);
+                        have_x = true;
+                        QCNT(QRMSA_CNT_GN_TERMS, terms);
+                        if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
+                    }
+                    const double acc = gb.with(x);
                     QCNT(QRMSA_CNT_GN_EVALS, 1);
-                    QCNT(QRMSA_CNT_GN_TERMS, terms);
-                    if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
                     if (qot_ok(t, m, acc, flags)) {
                         found = true;
                         acc_ok = acc;

@@ -173,7 +173,12 @@ def test_lanes_per_env_experiment_matches_product_kernel(tag, monkeypatch):
     assert np.array_equal(a[0], b[0]), "action words differ"
     assert np.array_equal(a[1], b[1]), "bitmaps differ"
     assert np.array_equal(a[2], b[2]), "env state differs"
-    assert np.array_equal(a[3], b[3]), "counters differ"
+    ca, cb = a[3].copy(), b[3].copy()
+    # the product kernel walks the lists once per slot count and reuses the sum for modulations that need the same
+    # number of slots; the experiment walks them once per QoT check.  Same checks, fewer terms summed.
+    assert (ca[:, 8] <= cb[:, 8]).all()
+    ca[:, 8] = cb[:, 8] = 0
+    assert np.array_equal(ca, cb), "counters differ"
     assert a[4] == b[4], "channel lists differ"
 
 
