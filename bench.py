@@ -10,7 +10,7 @@ k=5, 6 modulations, first-fit heuristic, load 300 Erlang, launch power 1 dBm, bi
 
 A bench "step" = one pass of the fused hot path over one batch of synthetic input = ONE kernel
 launch of the step kernel (followed by the small decision-log counting kernel) that advances every env by
-`chunk` requests (default 128).  Before the timed region every
+`chunk` requests (default 256).  Before the timed region every
 env is brought to steady state by an untimed prefill of 1000 requests from the empty network
 (SURVEY §8d C2).  `value` = env-steps/s with the trace resident in HBM; `e2e` = the same metric
 through the host-buffer C-ABI calls for a whole episode (reset + H2D of the trace from pinned memory
@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--chunk", type=int, default=128, help="requests per env per bench step (one launch)")
+    ap.add_argument("--chunk", type=int, default=256, help="requests per env per bench step (one launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-slices", type=int, default=4)
@@ -361,7 +361,10 @@ def run_b200(args, rank, local_rank, world):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj0 = json.load(open(tp))   # ncu --set full capture of this kernel (profiles/README.md)
+            traffic = tj0.get("dram_bytes_per_launch")
+            if tj0.get("dram_bytes_per_env_step"):   # per launch of THIS run's size
+                traffic = float(tj0["dram_bytes_per_env_step"]) * n_envs * chunk
         except Exception:
             traffic = None
     # what actually binds the kernel (profiles/README.md): warp-instruction issue.  Instructions per env-step come from
