@@ -188,10 +188,12 @@ int qrmsa_step_first_fit(qrmsa_ctx *ctx, int n_steps, void *stream);
  * selects by number):
  *   QRMSA_POLICY_FIRST_FIT       heuristic_shortest_available_path_first_fit_best_modulation (heuristics.py:923-966)
  *   QRMSA_POLICY_LOAD_BALANCING  load_balancing_best_modulation (heuristics.py:547-627)
+ *   QRMSA_POLICY_LB_FIRST_FIT    heuristic_load_balancing_first_fit (heuristics.py:202-270): paths ordered by the occupied
+ *                                fraction of their availability, then first fit on the first path that admits a modulation
  *   QRMSA_POLICY_HIGHEST_SNR     heuristic_highest_snr (heuristics.py:272-328): every valid start of every (path,
  *                                modulation) is QoT-checked, the acceptable candidate with the highest GSNR wins
  */
-enum { QRMSA_POLICY_FIRST_FIT = 0, QRMSA_POLICY_LOAD_BALANCING = 1, QRMSA_POLICY_HIGHEST_SNR = 2 };
+enum { QRMSA_POLICY_FIRST_FIT = 0, QRMSA_POLICY_LOAD_BALANCING = 1, QRMSA_POLICY_HIGHEST_SNR = 2, QRMSA_POLICY_LB_FIRST_FIT = 3 };
 int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, void *stream);
 
 /*

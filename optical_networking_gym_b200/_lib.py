@@ -31,8 +31,8 @@ FLAG_ACCEPTED = 0x20000000
 FLAG_BLOCKED_RESOURCES = 0x01000000   # rejected requests: the heuristic's blocked_due_to_resources
 FLAG_BLOCKED_OSNR = 0x02000000        # rejected requests: blocked_due_to_osnr
 FLAG_NEAR_TIE = 0x04000000            # highest-SNR policy: runner-up within 1e-6 dB of the chosen candidate
-POLICY_FIRST_FIT, POLICY_LOAD_BALANCING, POLICY_HIGHEST_SNR = 0, 1, 2
-POLICIES = {"first_fit": 0, "load_balancing": 1, "highest_snr": 2}
+POLICY_FIRST_FIT, POLICY_LOAD_BALANCING, POLICY_HIGHEST_SNR, POLICY_LB_FIRST_FIT = 0, 1, 2, 3
+POLICIES = {"first_fit": 0, "load_balancing": 1, "highest_snr": 2, "load_balancing_first_fit": 3}
 STEP_ACCEPTED, STEP_REJECT_ACTION, STEP_NOT_FREE, STEP_LOW_GSNR, STEP_IDLE = range(5)
 
 

@@ -296,6 +296,8 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     const int sub_smem_max = kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2);
     const bool sub_fits = sub_smem_max <= ctx->smem_optin;   // the experiment kernel keeps a per-env link scratch after the tables
     if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<4, 320, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
@@ -597,7 +599,8 @@ extern "C" int qrmsa_get_trace_host(qrmsa_ctx *ctx, int first, int count, uint8_
 
 extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, void *stream) {
     if (!ctx || n_steps < 0) return QRMSA_ERR_ARG;
-    if (policy != QRMSA_POLICY_FIRST_FIT && policy != QRMSA_POLICY_LOAD_BALANCING && policy != QRMSA_POLICY_HIGHEST_SNR) { ctx->err = "unknown policy"; return QRMSA_ERR_ARG; }
+    if (policy != QRMSA_POLICY_FIRST_FIT && policy != QRMSA_POLICY_LOAD_BALANCING && policy != QRMSA_POLICY_HIGHEST_SNR &&
+        policy != QRMSA_POLICY_LB_FIRST_FIT) { ctx->err = "unknown policy"; return QRMSA_ERR_ARG; }
     if (ctx->kp.n_req < 2) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
     if (n_steps == 0) return QRMSA_OK;
     CK(cudaSetDevice(ctx->device));
@@ -620,6 +623,9 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else if (c640) k_step_policy<640, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+    } else if (policy == QRMSA_POLICY_LB_FIRST_FIT) {
+        if (c320) k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+        else k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_HIGHEST_SNR) {
         if (!ctx->cta_grid) { ctx->err = "highest-SNR policy needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
         k_step_highest_snr<<<ctx->cta_grid, OBS_THREADS, ctx->cta_smem, st>>>(kp, n_steps);

@@ -468,8 +468,11 @@ __device__ __forceinline__ bool qot_ok(const Tab &t, int m, double acc, uint32_t
 //   POLICY_LOAD_BALANCING  load_balancing_best_modulation (heuristics.py:547-627): among the k paths, the one
 //                          with the lowest (occupied slots of the path availability) / hops that admits a
 //                          modulation; best modulation + first-fit slot on it
+//   POLICY_LB_FIRST_FIT    heuristic_load_balancing_first_fit (heuristics.py:202-270): the k paths ordered by the
+//                          occupied fraction of their availability (ties: path index), then first-fit as above on
+//                          the first path that admits a modulation
 // --------------------------------------------------------------------------------------------------------
-enum { POLICY_FIRST_FIT = 0, POLICY_LOAD_BALANCING = 1 };
+enum { POLICY_FIRST_FIT = 0, POLICY_LOAD_BALANCING = 1, POLICY_LB_FIRST_FIT = 3 };   // ids of include/qrmsa_b200.h
 
 template <int S_, int M_, int K_, int POLICY>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p, const int n_steps) {
@@ -515,8 +518,34 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             double lowest_load = 1e300;
             int best_pi = -1, best_m = 0, best_s = 0;
 
+            // load-balancing first fit: lane j < K learns the rank of path j by (occupied slots, index)
+            int my_rank = lane;
+            if (POLICY == POLICY_LB_FIRST_FIT) {
+                int my_occ = 0x7fffffff;   // a missing path sorts last and is skipped below
 #pragma unroll 1
-            for (int pi = 0; pi < K && !(POLICY == POLICY_FIRST_FIT && found); ++pi) {
+                for (int pj = 0; pj < K; ++pj) {
+                    const int path = pbase + pj;
+                    const int hops = __ldg(p.path_hops + path) & 0x7f;
+                    if (hops == 0) continue;
+                    const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+                    const uint32_t av = path_available(dm, bm, hops, mylink, lane);
+                    int free_slots = __popc(lane == (S >> 5) ? av & ~(1u << (S & 31)) : av);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) free_slots += __shfl_xor_sync(FULL, free_slots, o);
+                    if (lane == pj) my_occ = S - free_slots;   // np.sum(available == 0) (heuristics.py:222-224)
+                    QCNT(QRMSA_CNT_LINKS_READ, hops);
+                }
+                my_rank = 0;
+#pragma unroll 1
+                for (int pj = 0; pj < K; ++pj) {
+                    const int o = __shfl_sync(FULL, my_occ, pj);
+                    my_rank += (o < my_occ || (o == my_occ && pj < lane)) ? 1 : 0;
+                }
+            }
+#pragma unroll 1
+            for (int kk = 0; kk < K && !(POLICY != POLICY_LOAD_BALANCING && found); ++kk) {
+                // path visited k-th: its own index, or the path of rank k
+                const int pi = POLICY == POLICY_LB_FIRST_FIT ? __ffs(__ballot_sync(FULL, lane < K && my_rank == kk)) - 1 : kk;
                 const int path = pbase + pi;
                 const int hp = __ldg(p.path_hops + path);  // bit 7: every neighbour term of this path is >= 0
                 const int hops = hp & 0x7f;
@@ -596,7 +625,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                         found = true;
                         acc_ok = acc;
                         ase_ok = gb.ase;
-                        if (POLICY == POLICY_FIRST_FIT) {
+                        if (POLICY != POLICY_LOAD_BALANCING) {
                             action = pi * M * S + ((M - 1) - m) * S + s;
                             const uint32_t rec = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
                                                  ((uint32_t)ncls << 23);
@@ -629,6 +658,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 flags |= QRMSA_FLAG_ACCEPTED;
             } else {
                 if (POLICY == POLICY_LOAD_BALANCING && blk_osnr) blk_res = 0;   // heuristics.py:624-626
+                if (POLICY == POLICY_LB_FIRST_FIT) { blk_res = 1; blk_osnr = 0; }   // heuristics.py:270
                 if (blk_res) flags |= QRMSA_FLAG_BLOCKED_RESOURCES;
                 if (blk_osnr) flags |= QRMSA_FLAG_BLOCKED_OSNR;
             }

@@ -134,3 +134,36 @@ def heuristic_highest_snr(env):
     if any_osnr:
         any_res = False
     return sim.action_space.n - 1, any_res, any_osnr
+
+
+def heuristic_load_balancing_first_fit(env):
+    """The k paths ordered by the occupied fraction of their availability (ties: path index), then best modulation and
+    first-fit slot on the first path that admits one; a reject reports (True, False) (heuristics.py:202-270).  Device
+    counterpart: policy "load_balancing_first_fit"."""
+    import numpy as np
+
+    sim = get_qrmsa_env(env)
+    svc = sim.current_service
+    order = []
+    for path_idx, path in enumerate(sim.k_shortest_paths[svc.source, svc.destination]):
+        available = sim.get_available_slots(path)
+        order.append((np.sum(available == 0) / len(available) if len(available) > 0 else 1.0, path_idx, path))
+    order.sort(key=lambda t: (t[0], t[1]))
+    for _, path_idx, path in order:
+        for modulation_idx in range(sim.max_modulation_idx, -1, -1):
+            modulation = sim.modulations[modulation_idx]
+            n = sim.get_number_slots(svc, modulation)
+            if n <= 0:
+                continue
+            starts = sim._get_candidates(sim.get_available_slots(path), n, sim.num_spectrum_resources)
+            if not starts:
+                continue
+            svc.path, svc.initial_slot, svc.number_slots, svc.current_modulation = path, starts[0], n, modulation
+            svc.center_frequency = (sim.frequency_start + (sim.frequency_slot_bandwidth * starts[0])
+                                    + (sim.frequency_slot_bandwidth * (n / 2)))
+            svc.bandwidth = sim.frequency_slot_bandwidth * n
+            svc.launch_power = sim.launch_power
+            osnr, _, _ = calculate_osnr(sim, svc)
+            if osnr >= modulation.minimum_osnr + sim.margin:
+                return get_action_index(sim, path_idx, modulation_idx, starts[0]), False, False
+    return sim.action_space.n - 1, True, False

@@ -282,3 +282,31 @@ def test_highest_snr_policy_batched_vs_oracle():
     compare_decisions(actions, np.array(ref), flagged, "highest_snr batched")
     assert eng.counters_dict()["errors"] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("tag", ["policy_lbff_nobel-eu_320_l400_s13", "policy_lbff_nsfnet_320_l300_s8"])
+def test_lb_first_fit_policy_vs_reference(tag):
+    """qrmsa_step_heuristic(QRMSA_POLICY_LB_FIRST_FIT) against the reference's heuristic_load_balancing_first_fit."""
+    from optical_networking_gym_b200 import _lib
+    from optical_networking_gym_b200.engine import unpack_bitmaps
+
+    topo = tag.split("_")[2]
+    tb, g = load_tables(topo, 320), load_golden(tag)
+    n = len(g["action"])
+    eng = _engine(tb, 1, n + 1)
+    eng.reset(); eng.load_trace_host(*[np.ascontiguousarray(g[k][:, None]) for k in TRACE_KEYS])
+    for c in (5, 700, n - 705):
+        eng.step_heuristic("load_balancing_first_fit", c)
+    words = eng.actions_host(0, n)
+    w = words.view(np.uint32)
+    actions = (words & _lib.ACTION_MASK).astype(np.int64).T
+    flagged = ((w & _lib.FLAG_NEAR_THRESHOLD) != 0).T
+    n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
+    if n_exc == 0:
+        assert np.abs(eng.gsnr_host(0, n).T[0] - g["gsnr"]).max() < GSNR_TOL_DB
+        assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
+        c = eng.counters_dict()
+        assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
+        rej = (w & _lib.FLAG_ACCEPTED) == 0                    # a reject always reports (True, False), heuristics.py:270
+        assert ((w[rej] & _lib.FLAG_BLOCKED_RESOURCES) != 0).all() and ((w[rej] & _lib.FLAG_BLOCKED_OSNR) == 0).all()
+    eng.close()

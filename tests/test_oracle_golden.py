@@ -154,3 +154,17 @@ def test_oracle_highest_snr_vs_reference(tag, topo):
     assert np.abs(r["gsnr"] - g["gsnr"]).max() < 1e-9
     assert np.array_equal(np.bincount(r["qot_step"], minlength=n), g["n_checks"])
     assert np.array_equal(o.slots(), g["final_slots"])
+
+
+@pytest.mark.parametrize("tag,topo", [("policy_lbff_nobel-eu_320_l400_s13", "nobel-eu"), ("policy_lbff_nsfnet_320_l300_s8", "nsfnet")])
+def test_oracle_lb_first_fit_vs_reference(tag, topo):
+    """heuristic_load_balancing_first_fit (heuristics.py:202-270): paths ordered by occupied fraction, then first fit."""
+    tb, g = load_tables(topo, 320), load_golden(tag)
+    n = len(g["action"])
+    o = orc.OracleEnv(tb, n + 1)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    r = o.run_first_fit(n, policy=3)
+    assert np.array_equal(r["action"], g["action"])
+    assert np.abs(r["gsnr"] - g["gsnr"]).max() < 1e-9
+    assert np.array_equal(r["qot_step"], g["qot_step"]) and np.abs(r["qot_gsnr"] - g["qot_gsnr"]).max() < 1e-9
+    assert np.array_equal(o.slots(), g["final_slots"])

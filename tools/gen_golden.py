@@ -46,6 +46,8 @@ POLICY = [
     # tag, topology, S, load, seed, steps, reference heuristic
     ("lb_nobel-eu_320_l400_s9", "nobel-eu", 320, 400.0, 9, 2000, "load_balancing_best_modulation"),
     ("lb_nsfnet_320_l300_s4", "nsfnet", 320, 300.0, 4, 1500, "load_balancing_best_modulation"),
+    ("lbff_nobel-eu_320_l400_s13", "nobel-eu", 320, 400.0, 13, 2000, "heuristic_load_balancing_first_fit"),
+    ("lbff_nsfnet_320_l300_s8", "nsfnet", 320, 300.0, 8, 1500, "heuristic_load_balancing_first_fit"),
 ]
 EXHAUSTIVE = [
     # tag, topology, S, load, seed, steps, reference heuristic: every valid start of every (path, modulation) is QoT-checked
