@@ -45,7 +45,8 @@ def main():
         for _ in range(args.steps):
             logits = policy(obs.bfloat16()).float()
             logits.masked_fill_(info["mask"] == 0, float("-inf"))
-            action = torch.distributions.Categorical(logits=logits).sample()
+            # masked categorical sample by the Gumbel-max trick: argmax(logits - log E), E ~ Exp(1); no normalisation pass
+            action = (logits - torch.empty_like(logits).exponential_().log_()).argmax(dim=1)
             torch.cuda.synchronize(); t1 = time.perf_counter()
             obs, reward, term, trunc, info = env.step(action)
             torch.cuda.synchronize(); t_env += time.perf_counter() - t1
