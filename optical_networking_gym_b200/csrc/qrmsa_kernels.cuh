@@ -2,22 +2,26 @@
 //
 // Execution model: ONE WARP PER ENVIRONMENT.  Lane j holds word j of a 320/640-slot availability
 // bitmap, so the AND along a path, the contiguous-block search and the commit/release masks are
-// single warp-wide instructions; the GN-model sum strides the lanes over a link's channel records.
-// A warp keeps its env for all n_steps of a launch, so the env's state is pulled from HBM once per
-// launch and then lives in L1/L2.  No tensor cores: no stage is a dense contraction.
+// single warp-wide instructions; the GN-model sum deals the path's channel records to the lanes in
+// groups of four (one 16-byte load each).  A warp keeps its env for all n_steps of a launch, so the
+// env's state is pulled from HBM once per launch and then lives in L1/L2.  No tensor cores: no stage
+// is a dense contraction.
 //
-// HBM layout per env (all per-env blocks are contiguous, 128-byte aligned):
-//   bm     uint32 [E][W]      packed slot bitmaps, 1 = free           (reference: graph["available_slots"],
-//                                                                       int32[E][S], envs/qrmsa.pyx:302-305)
-//   cnt    uint16 [E]         channels on each link
-//   lists  uint32 [E][CAP]    channel records  c2 | n<<12 | mod<<20 | cls<<23   (reference:
+// HBM layout per env (all per-env blocks are contiguous, 64-byte aligned):
+//   bm      uint32 [E][RW]    link rows: words 0..W-1 = packed slots, 1 = free (reference:
+//                             graph["available_slots"], int32[E][S], envs/qrmsa.pyx:302-305); word RW-1 = number of
+//                             channels on the link; RW = 16 (one 64-byte line) up to 479 slots, else 32
+//   lists   uint32 [E][CAP]   channel records  c2 | n<<12 | mod<<20 | cls<<23   (reference:
 //                             topology[u][v]["running_services"], qrmsa.pyx:1305-1306)
-//                             c2 = 2*initial_slot + n  (centre frequency in half-slots)
-//   trace  uint4  [T]         {arrival f32, holding f32, src|dst<<8|rate<<16, action word}
+//                             c2 = 2*initial_slot + n  (centre frequency in half-slots); entries at or past the
+//                             count hold the filler record (class NC: table rows of zeros)
+//   pos     uint8/16 [E][CAP] index, in the link's list, of the channel that starts in slot pair s>>1
+//   trace   uint4  [T]        {arrival f32, holding f32, src|dst<<8|rate<<16, action word}
 //                             request table == service table == decision log
-//   perm   uint16 [T]         request ids sorted by (float32(arrival+holding), id): the release schedule
+//   perm    uint16 [T]        request ids sorted by (float32(arrival+holding), id): the release schedule
 //                             (stands in for the heapq of qrmsa.pyx:1327-1330, :1113-1122)
-//   estate int4               {current request, release pointer, accepted, error}
+//   estate  int4              {current request, release pointer, accepted, error}
+//   counted uint32            requests already covered by k_count_decisions
 //
 // GN model (core/osnr.pyx:21-142), factorised: spans of a link are identical and all
 // frequencies sit on the half-slot grid, so with d = |c2_r - c2| (half-slots) the neighbour term is
