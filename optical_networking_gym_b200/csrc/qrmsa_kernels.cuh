@@ -822,6 +822,32 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
 // CTA first builds X[c2] for every c2 (thread per c2: consecutive threads read consecutive G/INV entries, so the
 // shared-memory lookups are conflict-free), then every (modulation, start) is one lookup + log10.
 // --------------------------------------------------------------------------------------------------------
+// Valid-start bitmaps of every modulation of the open path, by one warp (lane j = word j of the availability): the
+// doubling state carries over as the slot count grows.
+__device__ __forceinline__ void valid_starts_all(const Tab &t, uint32_t av, int rate, int M, uint32_t (*validM)[32], int lane) {
+    uint32_t r = av;
+    int a = 1;
+    for (int mi = 0; mi < M; ++mi) {
+        const int L = t.need(rate * M + (M - 1) - mi) + 1;
+        if (L < a) { r = av; a = 1; }
+        while (a < L) { const int b = min(a, L - a); r &= shr_multi(r, b); a += b; }
+        validM[mi][lane] = r;
+        const unsigned any = __ballot_sync(FULL, r != 0u);
+        if (lane == 31) validM[mi][31] = any ? 1u : 0u;   // word 31 is never spectrum (S <= 960): "some start is valid"
+    }
+}
+
+// Is the neighbour sum at centre c2 (half-slots) needed, i.e. is c2 = 2*s + n for a valid start s of some modulation?
+__device__ __forceinline__ bool centre_needed(const Tab &t, const uint32_t (*validM)[32], int rate, int M, int S, int c2) {
+    bool need = false;
+    for (int mi = 0; mi < M; ++mi) {
+        const int d = c2 - t.need(rate * M + (M - 1) - mi);
+        const int s = d >> 1;
+        if (d >= 0 && !(d & 1) && s < S && ((validM[mi][s >> 5] >> (s & 31)) & 1u)) need = true;
+    }
+    return need;
+}
+
 constexpr int OBS_THREADS = 320;   // 10 warps; two CTAs per SM overlap each other's barrier waits
 constexpr int OBS_NRED = 6;
 
@@ -832,6 +858,8 @@ struct ObsSmem {           // lives after the table blob in dynamic shared memor
     uint32_t valid[32];    // valid-start bitmap of the current modulation
     int link[32], cnt[32];
     double w1[32], w2[32];
+    uint32_t validM[8][32];                    // valid-start bitmaps of all modulations of the open path
+    double part[8][OBS_THREADS / 32][8];       // per-warp partial statistics: [modulation | 7 = free blocks][warp][k]
 };
 
 // sums (or max for index 4, 5) of OBS_NRED per-thread values over the CTA; result broadcast to all threads
@@ -916,6 +944,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                 sm->w2[tid] = t.W2(l);
                 const uint32_t a = path_available(dm, bm, hops, l, lane);
                 sm->av[tid] = a;
+                valid_starts_all(t, a, rate, M, sm->validM, lane);
             }
             __syncthreads();
             // stage the channel records of the path's links
@@ -925,105 +954,134 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                 for (int q = tid; q < c; q += blockDim.x) rec[i * CAP + q] = lst[q];
             }
             __syncthreads();
-            // X[c2]: neighbour sum for a candidate centred at c2 half-slots
-            for (int c2 = tid; c2 < D; c2 += blockDim.x) {
-                double x = 0.0;
-                for (int i = 0; i < hops; ++i) {
-                    const int c = sm->cnt[i];
-                    const uint32_t *r = rec + i * CAP;
-                    double s1 = 0.0, s2 = 0.0;
-                    for (int q = 0; q < c; ++q) {
-                        const uint32_t v = r[q];
-                        const int d = abs((int)(v & 0xfffu) - c2);
-                        s1 += t.G(D, (v >> 23) * D + d);
-                        s2 = fma(t.PHIN(v >> 20), t.INV(d), s2);
+            // X[c2]: neighbour sum for a candidate centred at c2 half-slots -- only where some modulation has a valid
+            // start with that centre (a loaded network leaves most centres unused); a warp whose 32 centres are all
+            // unused skips the sum, the others keep consecutive centres on consecutive lanes (conflict-free lookups)
+            for (int c0 = 0; c0 < D; c0 += blockDim.x) {
+                const int c2 = c0 + tid;
+                const bool need = c2 < D && centre_needed(t, sm->validM, rate, M, S, c2);
+                if (!__any_sync(FULL, need)) continue;
+                if (need) {
+                    double x = 0.0;
+                    for (int i = 0; i < hops; ++i) {
+                        const int c = sm->cnt[i];
+                        const uint32_t *r = rec + i * CAP;
+                        double s1 = 0.0, s2 = 0.0;
+                        for (int q = 0; q < c; ++q) gn_term(t, D, r[q], c2, s1, s2);
+                        x = fma(sm->w1[i], s1, x);
+                        x = fma(sm->w2[i], s2, x);
                     }
-                    x = fma(sm->w1[i], s1, x);
-                    x = fma(sm->w2[i], s2, x);
+                    X[c2] = x;
                 }
-                X[c2] = x;
             }
+            // Statistics are reduced once per path: every warp leaves its partial sums for the free blocks and for each
+            // modulation in shared memory, then warp mi finishes modulation mi.  Four barriers per path instead of
+            // three per modulation.
+            const int nw = blockDim.x >> 5;
+            auto warp_part = [&](double (&v)[8], int slot) {   // k = 0..3, 6: sums; 4, 5: maxima
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    double x = v[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double y = __shfl_xor_sync(FULL, x, o);
+                        x = (k == 4 || k == 5) ? fmax(x, y) : x + y;
+                    }
+                    if (lane == 0) sm->part[slot][warp][k] = x;
+                }
+            };
             // free-block statistics of the path availability (qrmsa.pyx:631-646), thread per slot
-            double bs[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};
-            for (int s = tid; s < S; s += blockDim.x) {
-                const bool free_s = (sm->av[s >> 5] >> (s & 31)) & 1u;
-                const bool free_n = (s + 1 < S) && ((sm->av[(s + 1) >> 5] >> ((s + 1) & 31)) & 1u);
-                if (free_s) bs[0] += 1.0;                       // total available slots
-                if (free_s && !free_n) {                        // a run ends here: walk back to its start
-                    int b = s;
-                    while (b > 0 && ((sm->av[(b - 1) >> 5] >> ((b - 1) & 31)) & 1u)) --b;
-                    const double len = (double)(s - b + 1);
-                    bs[1] += 1.0; bs[2] += len; bs[3] += len * len;
+            {
+                double bs[8] = {0, 0, 0, 0, -1e300, -1e300, 0, 0};
+                for (int s = tid; s < S; s += blockDim.x) {
+                    const bool free_s = (sm->av[s >> 5] >> (s & 31)) & 1u;
+                    const bool free_n = (s + 1 < S) && ((sm->av[(s + 1) >> 5] >> ((s + 1) & 31)) & 1u);
+                    if (free_s) bs[0] += 1.0;                       // total available slots
+                    if (free_s && !free_n) {                        // a run ends here: walk back to its start
+                        int b = s;
+                        while (b > 0 && ((sm->av[(b - 1) >> 5] >> ((b - 1) & 31)) & 1u)) --b;
+                        const double len = (double)(s - b + 1);
+                        bs[1] += 1.0; bs[2] += len; bs[3] += len * len;
+                    }
                 }
+                warp_part(bs, 7);
             }
-            block_reduce6(sm, bs, 0x30u);
-            const double total_av = bs[0], nb = bs[1];
-            double mean_block = 0.0, std_block = 0.0;
-            if (nb > 0.0) {
-                const double mb = bs[2] / nb;
-                const double var = fmax(bs[3] / nb - mb * mb, 0.0);
-                mean_block = ((mb - 4.0) / 4.0) / 100.0;
-                std_block = sqrt(var) / 100.0;
-            }
-            // per modulation: valid starts, GSNR per start, mask and features
-            uint32_t r = 0; int a = 1;
-            if (warp == 0) r = sm->av[lane];
+            __syncthreads();   // X[], validM[] complete
+            // per modulation: GSNR per valid start, mask, partial statistics
             for (int mi = 0; mi < M; ++mi) {
                 const int m = (M - 1) - mi;
                 const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
-                if (warp == 0) {
-                    const int L = n + 1;
-                    if (L < a) { r = sm->av[lane]; a = 1; }
-                    while (a < L) { const int b = min(a, L - a); r &= shr_multi(r, b); a += b; }
-                    sm->valid[lane] = r;
-                }
-                __syncthreads();
-                // count, sum s, sum s^2, sum norm, max s, max norm -- then one more reduction for sum (norm - mean)^2.
-                // Positions are small integers (their sums are exact in FP64), so their variance comes from one pass.
-                double v[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};
+                const double th = p.mod_thr_nomargin[m];
+                // count, sum s, sum s^2, sum norm, max s, max norm, sum norm^2 (positions are small integers and the
+                // normalised GSNR is O(1), so both variances come from one pass in FP64)
+                double v[8] = {0, 0, 0, 0, -1e300, -1e300, 0, 0};
                 for (int s = tid; s < S; s += blockDim.x) {
-                    const bool ok = (sm->valid[s >> 5] >> (s & 31)) & 1u;
+                    const bool ok = (sm->validM[mi][s >> 5] >> (s & 31)) & 1u;
                     uint8_t bit = 0;
                     if (ok) {
                         const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
                         const double g = 10.0 * log10(1.0 / acc);
-                        const double th = p.mod_thr_nomargin[m];
                         const double nrm = rint(((g - th) / fabs(th)) * 1e10) / 1e10;     // np.round(x, 10), osnr.pyx:366
                         bit = nrm >= 0.0 ? 1 : 0;
                         v[0] += 1.0; v[1] += (double)s; v[2] += (double)s * (double)s; v[3] += nrm;
                         v[4] = fmax(v[4], (double)s); v[5] = fmax(v[5], nrm);
-                        NRM[s] = nrm;
+                        v[6] = fma(nrm, nrm, v[6]);
                     }
                     mask[(size_t)pi * M * S + (size_t)mi * S + s] = bit;
                 }
-                block_reduce6(sm, v, 0x30u);
-                const double cntv = v[0];
-                double f_avg = 0, f_std = 0, f_max = 0, best = 0, omean = 0, ovar = 0;
-                if (cntv > 0.0) {
-                    f_avg = v[1] / cntv; omean = v[3] / cntv; f_max = v[4]; best = fmax(v[5], 0.0);
-                    f_std = sqrt(fmax(v[2] / cntv - f_avg * f_avg, 0.0));
-                    double w[OBS_NRED] = {0, 0, 0, 0, -1e300, -1e300};
-                    for (int s = tid; s < S; s += blockDim.x)
-                        if ((sm->valid[s >> 5] >> (s & 31)) & 1u) { const double dn = NRM[s] - omean; w[0] += dn * dn; }
-                    block_reduce6(sm, w, 0x30u);
-                    ovar = w[0] / cntv;
+                warp_part(v, mi);
+            }
+            __syncthreads();   // partial statistics complete
+            if (warp < M) {
+                const int mi = warp, m = (M - 1) - mi;
+                const int n = t.need(rate * M + m);
+                double f[8], b4[4];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    double x = lane < nw ? sm->part[mi][lane][k] : ((k == 4 || k == 5) ? -1e300 : 0.0);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double y = __shfl_xor_sync(FULL, x, o);
+                        x = (k == 4 || k == 5) ? fmax(x, y) : x + y;
+                    }
+                    f[k] = x;
                 }
-                if (tid == 0) {
-                    float *f = obs + 3 + K + (pi * M + mi) * 12;
-                    f[0] = (float)(cntv / (double)S);
-                    f[1] = (float)(f_avg / (double)(S - 1));
-                    f[2] = (float)(f_std / (double)(S - 1));
-                    f[3] = (float)fmax(((double)n - 5.5) / 3.5, 0.0);
-                    f[4] = (float)(2.0 * (total_av - 0.5 * (double)S) / (double)S);
-                    f[5] = (float)mean_block;
-                    f[6] = (float)std_block;
-                    f[7] = (float)best;
-                    f[8] = (float)omean;
-                    f[9] = (float)ovar;
-                    f[10] = (float)(2.0 * ((total_av / (double)S) - 0.5));
-                    f[11] = (float)(f_max / (double)(S - 1));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double x = lane < nw ? sm->part[7][lane][k] : 0.0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+                    b4[k] = x;
                 }
-                __syncthreads();
+                if (lane == 0) {
+                    const double total_av = b4[0], nb = b4[1];
+                    double mean_block = 0.0, std_block = 0.0;
+                    if (nb > 0.0) {
+                        const double mb = b4[2] / nb;
+                        mean_block = ((mb - 4.0) / 4.0) / 100.0;
+                        std_block = sqrt(fmax(b4[3] / nb - mb * mb, 0.0)) / 100.0;
+                    }
+                    const double cntv = f[0];
+                    double f_avg = 0, f_std = 0, f_max = 0, best = 0, omean = 0, ovar = 0;
+                    if (cntv > 0.0) {
+                        f_avg = f[1] / cntv; omean = f[3] / cntv; f_max = f[4]; best = fmax(f[5], 0.0);
+                        f_std = sqrt(fmax(f[2] / cntv - f_avg * f_avg, 0.0));
+                        ovar = fmax(f[6] / cntv - omean * omean, 0.0);
+                    }
+                    float *o = obs + 3 + K + (pi * M + mi) * 12;
+                    o[0] = (float)(cntv / (double)S);
+                    o[1] = (float)(f_avg / (double)(S - 1));
+                    o[2] = (float)(f_std / (double)(S - 1));
+                    o[3] = (float)fmax(((double)n - 5.5) / 3.5, 0.0);
+                    o[4] = (float)(2.0 * (total_av - 0.5 * (double)S) / (double)S);
+                    o[5] = (float)mean_block;
+                    o[6] = (float)std_block;
+                    o[7] = (float)best;
+                    o[8] = (float)omean;
+                    o[9] = (float)ovar;
+                    o[10] = (float)(2.0 * ((total_av / (double)S) - 0.5));
+                    o[11] = (float)(f_max / (double)(S - 1));
+                }
             }
         }
         __syncthreads();
@@ -1117,7 +1175,9 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                     sm->cnt[tid] = tid < hops ? (int)bm[(unsigned)(l * p.RW + p.RW - 1)] : 0;
                     sm->w1[tid] = t.W1(l);
                     sm->w2[tid] = t.W2(l);
-                    sm->av[tid] = path_available(dm, bm, hops, l, lane);
+                    const uint32_t a = path_available(dm, bm, hops, l, lane);
+                    sm->av[tid] = a;
+                    valid_starts_all(t, a, rate, M, sm->validM, lane);
                 }
                 __syncthreads();
                 for (int i = 0; i < hops; ++i) {
@@ -1126,7 +1186,11 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                     for (int q = tid; q < c; q += blockDim.x) rec[i * CAP + q] = lst[q];
                 }
                 __syncthreads();
-                for (int c2 = tid; c2 < D; c2 += blockDim.x) {   // X[c2]: neighbour sum for a candidate centred at c2
+                for (int c0 = 0; c0 < D; c0 += blockDim.x) {   // X[c2]: neighbour sum for a candidate centred at c2, where needed
+                    const int c2 = c0 + tid;
+                    const bool need = c2 < D && centre_needed(t, sm->validM, rate, M, S, c2);
+                    if (!__any_sync(FULL, need)) continue;
+                    if (!need) continue;
                     double x = 0.0;
                     for (int i = 0; i < hops; ++i) {
                         const int c = sm->cnt[i];
@@ -1139,24 +1203,13 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                     }
                     X[c2] = x;
                 }
-                uint32_t r = 0;
-                int a = 1;
-                if (warp == 0) r = sm->av[lane];
+                __syncthreads();   // X complete
                 for (int mi = 0; mi < M; ++mi) {
                     const int m = (M - 1) - mi;
                     const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
-                    __syncthreads();   // X complete / previous valid[] consumed
-                    if (warp == 0) {
-                        const int L = n + 1;
-                        if (L < a) { r = sm->av[lane]; a = 1; }
-                        while (a < L) { const int b = min(a, L - a); r &= shr_multi(r, b); a += b; }
-                        sm->valid[lane] = r;
-                    }
-                    __syncthreads();
-                    int here = 0;
+                    if (!sm->validM[mi][31]) any_res = 1;             // no valid start: blocked_resources (heuristics.py:295-297)
                     for (int s = tid; s < S; s += blockDim.x) {
-                        if (!((sm->valid[s >> 5] >> (s & 31)) & 1u)) continue;
-                        here = 1;
+                        if (!((sm->validM[mi][s >> 5] >> (s & 31)) & 1u)) continue;
                         const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
                         n_checks += 1;
                         const unsigned long long k = (unsigned long long)__double_as_longlong(acc);
@@ -1173,7 +1226,6 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                             any_osnr = 1;
                         }
                     }
-                    if (!__syncthreads_or(here)) any_res = 1;         // no valid start: blocked_resources (heuristics.py:295-297)
                 }
             }
             // ---- winner: smallest acc, first in search order among equals

@@ -1,0 +1,16 @@
+import sys, time, numpy as np, torch
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+from helpers import load_tables
+from optical_networking_gym_b200.env import BatchedQRMSAEnv
+tb = load_tables("nsfnet", 320)
+n = 8192
+env = BatchedQRMSAEnv(tb, n, num_spectrum_resources=320, episode_length=400, load=210.0, bit_rates=(10, 40, 100, 400, 1000),
+                      launch_power_dbm=1.0, gen_observation=False, seed=10, request_source="device")
+env.step_first_fit(300)
+obs = torch.zeros((n, env.observation_space.shape[0]), dtype=torch.float32, device="cuda")
+mask = torch.zeros((n, env.action_space.n), dtype=torch.uint8, device="cuda")
+for _ in range(2): env.engine.observation(obs, mask)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(5): env.engine.observation(obs, mask)
+torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
+print(f"k_observation: {n} envs in {dt*1e3:.2f} ms = {n/dt:,.0f} env/s; valid actions per env {float(mask.sum())/n:.0f}")
