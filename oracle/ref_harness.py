@@ -97,18 +97,25 @@ def seeded_random(seed: int):
         random.Random = orig
 
 
-def make_topology(name: str, k_paths: int = 5, max_span_km: float = 80, att_db_km: float = 0.2, nf_db: float = 4.5):
+# the ONDM 2025 set (reference test_qrmsa.py:11-54, examples/ONDM_2025): same spectral efficiencies, other thresholds
+ONDM_MODULATIONS = (("BPSK", 100_000, 1, 12.6, -14), ("QPSK", 2_000, 2, 12.6, -17), ("8QAM", 1_000, 3, 18.6, -20),
+                    ("16QAM", 500, 4, 22.4, -23), ("32QAM", 250, 5, 26.4, -26), ("64QAM", 125, 6, 30.4, -29))
+
+
+def make_topology(name: str, k_paths: int = 5, max_span_km: float = 80, att_db_km: float = 0.2, nf_db: float = 4.5,
+                  modulations=None):
     ref_topology, _, _, _ = import_reference()
     mods = tuple(
         ref_topology.Modulation(name=n, maximum_length=ml, spectral_efficiency=se, minimum_osnr=mo, inband_xt=xt)
-        for (n, ml, se, mo, xt) in JOCN_MODULATIONS
+        for (n, ml, se, mo, xt) in (modulations or JOCN_MODULATIONS)
     )
     path = os.path.join(TOPO_DIR, TOPOLOGY_FILES[name])
     return ref_topology.get_topology(path, None, mods, max_span_km, att_db_km, nf_db, k_paths)
 
 
 def env_kwargs(topology, n_slots=320, load=300.0, episode_length=1000, launch_power_dbm=1.0, seed=50,
-               bit_rates=(10, 40, 100, 400, 1000), margin=0.0, gen_observation=False, k_paths=5):
+               bit_rates=(10, 40, 100, 400, 1000), margin=0.0, gen_observation=False, k_paths=5,
+               bit_rate_probabilities=None):
     """The JOCN benchmark configuration (graph_load.py:316-336)."""
     return dict(
         topology=topology,
@@ -123,6 +130,7 @@ def env_kwargs(topology, n_slots=320, load=300.0, episode_length=1000, launch_po
         frequency_slot_bandwidth=12.5e9,
         bit_rate_selection="discrete",
         bit_rates=bit_rates,
+        bit_rate_probabilities=bit_rate_probabilities,
         margin=margin,
         measure_disruptions=False,
         file_name="",

@@ -310,3 +310,32 @@ def test_lb_first_fit_policy_vs_reference(tag):
         rej = (w & _lib.FLAG_ACCEPTED) == 0                    # a reject always reports (True, False), heuristics.py:270
         assert ((w[rej] & _lib.FLAG_BLOCKED_RESOURCES) != 0).all() and ((w[rej] & _lib.FLAG_BLOCKED_OSNR) == 0).all()
     eng.close()
+
+
+@pytest.mark.parametrize("tag", ["var_ondm_nsfnet", "var_margin_nobel-eu", "var_k3_nsfnet_160"])
+def test_configuration_variants_vs_reference(tag):
+    """The fused first-fit step away from the JOCN configuration (other modulation thresholds, margin, launch power,
+    bit-rate mix, k, slot count, span parameters): decisions, GSNR, bitmaps and QoT-check count against the reference."""
+    import os
+    from helpers import GOLDEN
+    from optical_networking_gym_b200 import _lib
+    from optical_networking_gym_b200.engine import unpack_bitmaps
+    from optical_networking_gym_b200.tables import StaticTables
+
+    tb = StaticTables.load(os.path.join(GOLDEN, f"tables_{tag}.npz"))
+    g = load_golden("run_" + tag)
+    n = len(g["action"])
+    eng = _engine(tb, 1, n + 1)
+    actions, flagged, accepted, gsnr = _run(eng, g, False, [7, 900, n - 907])
+    n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
+    if n_exc == 0:
+        assert np.array_equal(accepted[0], g["accepted"].astype(bool))
+        assert np.abs(gsnr[0] - g["gsnr"]).max() < GSNR_TOL_DB
+        assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), tb.n_slots)[0], g["final_slots"])
+        c = eng.counters_dict()
+        assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
+    near = np.abs(g["qot_gsnr"] - g["qot_thr"]) < GSNR_TOL_DB * 0.5
+    for s in np.unique(g["qot_step"][near]):
+        if s < n_cmp:
+            assert flagged[0, s]
+    eng.close()

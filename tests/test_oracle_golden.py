@@ -168,3 +168,27 @@ def test_oracle_lb_first_fit_vs_reference(tag, topo):
     assert np.abs(r["gsnr"] - g["gsnr"]).max() < 1e-9
     assert np.array_equal(r["qot_step"], g["qot_step"]) and np.abs(r["qot_gsnr"] - g["qot_gsnr"]).max() < 1e-9
     assert np.array_equal(o.slots(), g["final_slots"])
+
+
+VARIANTS = ["var_ondm_nsfnet", "var_margin_nobel-eu", "var_k3_nsfnet_160"]
+
+
+@pytest.mark.parametrize("tag", VARIANTS)
+def test_oracle_vs_reference_configuration_variants(tag):
+    """Away from the JOCN configuration: the ONDM modulation set (two modulations share a threshold), a 1.5 dB margin
+    with another launch power and a skewed bit-rate mix, k = 3 paths on 160 slots with other span parameters."""
+    import os
+    from helpers import GOLDEN
+    from optical_networking_gym_b200.tables import StaticTables
+
+    tb = StaticTables.load(os.path.join(GOLDEN, f"tables_{tag}.npz"))
+    g = load_golden("run_" + tag)
+    n = len(g["action"])
+    o = orc.OracleEnv(tb, n + 1)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    r = o.run_first_fit(n)
+    assert np.array_equal(r["action"], g["action"])
+    assert np.array_equal(r["accepted"], g["accepted"])
+    assert np.abs(r["gsnr"] - g["gsnr"]).max() < 1e-9
+    assert np.array_equal(r["qot_step"], g["qot_step"]) and np.abs(r["qot_gsnr"] - g["qot_gsnr"]).max() < 1e-9
+    assert np.array_equal(o.slots(), g["final_slots"])

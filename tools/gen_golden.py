@@ -56,6 +56,15 @@ EXHAUSTIVE = [
     ("hsnr_nsfnet_320_l300_s21", "nsfnet", 320, 300.0, 21, 150, "heuristic_highest_snr"),
     ("hsnr_nobel-eu_320_l400_s5", "nobel-eu", 320, 400.0, 5, 90, "heuristic_highest_snr"),
 ]
+VARIANTS = [
+    # first-fit runs away from the JOCN configuration: tag, topology, topology kwargs, env kwargs, seed, steps.
+    # Each writes its own tables fixture (tables_<tag>.npz) because modulations / margin / power / k / spans differ.
+    ("var_ondm_nsfnet", "nsfnet", dict(modulations="ONDM"), dict(n_slots=320, load=250.0, launch_power_dbm=0.0), 31, 2000),
+    ("var_margin_nobel-eu", "nobel-eu", dict(), dict(n_slots=320, load=350.0, launch_power_dbm=-1.0, margin=1.5,
+                                                    bit_rates=(40, 100, 400), bit_rate_probabilities=[0.5, 0.3, 0.2]), 32, 2000),
+    ("var_k3_nsfnet_160", "nsfnet", dict(k_paths=3, max_span_km=100, att_db_km=0.22, nf_db=5.5),
+     dict(n_slots=160, load=120.0, launch_power_dbm=2.0, k_paths=3, bit_rates=(10, 100, 400)), 33, 2000),
+]
 MULTI = [
     # tag, topology, S, load, base_seed, n_envs, steps
     ("nobel-eu_320_l300_b50", "nobel-eu", 320, 300.0, 50, 64, 400),
@@ -210,6 +219,25 @@ def main():
         out["meta_load"] = np.float64(load); out["meta_seed"] = np.int64(seed)
         np.savez_compressed(os.path.join(GOLDEN, f"policy_{tag}.npz"), **out)
         print(f"policy_{tag}: {steps} steps, accept {out['accepted'].mean():.3f}, {time.time() - t0:.1f}s")
+
+    for tag, name, tkw, ekw, seed, steps in VARIANTS:
+        if args.only and args.only not in tag:
+            continue
+        t0 = time.time()
+        tkw = dict(tkw)
+        if tkw.get("modulations") == "ONDM":
+            tkw["modulations"] = rh.ONDM_MODULATIONS
+        topo = rh.make_topology(name, **tkw)
+        tb = StaticTables.from_topology(topo, num_spectrum_resources=ekw["n_slots"],
+                                        bit_rates=ekw.get("bit_rates", BIT_RATES),
+                                        launch_power_dbm=ekw.get("launch_power_dbm", 1.0), margin=ekw.get("margin", 0.0),
+                                        k_paths=ekw.get("k_paths", 5), modulations_to_consider=6)
+        tb.save(os.path.join(GOLDEN, f"tables_{tag}.npz"))
+        out, _ = rh.run_first_fit(topo, seed, steps, **ekw)
+        out["meta_load"] = np.float64(ekw["load"]); out["meta_seed"] = np.int64(seed)
+        np.savez_compressed(os.path.join(GOLDEN, f"run_{tag}.npz"), **out)
+        print(f"run_{tag}: {steps} steps, accept {out['accepted'].mean():.3f}, {len(out['qot_gsnr'])} QoT checks, "
+              f"{time.time() - t0:.1f}s")
 
     for tag, name, S, load, seed, steps, hname in EXHAUSTIVE:
         if args.only and args.only not in ("policy_" + tag):
