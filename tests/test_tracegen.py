@@ -77,3 +77,21 @@ def test_philox_known_answers_and_restatement_properties():
     c = orc.generate_trace_philox(12, 15, 210.0, 77, *tabs, pos0=25)
     assert np.array_equal(a[1][25:], c[1])                                               # and the request index
     assert (a[0] != a[1]).all() and (np.diff(a[3].astype(np.float64), axis=0) >= 0).all()
+
+
+def test_skewed_bit_rate_mix_vs_reference():
+    """bit_rate_probabilities = [0.5, 0.3, 0.2] (qrmsa.pyx:256-257, :1089): the generator's `choices` bisection against
+    the stream the reference drew for the margin / bit-rate-mix recording."""
+    import os
+    from helpers import GOLDEN
+    from optical_networking_gym_b200.tables import StaticTables
+
+    tag = "var_margin_nobel-eu"
+    tb = StaticTables.load(os.path.join(GOLDEN, f"tables_{tag}.npz"))
+    g = load_golden("run_" + tag)
+    tg = TraceGenerator(1, tb.n_nodes, tb.n_rates, float(g["meta_load"]), base_seed=int(g["meta_seed"]),
+                        bit_rate_probabilities=[0.5, 0.3, 0.2])
+    out = tg.next(len(g["src"]))
+    for i, k in enumerate(TRACE_KEYS):
+        assert np.array_equal(out[i][:, 0], g[k]), k
+    assert abs((g["rate"] == 0).mean() - 0.5) < 0.05
