@@ -1008,6 +1008,8 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
             }
             __syncthreads();   // X[], validM[] complete
             // per modulation: GSNR per valid start, mask, partial statistics
+            double g_cached[3] = {0.0, 0.0, 0.0};
+            int n_cached = -1;
             for (int mi = 0; mi < M; ++mi) {
                 const int m = (M - 1) - mi;
                 const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
@@ -1015,12 +1017,22 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                 // count, sum s, sum s^2, sum norm, max s, max norm, sum norm^2 (positions are small integers and the
                 // normalised GSNR is O(1), so both variances come from one pass in FP64)
                 double v[8] = {0, 0, 0, 0, -1e300, -1e300, 0, 0};
-                for (int s = tid; s < S; s += blockDim.x) {
+                const bool same_n = n == n_cached;   // same slot count as the previous modulation: same starts, same GSNR
+#pragma unroll
+                for (int it = 0; it < 3; ++it) {     // S <= 960 = 3 * OBS_THREADS
+                    const int s = tid + it * OBS_THREADS;
+                    if (s >= S) break;
                     const bool ok = (sm->validM[mi][s >> 5] >> (s & 31)) & 1u;
                     uint8_t bit = 0;
                     if (ok) {
-                        const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
-                        const double g = 10.0 * log10(1.0 / acc);
+                        double g;
+                        if (same_n) {
+                            g = g_cached[it];
+                        } else {
+                            const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
+                            g = 10.0 * log10(1.0 / acc);
+                            g_cached[it] = g;
+                        }
                         const double nrm = rint(((g - th) / fabs(th)) * 1e10) / 1e10;     // np.round(x, 10), osnr.pyx:366
                         bit = nrm >= 0.0 ? 1 : 0;
                         v[0] += 1.0; v[1] += (double)s; v[2] += (double)s * (double)s; v[3] += nrm;
@@ -1030,6 +1042,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                     mask[(size_t)pi * M * S + (size_t)mi * S + s] = bit;
                 }
                 warp_part(v, mi);
+                n_cached = n;
             }
             __syncthreads();   // partial statistics complete
             if (warp < M) {
