@@ -620,16 +620,19 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         CK(cudaGetLastError());
         k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
     } else if (policy == QRMSA_POLICY_FIRST_FIT) {
+        CK(cudaMemsetAsync(kp.work, 0, 4, st));
         if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else if (c640) k_step_policy<640, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_LB_FIRST_FIT) {
+        CK(cudaMemsetAsync(kp.work, 0, 4, st));
         if (c320) k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_HIGHEST_SNR) {
         if (!ctx->cta_grid) { ctx->err = "highest-SNR policy needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
         k_step_highest_snr<<<ctx->cta_grid, OBS_THREADS, ctx->cta_smem, st>>>(kp, n_steps);
     } else {
+        CK(cudaMemsetAsync(kp.work, 0, 4, st));
         if (c320) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
     }

@@ -488,12 +488,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
     const int S = dm.S(), M = dm.M(), K = dm.K();
 
     const int lane = threadIdx.x & 31;
-    const int wpc = blockDim.x >> 5;
-    const int gw = blockIdx.x * wpc + (threadIdx.x >> 5);
-    const int gstride = gridDim.x * wpc;
     const int reject = K * M * S;
 
-    for (int env = gw; env < p.n_envs; env += gstride) {
+    // envs are handed out by a ticket counter (zeroed before the launch): a warp that finishes early takes the next
+    // env instead of idling behind a fixed share
+    for (;;) {
+        int env = 0;
+        if (lane == 0) env = atomicAdd(p.work, 1);
+        env = __shfl_sync(FULL, env, 0);
+        if (env >= p.n_envs) break;
         int4 st = p.estate[env];
         if (st.w != ENV_OK) continue;
         int cur = st.x, rel_ptr = st.y, accepted = st.z, err = 0;
