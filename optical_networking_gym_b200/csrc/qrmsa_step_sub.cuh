@@ -72,82 +72,6 @@ __device__ __forceinline__ GnBase gn_base_rec(const KParams &p, const Tab &t, in
     return b;
 }
 
-// Counters that follow from the decision log (decided / accepted / rejected / bit rates / hops / modulation
-// histogram / near-threshold and blocked-by flags), summed after a k_step_sub launch over the requests each env
-// decided since the last count; also maintains the env's accepted total (estate.z).  One warp per env at a time,
-// coalesced reads of the 16-byte request records.
-__global__ void k_count_decisions(const KParams p) {
-    constexpr int NL = 20;
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int per = (p.n_envs + nwarps - 1) / nwarps;
-    const int e0 = warp * per, e1 = min(e0 + per, p.n_envs);
-    const int *rate_tab = reinterpret_cast<const int *>(p.blob + lay::RATE);
-    const int MS = p.M * p.S;
-    uint32_t c[NL];
-    int grp = -1;
-    auto flush = [&]() {
-#pragma unroll
-        for (int k = 0; k < NL; ++k) {
-            uint32_t v = c[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-            const int slot = k == 0 ? QRMSA_CNT_DECIDED : k == 1 ? QRMSA_CNT_ACCEPTED : k == 2 ? QRMSA_CNT_REJECTED :
-                             k == 3 ? QRMSA_CNT_RATE_REQUESTED : k == 4 ? QRMSA_CNT_RATE_PROVISIONED :
-                             k == 5 ? QRMSA_CNT_HOPS_ACCEPTED : k == 6 ? QRMSA_CNT_NEAR_THRESHOLD :
-                             k == 7 ? QRMSA_CNT_BLOCKED_RESOURCES : k == 8 ? QRMSA_CNT_BLOCKED_OSNR :
-                             k == 9 ? QRMSA_CNT_ERRORS : k == 10 ? -1 : k == 11 ? -1 : QRMSA_CNT_MOD_HIST + (k - 12);
-            if (lane == 0 && v && slot >= 0 && grp >= 0)
-                atomicAdd(p.counters + (size_t)grp * QRMSA_N_COUNTERS + slot, (unsigned long long)v);
-            c[k] = 0u;
-        }
-    };
-#pragma unroll
-    for (int k = 0; k < NL; ++k) c[k] = 0u;
-    for (int env = e0; env < e1; ++env) {
-        const int g = env / p.group_size;
-        if (g != grp) {
-            flush();
-            grp = g;
-        }
-        const int4 es = p.estate[env];
-        const int first = (int)p.counted[env], last = es.x;
-        const uint4 *tr = p.trace + (size_t)env * p.T;
-        uint32_t acc_here = 0u;
-        for (int i = first + lane; i < last; i += 32) {
-            const uint4 rq = tr[i];
-            if (!(rq.w & QRMSA_FLAG_DECIDED)) continue;
-            const int rate = rate_tab[(rq.z >> 16) & 0xff];
-            c[0] += 1u;
-            c[3] += (uint32_t)rate;
-            if (rq.w & QRMSA_FLAG_NEAR_THRESHOLD) c[6] += 1u;
-            if (rq.w & QRMSA_FLAG_ACCEPTED) {
-                const uint32_t a = rq.w & QRMSA_ACTION_MASK;
-                const int pi = a / MS, m = (p.M - 1) - (int)((a / p.S) % p.M);
-                const int path = ((rq.z & 0xff) * p.N + ((rq.z >> 8) & 0xff)) * p.K + pi;
-                c[1] += 1u;
-                acc_here += 1u;
-                c[4] += (uint32_t)rate;
-                c[5] += __ldg(reinterpret_cast<const uint32_t *>(p.prec + (size_t)path * 4) + 12) & 0x7fu;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) c[12 + k] += (m == k) ? 1u : 0u;
-            } else {
-                c[2] += 1u;
-                if (rq.w & QRMSA_FLAG_BLOCKED_RESOURCES) c[7] += 1u;
-                if (rq.w & QRMSA_FLAG_BLOCKED_OSNR) c[8] += 1u;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc_here += __shfl_xor_sync(FULL, acc_here, o);
-        if (lane == 0) {
-            if (es.w != ENV_OK && first < last) c[9] += 1u;   // an env that stopped on an error during this span
-            if (acc_here) p.estate[env].z = es.z + (int)acc_here;
-            p.counted[env] = (uint32_t)last;
-        }
-    }
-    flush();
-}
-
 constexpr int SUB_HCAP = 16;   // hops per path the per-env link scratch holds (qrmsa_create routes longer paths to k_step_policy)
 
 template <int LPE, int S_, int M_, int K_>
