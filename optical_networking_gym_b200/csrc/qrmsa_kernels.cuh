@@ -981,14 +981,23 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
             // modulation in shared memory, then warp mi finishes modulation mi.  Four barriers per path instead of
             // three per modulation.
             const int nw = blockDim.x >> 5;
-            auto warp_part = [&](double (&v)[8], int slot) {   // k = 0..3, 6: sums; 4, 5: maxima
+            // k = 0..3, 6: sums; 4, 5: maxima.  Entries named in int_mask are small exact integers (counts, slot indices and
+            // their squares): they take one warp-reduce instruction instead of five shuffle rounds in FP64.
+            auto warp_part = [&](double (&v)[8], int slot, const unsigned int_mask) {
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
-                    double x = v[k];
+                    double x;
+                    if ((int_mask >> k) & 1u) {
+                        const int iv = v[k] < -1e299 ? -1 : (int)v[k];
+                        const int r = k == 4 ? __reduce_max_sync(FULL, iv) : __reduce_add_sync(FULL, iv);
+                        x = (k == 4 && r < 0) ? -1e300 : (double)r;
+                    } else {
+                        x = v[k];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double y = __shfl_xor_sync(FULL, x, o);
-                        x = (k == 4 || k == 5) ? fmax(x, y) : x + y;
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const double y = __shfl_xor_sync(FULL, x, o);
+                            x = (k == 4 || k == 5) ? fmax(x, y) : x + y;
+                        }
                     }
                     if (lane == 0) sm->part[slot][warp][k] = x;
                 }
@@ -1007,7 +1016,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                         bs[1] += 1.0; bs[2] += len; bs[3] += len * len;
                     }
                 }
-                warp_part(bs, 7);
+                warp_part(bs, 7, 0x0fu);   // free slots, blocks, sum of lengths, sum of squared lengths
             }
             __syncthreads();   // X[], validM[] complete
             // per modulation: GSNR per valid start, mask, partial statistics
@@ -1044,7 +1053,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                     }
                     mask[(size_t)pi * M * S + (size_t)mi * S + s] = bit;
                 }
-                warp_part(v, mi);
+                warp_part(v, mi, 0x17u);   // count, sum s, sum s^2, max s
                 n_cached = n;
             }
             __syncthreads();   // partial statistics complete
