@@ -41,7 +41,7 @@ struct qrmsa_ctx {
     std::vector<int> cls_n;
     const double *d_path_len_norm = nullptr;
     double inv_max_rate = 0.0;
-    int obs_grid = 0;
+    int obs_grid = 0, obs_epc = 0, obs_env_smem = 0;   // k_observation: envs per CTA, shared memory per env
     size_t obs_smem = 0;
     std::string err;
 };
@@ -345,11 +345,16 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         double mx = 0.0;
         for (int r = 0; r < R; r++) mx = std::max(mx, (double)rate_milli[r]);
         ctx->inv_max_rate = mx > 0 ? 1.0 / mx : 0.0;
-        ctx->obs_smem = (size_t)kp.blob_bytes + sizeof(ObsSmem) + (size_t)D * 8 + (size_t)S * 8 + (size_t)kp.Hmax * kp.CAP * 4;
+        // up to OBS_MAX_EPC envs per CTA (each with its own X / record staging area after the shared tables)
+        ctx->obs_env_smem = (int)round_up(sizeof(ObsSmem) + (size_t)D * 8 + (size_t)S * 8 + (size_t)kp.Hmax * kp.CAP * 4, 16);
+        int epc = OBS_MAX_EPC;
+        while (epc > 1 && kp.blob_bytes + epc * ctx->obs_env_smem > ctx->smem_optin) epc >>= 1;
+        ctx->obs_smem = (size_t)kp.blob_bytes + (size_t)epc * ctx->obs_env_smem;
         if ((int)ctx->obs_smem <= ctx->smem_optin) {
+            ctx->obs_epc = epc;
             CK(cudaFuncSetAttribute(k_observation, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->obs_smem));
-            const int per_sm = (2 * (ctx->obs_smem + 1024) <= (size_t)smem_sm) ? 2 : 1;
-            ctx->obs_grid = std::min(n_envs, ctx->sm_count * per_sm);
+            const int per_sm = std::max(1, std::min((int)((size_t)smem_sm / (ctx->obs_smem + 1024)), 2048 / (epc * OBS_ENV_THREADS)));
+            ctx->obs_grid = std::min((n_envs + epc - 1) / epc, ctx->sm_count * per_sm);
         }
     }
 
@@ -674,8 +679,8 @@ extern "C" int qrmsa_observation(qrmsa_ctx *ctx, float *d_obs, uint8_t *d_mask, 
     CK(cudaSetDevice(ctx->device));
     int obs_dim = 0, n_actions = 0;
     qrmsa_observation_dims(ctx, &obs_dim, &n_actions);
-    k_observation<<<ctx->obs_grid, OBS_THREADS, ctx->obs_smem, (cudaStream_t)stream>>>(
-        ctx->kp, ctx->d_path_len_norm, ctx->inv_max_rate, d_obs, d_mask, obs_dim, n_actions);
+    k_observation<<<ctx->obs_grid, ctx->obs_epc * OBS_ENV_THREADS, ctx->obs_smem, (cudaStream_t)stream>>>(
+        ctx->kp, ctx->d_path_len_norm, ctx->inv_max_rate, d_obs, d_mask, obs_dim, n_actions, ctx->obs_epc, ctx->obs_env_smem);
     CK(cudaGetLastError());
     return QRMSA_OK;
 }

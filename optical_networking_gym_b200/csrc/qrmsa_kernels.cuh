@@ -851,7 +851,10 @@ __device__ __forceinline__ bool centre_needed(const Tab &t, const uint32_t (*val
     return need;
 }
 
-constexpr int OBS_THREADS = 320;   // 10 warps; two CTAs per SM overlap each other's barrier waits
+constexpr int OBS_THREADS = 320;       // k_step_highest_snr: 10 warps per env, two CTAs per SM
+constexpr int OBS_ENV_THREADS = 160;   // k_observation: 5 warps per env, up to OBS_MAX_EPC envs per CTA
+constexpr int OBS_MAX_EPC = 4;
+constexpr int OBS_MAX_IT = 6;          // 960 slots / OBS_ENV_THREADS
 constexpr int OBS_NRED = 6;
 
 struct ObsSmem {           // lives after the table blob in dynamic shared memory
@@ -897,23 +900,28 @@ __device__ __forceinline__ void block_reduce6(ObsSmem *sm, double v[OBS_NRED], c
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(OBS_THREADS, 2)
+__global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
     k_observation(const KParams p, const double *__restrict__ path_len_norm, const double inv_max_rate,
-                  float *__restrict__ obs_out, uint8_t *__restrict__ mask_out, const int obs_dim, const int n_actions) {
+                  float *__restrict__ obs_out, uint8_t *__restrict__ mask_out, const int obs_dim, const int n_actions,
+                  const int epc, const int env_smem) {
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
     Tab t;
     t.init();
     const Dim<0, 0, 0> dm(p);
     const int S = p.S, W = p.W, M = p.M, K = p.K, D = p.D, CAP = p.CAP;
-    unsigned char *extra = qsmem + p.blob_bytes;
+    // epc envs per CTA, OBS_ENV_THREADS threads each, synchronised by their own named barrier: while the warps of one
+    // env wait for its slowest warp, the warps of the other envs keep the SM busy (the tables are shared)
+    const int slot = threadIdx.x / OBS_ENV_THREADS;
+    auto env_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(OBS_ENV_THREADS) : "memory"); };
+    unsigned char *extra = qsmem + p.blob_bytes + (size_t)slot * env_smem;
     ObsSmem *sm = reinterpret_cast<ObsSmem *>(extra);
     double *X = reinterpret_cast<double *>(extra + sizeof(ObsSmem));          // [D]
     double *NRM = X + D;                                                        // [S] normalised GSNR per start
     uint32_t *rec = reinterpret_cast<uint32_t *>(NRM + p.S);                    // [Hmax][CAP]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x - slot * OBS_ENV_THREADS, lane = tid & 31, warp = tid >> 5;
 
-    for (int env = blockIdx.x; env < p.n_envs; env += gridDim.x) {
+    for (int env = blockIdx.x * epc + slot; env < p.n_envs; env += gridDim.x * epc) {
         const int4 st = p.estate[env];
         float *obs = obs_out + (size_t)env * obs_dim;
         uint8_t *mask = mask_out + (size_t)env * n_actions;
@@ -934,11 +942,11 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
             const int hops = __ldg(p.path_hops + path) & 0x7f;
             if (tid == 0) obs[3 + pi] = hops ? (float)path_len_norm[path] : 0.f;
             if (hops == 0) {   // fewer than k paths for this pair: features stay -1, no valid action (qrmsa.pyx:697)
-                for (int i = tid; i < M * 12; i += blockDim.x) obs[3 + K + pi * M * 12 + i] = -1.f;
-                for (int i = tid; i < M * S; i += blockDim.x) mask[(size_t)pi * M * S + i] = 0;
+                for (int i = tid; i < M * 12; i += OBS_ENV_THREADS) obs[3 + K + pi * M * 12 + i] = -1.f;
+                for (int i = tid; i < M * S; i += OBS_ENV_THREADS) mask[(size_t)pi * M * S + i] = 0;
                 continue;
             }
-            __syncthreads();
+            env_sync();
             if (tid < 32) {
                 const int l = tid < hops ? __ldg(p.path_links + path * p.Hmax + tid) : 0;
                 sm->link[tid] = l;
@@ -949,18 +957,18 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                 sm->av[tid] = a;
                 valid_starts_all(t, a, rate, M, sm->validM, lane);
             }
-            __syncthreads();
+            env_sync();
             // stage the channel records of the path's links
             for (int i = 0; i < hops; ++i) {
                 const int c = sm->cnt[i];
                 const uint32_t *lst = lists + (unsigned)(sm->link[i] * CAP);
-                for (int q = tid; q < c; q += blockDim.x) rec[i * CAP + q] = lst[q];
+                for (int q = tid; q < c; q += OBS_ENV_THREADS) rec[i * CAP + q] = lst[q];
             }
-            __syncthreads();
+            env_sync();
             // X[c2]: neighbour sum for a candidate centred at c2 half-slots -- only where some modulation has a valid
             // start with that centre (a loaded network leaves most centres unused); a warp whose 32 centres are all
             // unused skips the sum, the others keep consecutive centres on consecutive lanes (conflict-free lookups)
-            for (int c0 = 0; c0 < D; c0 += blockDim.x) {
+            for (int c0 = 0; c0 < D; c0 += OBS_ENV_THREADS) {
                 const int c2 = c0 + tid;
                 const bool need = c2 < D && centre_needed(t, sm->validM, rate, M, S, c2);
                 if (!__any_sync(FULL, need)) continue;
@@ -980,7 +988,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
             // Statistics are reduced once per path: every warp leaves its partial sums for the free blocks and for each
             // modulation in shared memory, then warp mi finishes modulation mi.  Four barriers per path instead of
             // three per modulation.
-            const int nw = blockDim.x >> 5;
+            const int nw = OBS_ENV_THREADS >> 5;
             // k = 0..3, 6: sums; 4, 5: maxima.  Entries named in int_mask are small exact integers (counts, slot indices and
             // their squares): they take one warp-reduce instruction instead of five shuffle rounds in FP64.
             auto warp_part = [&](double (&v)[8], int slot, const unsigned int_mask) {
@@ -1005,7 +1013,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
             // free-block statistics of the path availability (qrmsa.pyx:631-646), thread per slot
             {
                 double bs[8] = {0, 0, 0, 0, -1e300, -1e300, 0, 0};
-                for (int s = tid; s < S; s += blockDim.x) {
+                for (int s = tid; s < S; s += OBS_ENV_THREADS) {
                     const bool free_s = (sm->av[s >> 5] >> (s & 31)) & 1u;
                     const bool free_n = (s + 1 < S) && ((sm->av[(s + 1) >> 5] >> ((s + 1) & 31)) & 1u);
                     if (free_s) bs[0] += 1.0;                       // total available slots
@@ -1018,9 +1026,11 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                 }
                 warp_part(bs, 7, 0x0fu);   // free slots, blocks, sum of lengths, sum of squared lengths
             }
-            __syncthreads();   // X[], validM[] complete
+            env_sync();   // X[], validM[] complete
             // per modulation: GSNR per valid start, mask, partial statistics
-            double g_cached[3] = {0.0, 0.0, 0.0};
+            double g_cached[OBS_MAX_IT];
+#pragma unroll
+            for (int it = 0; it < OBS_MAX_IT; ++it) g_cached[it] = 0.0;
             int n_cached = -1;
             for (int mi = 0; mi < M; ++mi) {
                 const int m = (M - 1) - mi;
@@ -1031,8 +1041,8 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                 double v[8] = {0, 0, 0, 0, -1e300, -1e300, 0, 0};
                 const bool same_n = n == n_cached;   // same slot count as the previous modulation: same starts, same GSNR
 #pragma unroll
-                for (int it = 0; it < 3; ++it) {     // S <= 960 = 3 * OBS_THREADS
-                    const int s = tid + it * OBS_THREADS;
+                for (int it = 0; it < OBS_MAX_IT; ++it) {     // S <= 960 = OBS_MAX_IT * OBS_ENV_THREADS
+                    const int s = tid + it * OBS_ENV_THREADS;
                     if (s >= S) break;
                     const bool ok = (sm->validM[mi][s >> 5] >> (s & 31)) & 1u;
                     uint8_t bit = 0;
@@ -1056,9 +1066,9 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                 warp_part(v, mi, 0x17u);   // count, sum s, sum s^2, max s
                 n_cached = n;
             }
-            __syncthreads();   // partial statistics complete
-            if (warp < M) {
-                const int mi = warp, m = (M - 1) - mi;
+            env_sync();   // partial statistics complete
+            for (int mi = warp; mi < M; mi += nw) {   // warp w finishes modulations w, w + nw, ...
+                const int m = (M - 1) - mi;
                 const int n = t.need(rate * M + m);
                 double f[8], b4[4];
 #pragma unroll
@@ -1109,7 +1119,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2)
                 }
             }
         }
-        __syncthreads();
+        env_sync();
     }
 }
 
