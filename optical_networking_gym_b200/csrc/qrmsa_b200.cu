@@ -24,7 +24,7 @@ struct qrmsa_ctx {
     bool use_warp_kernel = false;
     size_t sub_smem = 0;
     size_t cta_smem = 0;   // k_step_highest_snr (and k_observation): one CTA per env
-    int cta_grid = 0;
+    int cta_grid = 0, cta_epc = 0, cta_env_smem = 0;
     // on-device request generator
     float *gen_clock = nullptr;
     double *gen_tables = nullptr;   // load[n_envs] | src_cum[N] | dst_cum[N*N] | rate_cum[R]
@@ -329,11 +329,17 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
 
     // ---- CTA-per-env kernels (observation, highest-SNR policy): shared memory = tables + X[c2] + staged records
     int rc;
-    ctx->cta_smem = (size_t)kp.blob_bytes + sizeof(ObsSmem) + (size_t)D * 8 + (size_t)S * 8 + (size_t)kp.Hmax * kp.CAP * 4;
-    if ((int)ctx->cta_smem <= ctx->smem_optin) {
-        CK(cudaFuncSetAttribute(k_step_highest_snr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->cta_smem));
-        const int per_sm = (2 * (ctx->cta_smem + 1024) <= (size_t)smem_sm) ? 2 : 1;
-        ctx->cta_grid = std::min(n_envs, ctx->sm_count * per_sm);
+    ctx->cta_env_smem = (int)round_up(sizeof(ObsSmem) + (size_t)D * 8 + (size_t)S * 8 + (size_t)kp.Hmax * kp.CAP * 4, 16);
+    {
+        int epc = OBS_MAX_EPC;   // envs per CTA, each with its own staging area after the shared tables
+        while (epc > 1 && kp.blob_bytes + epc * ctx->cta_env_smem > ctx->smem_optin) epc >>= 1;
+        ctx->cta_smem = (size_t)kp.blob_bytes + (size_t)epc * ctx->cta_env_smem;
+        if ((int)ctx->cta_smem <= ctx->smem_optin) {
+            ctx->cta_epc = epc;
+            CK(cudaFuncSetAttribute(k_step_highest_snr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->cta_smem));
+            const int per_sm = std::max(1, std::min((int)((size_t)smem_sm / (ctx->cta_smem + 1024)), 2048 / (epc * OBS_ENV_THREADS)));
+            ctx->cta_grid = std::min((n_envs + epc - 1) / epc, ctx->sm_count * per_sm);
+        }
     }
     // ---- observation kernel: route-length normalisation (qrmsa.pyx:676-690) and launch shape
     if (t->path_length_km && t->link_length_km) {
@@ -635,7 +641,7 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         else k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_HIGHEST_SNR) {
         if (!ctx->cta_grid) { ctx->err = "highest-SNR policy needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
-        k_step_highest_snr<<<ctx->cta_grid, OBS_THREADS, ctx->cta_smem, st>>>(kp, n_steps);
+        k_step_highest_snr<<<ctx->cta_grid, ctx->cta_epc * OBS_ENV_THREADS, ctx->cta_smem, st>>>(kp, n_steps, ctx->cta_epc, ctx->cta_env_smem);
     } else {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
         if (c320) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);

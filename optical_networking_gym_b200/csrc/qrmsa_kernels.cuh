@@ -1133,17 +1133,20 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
 // candidate wins a tie.  The reference compares GSNR in dB, several 1/GSNR values share one dB value, so a
 // runner-up within 1e-6 dB of the winner raises QRMSA_FLAG_NEAR_TIE (reported like the near-threshold flag).
 // --------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long *red, unsigned long long *bc) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// minimum over the OBS_ENV_THREADS threads of one env (named barrier `bar`); red has one entry per warp of the env
+__device__ __forceinline__ void env_bar(int bar) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(OBS_ENV_THREADS) : "memory"); }
+
+__device__ __forceinline__ unsigned long long env_min_u64(unsigned long long v, unsigned long long *red, unsigned long long *bc,
+                                                          int lane, int warp, int bar) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long y = __shfl_xor_sync(FULL, v, o);
         v = y < v ? y : v;
     }
     if (lane == 0) red[warp] = v;
-    __syncthreads();
+    env_bar(bar);
     if (warp == 0) {
-        unsigned long long x = lane < (int)(blockDim.x >> 5) ? red[lane] : ~0ull;
+        unsigned long long x = lane < OBS_ENV_THREADS / 32 ? red[lane] : ~0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long y = __shfl_xor_sync(FULL, x, o);
@@ -1151,31 +1154,37 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
         }
         if (lane == 0) *bc = x;
     }
-    __syncthreads();
+    env_bar(bar);
     const unsigned long long r = *bc;
-    __syncthreads();
+    env_bar(bar);
     return r;
 }
 
-__global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KParams p, const int n_steps) {
+__global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
+    k_step_highest_snr(const KParams p, const int n_steps, const int epc, const int env_smem) {
     __shared__ uint64_t mbar;
-    __shared__ unsigned long long red64[OBS_THREADS / 32], bc64;
-    __shared__ unsigned int s_checks, s_terms;
-    __shared__ int s_cur, s_err;
+    __shared__ unsigned long long red64_[OBS_MAX_EPC][OBS_ENV_THREADS / 32], bc64_[OBS_MAX_EPC];
+    __shared__ unsigned int s_checks_[OBS_MAX_EPC], s_terms_[OBS_MAX_EPC], s_osnr_[OBS_MAX_EPC];
+    __shared__ int s_cur_[OBS_MAX_EPC], s_err_[OBS_MAX_EPC];
     stage_tables(p, &mbar);
     Tab t;
     t.init();
     const Dim<0, 0, 0> dm(p);
     const int S = p.S, M = p.M, K = p.K, D = p.D, CAP = p.CAP;
-    unsigned char *extra = qsmem + p.blob_bytes;
+    // epc envs per CTA, OBS_ENV_THREADS threads each, each env on its own named barrier (see k_observation)
+    const int slot = threadIdx.x / OBS_ENV_THREADS, bar = slot + 1;
+    unsigned long long *red64 = red64_[slot], &bc64 = bc64_[slot];
+    unsigned int &s_checks = s_checks_[slot], &s_terms = s_terms_[slot], &s_osnr = s_osnr_[slot];
+    int &s_cur = s_cur_[slot], &s_err = s_err_[slot];
+    unsigned char *extra = qsmem + p.blob_bytes + (size_t)slot * env_smem;
     ObsSmem *sm = reinterpret_cast<ObsSmem *>(extra);
     double *X = reinterpret_cast<double *>(extra + sizeof(ObsSmem));          // [D]
     uint32_t *rec = reinterpret_cast<uint32_t *>(X + D + p.S);                  // [Hmax][CAP]  (same carve-up as k_observation)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x - slot * OBS_ENV_THREADS, lane = tid & 31, warp = tid >> 5;
     const int reject = K * M * S;
     const double TIE = 1.0000002302585359;   // 10^(1e-6 / 10): 1e-6 dB on the linear value
 
-    for (int env = blockIdx.x; env < p.n_envs; env += gridDim.x) {
+    for (int env = blockIdx.x * epc + slot; env < p.n_envs; env += gridDim.x * epc) {
         int4 st = p.estate[env];
         if (st.w != ENV_OK) continue;   // (uniform over the CTA)
         int cur = st.x, rel_ptr = st.y, err = 0;
@@ -1186,7 +1195,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
         uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
         Head head = load_head(p, tr, perm, rel_ptr);
         unsigned long long *cglob = p.counters + (size_t)(env / p.group_size) * QRMSA_N_COUNTERS;
-        if (tid == 0) { s_checks = 0u; s_terms = 0u; }
+        if (tid == 0) { s_checks = 0u; s_terms = 0u; s_osnr = 0u; }
 
 #pragma unroll 1
         for (int step = 0; step < n_steps && cur + 1 < p.n_req && !err; ++step) {
@@ -1203,7 +1212,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                 const int path = pbase + pi;
                 const int hops = __ldg(p.path_hops + path) & 0x7f;
                 if (hops == 0) continue;
-                __syncthreads();
+                env_bar(bar);
                 if (tid < 32) {
                     const int l = tid < hops ? __ldg(p.path_links + path * p.Hmax + tid) : 0;
                     sm->link[tid] = l;
@@ -1214,14 +1223,14 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                     sm->av[tid] = a;
                     valid_starts_all(t, a, rate, M, sm->validM, lane);
                 }
-                __syncthreads();
+                env_bar(bar);
                 for (int i = 0; i < hops; ++i) {
                     const int c = sm->cnt[i];
                     const uint32_t *lst = lists + (unsigned)(sm->link[i] * CAP);
-                    for (int q = tid; q < c; q += blockDim.x) rec[i * CAP + q] = lst[q];
+                    for (int q = tid; q < c; q += OBS_ENV_THREADS) rec[i * CAP + q] = lst[q];
                 }
-                __syncthreads();
-                for (int c0 = 0; c0 < D; c0 += blockDim.x) {   // X[c2]: neighbour sum for a candidate centred at c2, where needed
+                env_bar(bar);
+                for (int c0 = 0; c0 < D; c0 += OBS_ENV_THREADS) {   // X[c2]: neighbour sum for a candidate centred at c2, where needed
                     const int c2 = c0 + tid;
                     const bool need = c2 < D && centre_needed(t, sm->validM, rate, M, S, c2);
                     if (!__any_sync(FULL, need)) continue;
@@ -1238,12 +1247,12 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                     }
                     X[c2] = x;
                 }
-                __syncthreads();   // X complete
+                env_bar(bar);   // X complete
                 for (int mi = 0; mi < M; ++mi) {
                     const int m = (M - 1) - mi;
                     const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
                     if (!sm->validM[mi][31]) any_res = 1;             // no valid start: blocked_resources (heuristics.py:295-297)
-                    for (int s = tid; s < S; s += blockDim.x) {
+                    for (int s = tid; s < S; s += OBS_ENV_THREADS) {
                         if (!((sm->validM[mi][s >> 5] >> (s & 31)) & 1u)) continue;
                         const double acc = gn_base(p, t, path, s, n, ncls).with(X[2 * s + n]);
                         n_checks += 1;
@@ -1264,11 +1273,13 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                 }
             }
             // ---- winner: smallest acc, first in search order among equals
-            const unsigned long long gbest = block_min_u64(best, red64, &bc64);
-            const int widx = (int)block_min_u64(best == gbest ? (unsigned long long)(unsigned)best_idx : ~0ull, red64, &bc64);
-            const unsigned long long gsecond = block_min_u64((best == gbest && best_idx == widx) ? second : best, red64, &bc64);
-            const unsigned long long gnear = block_min_u64(near, red64, &bc64);
-            const int g_osnr = __syncthreads_or(any_osnr);
+            const unsigned long long gbest = env_min_u64(best, red64, &bc64, lane, warp, bar);
+            const int widx = (int)env_min_u64(best == gbest ? (unsigned long long)(unsigned)best_idx : ~0ull, red64, &bc64, lane, warp, bar);
+            const unsigned long long gsecond = env_min_u64((best == gbest && best_idx == widx) ? second : best, red64, &bc64, lane, warp, bar);
+            const unsigned long long gnear = env_min_u64(near, red64, &bc64, lane, warp, bar);
+            if (__any_sync(FULL, any_osnr) && lane == 0) atomicOr(&s_osnr, 1u);
+            env_bar(bar);
+            const int g_osnr = (int)s_osnr;
             const bool found = gbest != ~0ull;
             uint32_t flags = QRMSA_FLAG_DECIDED;
             // a check within 1e-3 dB of its threshold matters when flipping it could change the outcome: no acceptable
@@ -1292,7 +1303,7 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                 for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(FULL, v0, o); v1 += __shfl_xor_sync(FULL, v1, o); }
                 if (lane == 0) { atomicAdd(&s_checks, v0); atomicAdd(&s_terms, v1); }
             }
-            __syncthreads();
+            env_bar(bar);
             if (warp == 0) {
                 if (found) {
                     const int s = widx % S, mi = (widx / S) % M, pi = widx / (S * M), m = (M - 1) - mi;
@@ -1322,17 +1333,17 @@ __global__ void __launch_bounds__(OBS_THREADS, 2) k_step_highest_snr(const KPara
                     atomicAdd(cglob + QRMSA_CNT_GN_TERMS, (unsigned long long)s_terms);
                     atomicAdd(cglob + QRMSA_CNT_PATHS_TRIED, (unsigned long long)K);
                     if (n_rel) atomicAdd(cglob + QRMSA_CNT_RELEASES, (unsigned long long)n_rel);
-                    s_checks = 0u; s_terms = 0u;
+                    s_checks = 0u; s_terms = 0u; s_osnr = 0u;
                     s_cur = cur; s_err = err;
                 }
             }
-            __syncthreads();
+            env_bar(bar);
             cur = s_cur;
             err = s_err;
-            __syncthreads();
+            env_bar(bar);
         }
         if (tid == 0) p.estate[env] = make_int4(cur, rel_ptr, st.z, err);
-        __syncthreads();
+        env_bar(bar);
     }
 }
 
