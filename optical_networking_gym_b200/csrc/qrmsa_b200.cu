@@ -538,8 +538,11 @@ static int build_schedule(qrmsa_ctx *ctx, int n_requests, cudaStream_t st) {
     const KParams &kp = ctx->kp;
     int n_pad = 2;
     while (n_pad < n_requests) n_pad <<= 1;
-    int threads = n_pad / 2 < 1024 ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : 1024;
-    int blocks = kp.n_envs < ctx->sm_count * 8 ? kp.n_envs : ctx->sm_count * 8;
+    // barrier-heavy (one per compare-exchange stage): several small CTAs per SM overlap each other's waits
+    int cap = 256;
+    if (const char *e = getenv("QRMSA_SORT_THREADS")) cap = atoi(e) >= 32 ? atoi(e) : cap;
+    int threads = n_pad / 2 < cap ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : cap;
+    int blocks = kp.n_envs < ctx->sm_count * 16 ? kp.n_envs : ctx->sm_count * 16;
     k_build_schedule<<<blocks, threads, (size_t)n_pad * 8, st>>>(kp, n_requests, n_pad);
     CK(cudaGetLastError());
     return QRMSA_OK;
@@ -574,7 +577,7 @@ extern "C" int qrmsa_generate_trace(qrmsa_ctx *ctx, uint64_t seed, int restart, 
     CK(cudaStreamSynchronize(st));   // the host tables may be pageable and short-lived
     kp.n_req = n_requests;
     // set_load takes the holding time as a C float (qrmsa.pyx:1124)
-    k_generate_trace<<<(kp.n_envs + 127) / 128, 128, 0, st>>>(kp, seed, ctx->gen_pos, env_offset, d_load,
+    k_generate_trace<<<(kp.n_envs + 7) / 8, 256, 0, st>>>(kp, seed, ctx->gen_pos, env_offset, d_load,
                                                               (double)(float)mean_holding_time, d_src, d_dst, d_rate,
                                                               ctx->gen_clock, n_requests);
     CK(cudaGetLastError());

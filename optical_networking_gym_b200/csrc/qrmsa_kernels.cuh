@@ -1428,11 +1428,15 @@ __device__ __forceinline__ int bisect_right_dev(const double *__restrict__ a, do
     return lo;
 }
 
+// One warp per env: the draws of 32 consecutive requests are made in parallel (they depend only on the request
+// index), then the float32 clock -- at_k = float32(at_{k-1} + x_k), a rounding chain that cannot be reassociated --
+// is walked through the 32 inter-arrival times; the records leave as one coalesced 512-byte store.
 __global__ void k_generate_trace(const KParams p, const unsigned long long seed, const unsigned long long pos0,
                                  const long long env_offset, const double *__restrict__ load, const double mean_holding,
                                  const double *__restrict__ src_cum, const double *__restrict__ dst_cum,
                                  const double *__restrict__ rate_cum, float *__restrict__ clock, const int n_req) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (e >= p.n_envs) return;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const unsigned long long ge = (unsigned long long)(env_offset + e);
@@ -1441,20 +1445,28 @@ __global__ void k_generate_trace(const KParams p, const unsigned long long seed,
     const int N = p.N, R = p.R;
     double now = (double)clock[e];
     uint4 *tr = p.trace + (size_t)e * p.T;
-    for (int k = 0; k < n_req; ++k) {
+    for (int k0 = 0; k0 < n_req; k0 += 32) {
+        const int k = k0 + lane;
         const unsigned long long c = pos0 + (unsigned long long)k;
         const uint4 a = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)ge, (uint32_t)(ge >> 32) * 2u), key);
         const uint4 b = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)ge, (uint32_t)(ge >> 32) * 2u + 1u), key);
-        const float at = (float)(now + (-log(1.0 - u53(a.x, a.y)) / lam));       // qrmsa.pyx:1079-1081
-        now = (double)at;
+        const double x = -log(1.0 - u53(a.x, a.y)) / lam;                        // qrmsa.pyx:1079-1081
         const float ht = (float)(-log(1.0 - u53(a.z, a.w)) / lam_hold);          // qrmsa.pyx:1083-1084
         const int src = bisect_right_dev(src_cum, ((double)b.x * (1.0 / 4294967296.0)) * src_cum[N - 1], N - 1);
         const double *dc = dst_cum + (size_t)src * N;
         const int dst = bisect_right_dev(dc, ((double)b.y * (1.0 / 4294967296.0)) * dc[N - 1], N - 1);
         const int rate = bisect_right_dev(rate_cum, ((double)b.z * (1.0 / 4294967296.0)) * rate_cum[R - 1], R - 1);
-        tr[k] = make_uint4(__float_as_uint(at), __float_as_uint(ht), (uint32_t)src | ((uint32_t)dst << 8) | ((uint32_t)rate << 16), 0u);
+        float at = 0.f;
+        const int m = min(32, n_req - k0);
+        for (int j = 0; j < m; ++j) {   // the clock chain, same on every lane
+            const float aj = (float)(now + __shfl_sync(FULL, x, j));
+            now = (double)aj;
+            if (lane == j) at = aj;
+        }
+        if (k < n_req)
+            tr[k] = make_uint4(__float_as_uint(at), __float_as_uint(ht), (uint32_t)src | ((uint32_t)dst << 8) | ((uint32_t)rate << 16), 0u);
     }
-    clock[e] = (float)now;
+    if (lane == 0) clock[e] = (float)now;
 }
 
 // request records [first, first+count) -> request-major SoA [count][n_envs] (the inverse of k_ingest_trace)
