@@ -18,7 +18,7 @@
 //   pos     uint8/16 [E][CAP] index, in the link's list, of the channel that starts in slot pair s>>1
 //   trace   uint4  [T]        {arrival f32, holding f32, src|dst<<8|rate<<16, action word}
 //                             request table == service table == decision log
-//   perm    uint16 [T]        request ids sorted by (float32(arrival+holding), id): the release schedule
+//   perm    uint64 [T]        float32(arrival+holding) << 32 | request id, ascending: the release schedule
 //                             (stands in for the heapq of qrmsa.pyx:1327-1330, :1113-1122)
 //   estate  int4              {current request, release pointer, accepted, error}
 //   counted uint32            requests already covered by k_count_decisions
@@ -77,7 +77,7 @@ struct KParams {
     uint32_t *bm;
     uint32_t *lists;
     uint4 *trace;
-    uint16_t *perm;
+    unsigned long long *perm;      // [n_envs][T] release schedule: float32 release key << 32 | request id, ascending
     int4 *estate;
     unsigned long long *counters;  // [n_groups][QRMSA_N_COUNTERS]
     double *gsnr_log;              // nullable, [n_envs][T][3] = GSNR, ASE-only, NLI-only in dB (osnr.pyx:138-140)
@@ -392,8 +392,7 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int path = (src * p.N + dst) * dm.K() + pi;
     const int hops = __ldg(p.path_hops + path) & 0x7f;
     const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
-    const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) |
-                            ((uint32_t)t.cls(rate * M + m) << 23);
+    const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12);   // centre and width identify the record
     update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
     int err = 0;
     if (lane < hops) {
@@ -402,7 +401,7 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
         uint32_t *lst = lists + (unsigned)(mylink * CAP);
         const unsigned pidx = (unsigned)(mylink * CAP + (s >> 1));
         const int fpos = p.pos_bytes == 1 ? (int)pos[pidx] : (int)reinterpret_cast<const uint16_t *>(pos)[pidx];
-        if (fpos >= c || lst[fpos] != target) {
+        if (fpos >= c || (lst[fpos] & 0xfffffu) != target) {
             err = 1;
         } else {
             const uint32_t last = lst[c - 1];
@@ -422,14 +421,16 @@ struct Head {
     float rel;  // its release time, float32(arrival + holding)  (qrmsa.pyx:1329)
 };
 
-__device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, const uint16_t *perm, int ptr) {
+__device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, const unsigned long long *perm, int ptr) {
+    // one 8-byte load: the schedule entry carries the release key, so the head's request record is only read
+    // when the service is actually released
     Head h;
     h.id = -1;
     h.rel = 0.f;
     if (ptr < p.n_req) {
-        h.id = perm[ptr];
-        const uint4 r = tr[h.id];
-        h.rel = __fadd_rn(__uint_as_float(r.x), __uint_as_float(r.y));
+        const unsigned long long k = perm[ptr];
+        h.id = (int)(unsigned)k;
+        h.rel = __uint_as_float((unsigned)(k >> 32));
     }
     return h;
 }
@@ -439,7 +440,7 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
 // schedule exactly as they are absent from the reference heap.
 template <class DM>
 __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
-                                                   const uint16_t *perm, uint32_t *bm, uint32_t *lists, uint8_t *pos,
+                                                   const unsigned long long *perm, uint32_t *bm, uint32_t *lists, uint8_t *pos,
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
     cur += 1;
     const float now = __uint_as_float(tr[cur].x);
@@ -495,22 +496,36 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
     for (;;) {
         int env = 0;
         if (lane == 0) env = atomicAdd(p.work, 1);
-        env = __shfl_sync(FULL, env, 0);
+        // broadcast by a REDUX: its result lives in a uniform register, so the compiler knows the env index (and
+        // every per-env base address derived from it) is warp-uniform and keeps that arithmetic on the uniform datapath
+        env = (int)__reduce_add_sync(FULL, (unsigned)env);
         if (env >= p.n_envs) break;
         int4 st = p.estate[env];
         if (st.w != ENV_OK) continue;
-        int cur = st.x, rel_ptr = st.y, accepted = st.z, err = 0;
+        int cur = st.x, rel_ptr = st.y, err = 0;
         uint4 *tr = p.trace + (size_t)env * p.T;
-        const uint16_t *perm = p.perm + (size_t)env * p.T;
+        const unsigned long long *perm = p.perm + (size_t)env * p.T;
         uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
         uint32_t *lists = p.lists + (size_t)env * p.E * dm.CAP();
         uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
-        double *glog = p.gsnr_log ? p.gsnr_log + (size_t)env * p.T * 3 : nullptr;
+        // the per-env base addresses are made opaque so that they stay in registers: left alone, the compiler
+        // re-derives env * stride (two IMADs, an IMAD.WIDE, LEA + LEA.HI.X and the constant loads) at most accesses
+        asm volatile("" : "+l"(tr));
+        asm volatile("" : "+l"(perm));
+        asm volatile("" : "+l"(bm));
+        asm volatile("" : "+l"(lists));
+        asm volatile("" : "+l"(pos));
+        __builtin_assume(__isGlobal(tr));
+        __builtin_assume(__isGlobal(perm));
+        __builtin_assume(__isGlobal(bm));
+        __builtin_assume(__isGlobal(lists));
+        __builtin_assume(__isGlobal(pos));
         Head head = load_head(p, tr, perm, rel_ptr);
         uint32_t cnt_reg = 0;
 
+        const int cur_end = min(cur + n_steps, p.n_req - 1);   // the last request of a trace is never decided
 #pragma unroll 1
-        for (int step = 0; step < n_steps && cur + 1 < p.n_req && !err; ++step) {
+        while (cur < cur_end && !err) {
             const uint4 rq = tr[cur];
             const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
             const int pbase = (src * p.N + dst) * K;
@@ -671,10 +686,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             }
             if (lane == 0) {
                 tr[cur].w = (uint32_t)action | flags;
-                if (glog) {   // 10*log10(1/acc) for the total, ASE-only and NLI-only accumulators (osnr.pyx:133-140)
-                    glog[3 * cur + 0] = found ? -10.0 * log10(acc_ok) : 0.0;
-                    glog[3 * cur + 1] = found ? -10.0 * log10(ase_ok) : 0.0;
-                    glog[3 * cur + 2] = found ? -10.0 * log10(acc_ok - ase_ok) : 0.0;
+                if (p.gsnr_log) {   // 10*log10(1/acc) for the total, ASE-only and NLI-only accumulators (osnr.pyx:133-140)
+                    double *gl = p.gsnr_log + ((size_t)env * p.T + cur) * 3;
+                    gl[0] = found ? -10.0 * log10(acc_ok) : 0.0;
+                    gl[1] = found ? -10.0 * log10(ase_ok) : 0.0;
+                    gl[2] = found ? -10.0 * log10(acc_ok - ase_ok) : 0.0;
                 }
             }
             __syncwarp();
@@ -683,7 +699,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
         }
-        if (lane == 0) p.estate[env] = make_int4(cur, rel_ptr, accepted, err);
+        if (lane == 0) {   // estate.z (the accepted total) belongs to k_count_decisions
+            int *es = reinterpret_cast<int *>(p.estate + env);
+            *reinterpret_cast<int2 *>(es) = make_int2(cur, rel_ptr);
+            es[3] = err;
+        }
         if (cnt_reg) atomicAdd(p.counters + (size_t)(env / p.group_size) * QRMSA_N_COUNTERS + lane,
                                (unsigned long long)cnt_reg);
     }
@@ -718,7 +738,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
         uint32_t cnt_reg = 0;
         if (err == ENV_OK && cur + 1 < p.n_req) {
             uint4 *tr = p.trace + (size_t)env * p.T;
-            const uint16_t *perm = p.perm + (size_t)env * p.T;
+            const unsigned long long *perm = p.perm + (size_t)env * p.T;
             uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
             uint32_t *lists = p.lists + (size_t)env * p.E * p.CAP;
             uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
@@ -1189,7 +1209,7 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
         if (st.w != ENV_OK) continue;   // (uniform over the CTA)
         int cur = st.x, rel_ptr = st.y, err = 0;
         uint4 *tr = p.trace + (size_t)env * p.T;
-        const uint16_t *perm = p.perm + (size_t)env * p.T;
+        const unsigned long long *perm = p.perm + (size_t)env * p.T;
         uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
         uint32_t *lists = p.lists + (size_t)env * p.E * CAP;
         uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
@@ -1522,8 +1542,8 @@ __global__ void __launch_bounds__(1024) k_build_schedule(const KParams p, const 
                 __syncthreads();
             }
         }
-        uint16_t *perm = p.perm + (size_t)env * p.T;
-        for (int i = threadIdx.x; i < n_req; i += blockDim.x) perm[i] = (uint16_t)(keys[i] & 0xffffu);
+        unsigned long long *perm = p.perm + (size_t)env * p.T;
+        for (int i = threadIdx.x; i < n_req; i += blockDim.x) perm[i] = keys[i];
         __syncthreads();
     }
 }
