@@ -23,6 +23,7 @@ struct qrmsa_ctx {
     int sub_grid = 0;
     bool use_warp_kernel = false;
     size_t sub_smem = 0;
+    size_t bm_smem = 0;              // dynamic shared memory of the step kernel with the bitmap rows staged (0 = not used)
     size_t cta_smem = 0;   // k_step_highest_snr (and k_observation): one CTA per env
     int cta_grid = 0, cta_epc = 0, cta_env_smem = 0;
     // on-device request generator
@@ -298,6 +299,16 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    // bitmap rows staged in shared memory (one area per warp after the tables) when they fit
+    ctx->bm_smem = 0;
+    {
+        const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * E * kp.RW * 4;
+        const char *e = getenv("QRMSA_BM_SMEM");
+        if (e && atoi(e) == 1 && need <= (size_t)ctx->smem_optin) {
+            ctx->bm_smem = need;
+            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        }
+    }
     const int sub_smem_max = kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2);
     const bool sub_fits = sub_smem_max <= ctx->smem_optin;   // the experiment kernel keeps a per-env link scratch after the tables
     if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<4, 320, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
@@ -635,7 +646,8 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
     } else if (policy == QRMSA_POLICY_FIRST_FIT) {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
-        if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+        if (c320 && ctx->bm_smem) k_step_policy<320, 6, 5, POLICY_FIRST_FIT, true><<<g, th, ctx->bm_smem, st>>>(kp, n_steps);
+        else if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else if (c640) k_step_policy<640, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_LB_FIRST_FIT) {

@@ -393,6 +393,9 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int hops = __ldg(p.path_hops + path) & 0x7f;
     const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12);   // centre and width identify the record
+#ifdef QRMSA_PF_REL
+    if (lane < hops) prefetch_l1(lists + (unsigned)(mylink * CAP));   // most lists fit the first 128-byte line
+#endif
     update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
     int err = 0;
     if (lane < hops) {
@@ -431,6 +434,9 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
         const unsigned long long k = perm[ptr];
         h.id = (int)(unsigned)k;
         h.rel = __uint_as_float((unsigned)(k >> 32));
+#ifdef QRMSA_PF_HEAD
+        prefetch_l1(tr + h.id);   // the record is read when the service is released, usually a few requests later
+#endif
     }
     return h;
 }
@@ -444,6 +450,9 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
     cur += 1;
     const float now = __uint_as_float(tr[cur].x);
+#ifdef QRMSA_PF_NEXT
+    if ((cur & 7) == 0) prefetch_l1(tr + cur + 16);   // request records are read in order: pull the line two ahead
+#endif
     int err = 0;
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];
@@ -479,7 +488,7 @@ __device__ __forceinline__ bool qot_ok(const Tab &t, int m, double acc, uint32_t
 // --------------------------------------------------------------------------------------------------------
 enum { POLICY_FIRST_FIT = 0, POLICY_LOAD_BALANCING = 1, POLICY_LB_FIRST_FIT = 3 };   // ids of include/qrmsa_b200.h
 
-template <int S_, int M_, int K_, int POLICY>
+template <int S_, int M_, int K_, int POLICY, bool BMS = false>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p, const int n_steps) {
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
@@ -506,18 +515,28 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         uint4 *tr = p.trace + (size_t)env * p.T;
         const unsigned long long *perm = p.perm + (size_t)env * p.T;
         uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
+        uint32_t *const bm_global = bm;
+        if (BMS) {
+            // BMS: the env's link rows (bitmaps + channel counts) live in shared memory for the whole launch -- every
+            // row read, commit and release is an LDS/STS instead of a trip to L1/L2; 16-byte copies in and out
+            bm = reinterpret_cast<uint32_t *>(qsmem + p.blob_bytes) + (unsigned)((threadIdx.x >> 5) * (int)p.bm_stride);
+            const uint4 *src = reinterpret_cast<const uint4 *>(bm_global);
+            uint4 *dst = reinterpret_cast<uint4 *>(bm);
+            for (int i = lane; i < (int)(p.bm_stride >> 2); i += 32) dst[i] = src[i];
+            __syncwarp();
+        }
         uint32_t *lists = p.lists + (size_t)env * p.E * dm.CAP();
         uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
         // the per-env base addresses are made opaque so that they stay in registers: left alone, the compiler
         // re-derives env * stride (two IMADs, an IMAD.WIDE, LEA + LEA.HI.X and the constant loads) at most accesses
         asm volatile("" : "+l"(tr));
         asm volatile("" : "+l"(perm));
-        asm volatile("" : "+l"(bm));
+        if (!BMS) asm volatile("" : "+l"(bm));
         asm volatile("" : "+l"(lists));
         asm volatile("" : "+l"(pos));
         __builtin_assume(__isGlobal(tr));
         __builtin_assume(__isGlobal(perm));
-        __builtin_assume(__isGlobal(bm));
+        if (!BMS) __builtin_assume(__isGlobal(bm));
         __builtin_assume(__isGlobal(lists));
         __builtin_assume(__isGlobal(pos));
         Head head = load_head(p, tr, perm, rel_ptr);
@@ -698,6 +717,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
+        }
+        if (BMS) {
+            __syncwarp();
+            const uint4 *src = reinterpret_cast<const uint4 *>(bm);
+            uint4 *dst = reinterpret_cast<uint4 *>(bm_global);
+            for (int i = lane; i < (int)(p.bm_stride >> 2); i += 32) dst[i] = src[i];
         }
         if (lane == 0) {   // estate.z (the accepted total) belongs to k_count_decisions
             int *es = reinterpret_cast<int *>(p.estate + env);
