@@ -299,14 +299,22 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    // bitmap rows staged in shared memory (one area per warp after the tables) when they fit
+    // Bitmap rows staged in shared memory (one area per warp after the tables): every row read, commit and release
+    // becomes an LDS/STS.  Used when tables + rows leave at least 64 KB of the SM's 256 KB to L1 (the lists, the
+    // position table and the trace still go through it): nobel-eu/320 = 96 + 84 KB, measured 7.50e8 -> 7.85e8.
+    // QRMSA_BM_SMEM=0 switches it off (experiments).
     ctx->bm_smem = 0;
     {
         const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * E * kp.RW * 4;
         const char *e = getenv("QRMSA_BM_SMEM");
-        if (e && atoi(e) == 1 && need <= (size_t)ctx->smem_optin) {
+        if (!(e && atoi(e) == 0) && ctas_per_sm == 1 && need <= (size_t)ctx->smem_optin && need <= 192 * 1024) {
             ctx->bm_smem = need;
             CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         }
     }
     const int sub_smem_max = kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2);
@@ -632,6 +640,7 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
     const KParams &kp = ctx->kp;
     cudaStream_t st = (cudaStream_t)stream;
     const int g = ctx->grid, th = ctx->threads, sm = kp.blob_bytes;
+    const size_t bsm = ctx->bm_smem;   // != 0: the kernel variant with the bitmap rows staged in shared memory
     // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
     const bool c320 = kp.S == 320 && kp.M == 6 && kp.K == 5, c640 = kp.S == 640 && kp.M == 6 && kp.K == 5;
     if (policy == QRMSA_POLICY_FIRST_FIT && !ctx->use_warp_kernel) {
@@ -646,20 +655,25 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
     } else if (policy == QRMSA_POLICY_FIRST_FIT) {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
-        if (c320 && ctx->bm_smem) k_step_policy<320, 6, 5, POLICY_FIRST_FIT, true><<<g, th, ctx->bm_smem, st>>>(kp, n_steps);
+        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_FIRST_FIT, true><<<g, th, bsm, st>>>(kp, n_steps);
         else if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
         else if (c640) k_step_policy<640, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+        else if (bsm) k_step_policy<0, 0, 0, POLICY_FIRST_FIT, true><<<g, th, bsm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_LB_FIRST_FIT) {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
-        if (c320) k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT, true><<<g, th, bsm, st>>>(kp, n_steps);
+        else if (c320) k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+        else if (bsm) k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, true><<<g, th, bsm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_HIGHEST_SNR) {
         if (!ctx->cta_grid) { ctx->err = "highest-SNR policy needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
         k_step_highest_snr<<<ctx->cta_grid, ctx->cta_epc * OBS_ENV_THREADS, ctx->cta_smem, st>>>(kp, n_steps, ctx->cta_epc, ctx->cta_env_smem);
     } else {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
-        if (c320) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
+        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, true><<<g, th, bsm, st>>>(kp, n_steps);
+        else if (c320) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
+        else if (bsm) k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, true><<<g, th, bsm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
     }
     if (policy != QRMSA_POLICY_FIRST_FIT || ctx->use_warp_kernel) {

@@ -4,7 +4,8 @@
 // bitmap, so the AND along a path, the contiguous-block search and the commit/release masks are
 // single warp-wide instructions; the GN-model sum deals the path's channel records to the lanes in
 // groups of four (one 16-byte load each).  A warp keeps its env for all n_steps of a launch, so the
-// env's state is pulled from HBM once per launch and then lives in L1/L2.  No tensor cores: no stage
+// env's state is pulled from HBM once per launch and then lives in L1/L2 -- the link rows (bitmaps + channel counts)
+// in shared memory when tables + 32 envs' rows leave L1 at least 64 KB (BMS variant).  No tensor cores: no stage
 // is a dense contraction.
 //
 // HBM layout per env (all per-env blocks are contiguous, 64-byte aligned):
@@ -15,7 +16,8 @@
 //                             topology[u][v]["running_services"], qrmsa.pyx:1305-1306)
 //                             c2 = 2*initial_slot + n  (centre frequency in half-slots); entries at or past the
 //                             count hold the filler record (class NC: table rows of zeros)
-//   pos     uint8/16 [E][CAP] index, in the link's list, of the channel that starts in slot pair s>>1
+//   pos     uint8/16 [CAP][E] index, in the link's list, of the channel that starts in slot pair s>>1 (pair-major:
+//                             the entries of one service on the links of its path share a line)
 //   trace   uint4  [T]        {arrival f32, holding f32, src|dst<<8|rate<<16, action word}
 //                             request table == service table == decision log
 //   perm    uint64 [T]        float32(arrival+holding) << 32 | request id, ascending: the release schedule
@@ -192,8 +194,17 @@ __device__ __forceinline__ const uint32_t *cnt_word(const uint32_t *bm, int l, i
 
 // pos[link][s >> 1] = index of the channel record in the link's list.  A service and its guard slot cover at least
 // one aligned slot pair exclusively, so the pair index identifies the service on that link.
+// Laid out [pair][link]: the entries of one service on the links of its path share a 128-byte line (E <= 128), so a
+// commit or a release touches one line of the table instead of one per hop.
+__device__ __forceinline__ unsigned pos_index(const KParams &p, int l, int pair) {
+#ifdef QRMSA_POS_LINK_MAJOR
+    return (unsigned)(l * p.CAP + pair);
+#else
+    return (unsigned)(pair * p.E + l);
+#endif
+}
 __device__ __forceinline__ void pos_store(const KParams &p, uint8_t *pos, int l, int pair, int v) {
-    const unsigned i = (unsigned)(l * p.CAP + pair);
+    const unsigned i = pos_index(p, l, pair);
     if (p.pos_bytes == 1) pos[i] = (uint8_t)v;
     else reinterpret_cast<uint16_t *>(pos)[i] = (uint16_t)v;
 }
@@ -393,16 +404,13 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int hops = __ldg(p.path_hops + path) & 0x7f;
     const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12);   // centre and width identify the record
-#ifdef QRMSA_PF_REL
-    if (lane < hops) prefetch_l1(lists + (unsigned)(mylink * CAP));   // most lists fit the first 128-byte line
-#endif
     update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
     int err = 0;
     if (lane < hops) {
         uint32_t *cw = cnt_word(bm, mylink, dm.RW());
         const int c = (int)*cw;
         uint32_t *lst = lists + (unsigned)(mylink * CAP);
-        const unsigned pidx = (unsigned)(mylink * CAP + (s >> 1));
+        const unsigned pidx = pos_index(p, mylink, s >> 1);
         const int fpos = p.pos_bytes == 1 ? (int)pos[pidx] : (int)reinterpret_cast<const uint16_t *>(pos)[pidx];
         if (fpos >= c || (lst[fpos] & 0xfffffu) != target) {
             err = 1;
@@ -434,9 +442,7 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
         const unsigned long long k = perm[ptr];
         h.id = (int)(unsigned)k;
         h.rel = __uint_as_float((unsigned)(k >> 32));
-#ifdef QRMSA_PF_HEAD
         prefetch_l1(tr + h.id);   // the record is read when the service is released, usually a few requests later
-#endif
     }
     return h;
 }
@@ -450,9 +456,6 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
     cur += 1;
     const float now = __uint_as_float(tr[cur].x);
-#ifdef QRMSA_PF_NEXT
-    if ((cur & 7) == 0) prefetch_l1(tr + cur + 16);   // request records are read in order: pull the line two ahead
-#endif
     int err = 0;
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(QRMSA_SUB_THREADS, 1) k_step_sub(const KParams
                             if (on && sub == 0) {
                                 // the record sits where the position table says (kept by every commit and every move)
                                 uint32_t *lst = LISTS + (unsigned)(l * CAP);
-                                const unsigned pidx = (unsigned)(l * CAP + (rs >> 1));
+                                const unsigned pidx = pos_index(p, l, rs >> 1);
                                 const int fpos = LPE == 4 ? (int)POS[pidx] : (int)reinterpret_cast<const uint16_t *>(POS)[pidx];
                                 if (fpos >= c || lst[fpos] != target) {
                                     bad = 1;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(QRMSA_SUB_THREADS, 1) k_step_sub(const KParams
                                     const uint32_t last = lst[c - 1];
                                     lst[fpos] = last;
                                     lst[c - 1] = p.sentinel;
-                                    const unsigned midx = (unsigned)(l * CAP + rec_pair(last));
+                                    const unsigned midx = pos_index(p, l, rec_pair(last));
                                     if (LPE == 4) POS[midx] = (uint8_t)fpos;
                                     else reinterpret_cast<uint16_t *>(POS)[midx] = (uint16_t)fpos;
                                 }
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(QRMSA_SUB_THREADS, 1) k_step_sub(const KParams
                                     ovf = 1;
                                 } else {
                                     LISTS[(unsigned)(l * CAP + c)] = rec;
-                                    const unsigned pidx = (unsigned)(l * CAP + (cs >> 1));
+                                    const unsigned pidx = pos_index(p, l, cs >> 1);
                                     if (LPE == 4) POS[pidx] = (uint8_t)c;
                                     else reinterpret_cast<uint16_t *>(POS)[pidx] = (uint16_t)c;
                                     v.w = (uint32_t)(c + 1);
