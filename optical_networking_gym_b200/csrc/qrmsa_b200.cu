@@ -247,6 +247,26 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         hops_dev[pi_] = (uint8_t)(hops | (ok ? 0x80 : 0));
     }
 
+    // compact path table for the step kernel's shared memory: u16 offset[n_paths] | u8 hops+flag[n_paths] | u8 links[...]
+    std::vector<unsigned char> ptab;
+    bool ptab_ok = true;
+    {
+        size_t total = 0;
+        for (size_t pi_ = 0; pi_ < n_paths; pi_++) total += t->path_hops[pi_];
+        kp.pt_hops_off = (int)round_up(2 * n_paths, 4);
+        kp.pt_links_off = kp.pt_hops_off + (int)round_up(n_paths, 4);
+        ptab.assign(round_up((size_t)kp.pt_links_off + total + 32, 16), 0);   // + 32: a full warp may read past the last path
+        if (total > 0xffff) ptab_ok = false;
+        size_t off = 0;
+        for (size_t pi_ = 0; pi_ < n_paths && ptab_ok; pi_++) {
+            const uint16_t o = (uint16_t)off;
+            memcpy(&ptab[2 * pi_], &o, 2);
+            ptab[kp.pt_hops_off + pi_] = hops_dev[pi_];
+            for (int h = 0; h < t->path_hops[pi_]; h++) ptab[kp.pt_links_off + off++] = t->path_links[pi_ * t->max_hops + h];
+        }
+        kp.ptab_bytes = (int)ptab.size();
+    }
+
     // ---- shared-memory image, fixed layout (qrmsa_kernels.cuh namespace lay)
     if (R * M > lay::MAX_RM || E > lay::MAX_E || NC > lay::MAX_NC || M > lay::MAX_M || R > lay::MAX_R) {
         ctx->err = "table dimension exceeds the shared-memory layout capacity";
@@ -300,14 +320,18 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     // Bitmap rows staged in shared memory (one area per warp after the tables): every row read, commit and release
-    // becomes an LDS/STS.  Used when tables + rows leave at least 64 KB of the SM's 256 KB to L1 (the lists, the
-    // position table and the trace still go through it): nobel-eu/320 = 96 + 84 KB, measured 7.50e8 -> 7.85e8.
+    // becomes an LDS/STS; a compact copy of the path table (hop counts + link ids) follows them.  Used whenever
+    // tables + rows + paths fit the 227 KB a CTA may have: nobel-eu/320 = 96 + 84 + 31 KB, which leaves L1 only
+    // 28 KB for the lists, the position table and the trace -- measured 7.50e8 (all through L1, 156 KB) -> 7.85e8
+    // (rows in shared memory, 60 KB of L1) -> 8.03e8 (rows + paths).  QRMSA_SMEM_LIMIT_KB caps it (experiments).
     // QRMSA_BM_SMEM=0 switches it off (experiments).
     ctx->bm_smem = 0;
     {
-        const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * E * kp.RW * 4;
+        const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * E * kp.RW * 4 + ptab.size();
         const char *e = getenv("QRMSA_BM_SMEM");
-        if (!(e && atoi(e) == 0) && ctas_per_sm == 1 && need <= (size_t)ctx->smem_optin && need <= 192 * 1024) {
+        const char *lim = getenv("QRMSA_SMEM_LIMIT_KB");
+        const size_t limit = lim && atoi(lim) > 0 ? (size_t)atoi(lim) * 1024 : (size_t)ctx->smem_optin;
+        if (!(e && atoi(e) == 0) && ptab_ok && ctas_per_sm == 1 && need <= (size_t)ctx->smem_optin && need <= limit) {
             ctx->bm_smem = need;
             CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
@@ -385,6 +409,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
 
     // ---- uploads and state
     if ((rc = dev_upload(ctx, &kp.path_hops, (const uint8_t *)hops_dev.data(), n_paths))) return rc;
+    if ((rc = dev_upload(ctx, &kp.ptab, (const unsigned char *)ptab.data(), ptab.size()))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_links, t->path_links, n_paths * t->max_hops))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_gn, pgn.data(), n_paths))) return rc;
     {

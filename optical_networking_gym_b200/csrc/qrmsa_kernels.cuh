@@ -66,6 +66,8 @@ struct KParams {
     const uint8_t *path_links;  // [N*N*K*Hmax]
     const double2 *path_gn;     // [N*N*K] {PA, PB}
     const unsigned char *blob;  // shared-memory image, 16-byte multiple
+    const unsigned char *ptab;  // compact path table for shared memory: u16 offset[n_paths] | u8 hops[n_paths] | u8 links[sum hops]
+    int ptab_bytes, pt_hops_off, pt_links_off;   // (16-byte multiple; byte offsets of the second and third part)
     const uint4 *prec;          // [N*N*K][4] path records (64 B): link ids u8[32] | {PA, PB} | hops (bit 7: prunable)
     int *work;                  // env-group ticket counter of k_step_sub (zeroed before each launch)
     uint8_t *pos;               // [n_envs][E][CAP] (u8 if CAP <= 256, else u16): list position of the channel that starts in
@@ -251,6 +253,32 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Path lookups (hop count + flag, link ids).  PathTab<false>: the global tables, read through L1.  PathTab<true>: the
+// compact copy the step kernel keeps in shared memory (offset u16 | hops u8 | link ids u8, variable length): the two
+// dependent table loads of every path visit and of every release become LDS, and ~19 KB of hot lines leave L1.
+template <bool SMEM>
+struct PathTab {
+    uint32_t base;   // shared-window address of the compact table (SMEM only)
+    __device__ __forceinline__ int hops_flags(const KParams &p, int path) const {
+        if (SMEM) {
+            uint32_t v;
+            asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)(p.pt_hops_off + path)));
+            return (int)v;
+        }
+        return __ldg(p.path_hops + path);
+    }
+    // link id of hop `lane` (0 for lanes past the path)
+    __device__ __forceinline__ int link(const KParams &p, int path, int lane, int hops) const {
+        if (SMEM) {
+            uint32_t off, v = 0;
+            asm("ld.shared.u16 %0, [%1];" : "=r"(off) : "r"(base + 2u * (uint32_t)path));
+            if (lane < hops) asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p.pt_links_off + off + (uint32_t)lane));
+            return (int)v;
+        }
+        return lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+    }
+};
+
 // qrmsa.pyx:1482-1512: AND of the path's link rows; plus one virtual free slot at index S, which turns the
 // guard-band rule of qrmsa.pyx:529-540 ("n slots if the run touches the spectrum end, else n+1") into
 // "n+1 consecutive free slots".  32/W link rows are fetched per pass (3 at W=10), then folded with shuffles.
@@ -295,8 +323,14 @@ __device__ __forceinline__ GnBase gn_base(const KParams &p, const Tab &t, int pa
 // one channel record against a candidate centred at c2 half-slots (core/osnr.pyx:64-94, table form)
 __device__ __forceinline__ void gn_term(const Tab &t, const int D, const uint32_t rec, const int c2, double &s1, double &s2) {
     const int d = abs((int)(rec & 0xfffu) - c2);
-    s1 += t.G(D, (rec >> 23) * D + d);
-    s2 = fma(t.PHIN(rec >> 20), t.INV(d), s2);
+    // INV[d] and G[class][d] from one scaled index: a_inv = base + 8 d, a_g = a_inv + (class + 1) * 8 D
+    const uint32_t a_inv = t.sb + 8u * (uint32_t)d;
+    const uint32_t a_g = a_inv + ((rec >> 23) + 1u) * (8u * (uint32_t)D);
+    double g, inv;
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(a_g), "n"(lay::INV));
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(a_inv), "n"(lay::INV));
+    s1 += g;
+    s2 = fma(t.PHIN(rec >> 20), inv, s2);
 }
 
 // sum over the path's links and every channel on them (same value on every lane).
@@ -389,9 +423,10 @@ __device__ __forceinline__ int commit(const DM &dm, const KParams &p, uint32_t *
 
 // qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record.
 // Lane i handles hop i: the record's place in the link's list comes from the position table, so there is no search.
-template <class DM>
+template <class DM, class PT = PathTab<false>>
 __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, const Tab &t, uint32_t *bm,
-                                               uint32_t *lists, uint8_t *pos, const uint4 rq, int lane) {
+                                               uint32_t *lists, uint8_t *pos, const uint4 rq, int lane,
+                                               const PT pt = PT()) {
     const int S = dm.S(), M = dm.M(), CAP = dm.CAP();
     const uint32_t a = rq.w & QRMSA_ACTION_MASK;
     const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
@@ -401,8 +436,8 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int m = (M - 1) - rel;
     const int n = t.need(rate * M + m);
     const int path = (src * p.N + dst) * dm.K() + pi;
-    const int hops = __ldg(p.path_hops + path) & 0x7f;
-    const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+    const int hops = pt.hops_flags(p, path) & 0x7f;
+    const int mylink = pt.link(p, path, lane, hops);
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12);   // centre and width identify the record
     update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
     int err = 0;
@@ -450,17 +485,18 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
 // qrmsa.pyx:1067-1122 after a request has been decided: take the next request (clock := its arrival) and
 // release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
 // schedule exactly as they are absent from the reference heap.
-template <class DM>
+template <class DM, class PT = PathTab<false>>
 __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
                                                    const unsigned long long *perm, uint32_t *bm, uint32_t *lists, uint8_t *pos,
-                                                   int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel) {
+                                                   int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel,
+                                                   const PT pt = PT()) {
     cur += 1;
     const float now = __uint_as_float(tr[cur].x);
     int err = 0;
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];
         if (rq.w & QRMSA_FLAG_ACCEPTED) {
-            err |= release_service(dm, p, t, bm, lists, pos, rq, lane);
+            err |= release_service(dm, p, t, bm, lists, pos, rq, lane, pt);
             n_rel += 1;
         }
         rel_ptr += 1;
@@ -502,6 +538,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
 
     const int lane = threadIdx.x & 31;
     const int reject = K * M * S;
+    PathTab<BMS> pt;
+    pt.base = 0;
+    if (BMS) {
+        // compact path table after the per-warp row areas
+        const unsigned off = (unsigned)p.blob_bytes + (unsigned)((blockDim.x >> 5) * (int)p.bm_stride * 4);
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.ptab);
+        uint4 *dst = reinterpret_cast<uint4 *>(qsmem + off);
+        for (int i = threadIdx.x; i < (p.ptab_bytes >> 4); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        pt.base = t.sb + off;
+    }
 
     // envs are handed out by a ticket counter (zeroed before the launch): a warp that finishes early takes the next
     // env instead of idling behind a fixed share
@@ -569,9 +616,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
 #pragma unroll 1
                 for (int pj = 0; pj < K; ++pj) {
                     const int path = pbase + pj;
-                    const int hops = __ldg(p.path_hops + path) & 0x7f;
+                    const int hops = pt.hops_flags(p, path) & 0x7f;
                     if (hops == 0) continue;
-                    const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+                    const int mylink = pt.link(p, path, lane, hops);
                     const uint32_t av = path_available(dm, bm, hops, mylink, lane);
                     int free_slots = __popc(lane == (S >> 5) ? av & ~(1u << (S & 31)) : av);
 #pragma unroll
@@ -591,11 +638,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 // path visited k-th: its own index, or the path of rank k
                 const int pi = POLICY == POLICY_LB_FIRST_FIT ? __ffs(__ballot_sync(FULL, lane < K && my_rank == kk)) - 1 : kk;
                 const int path = pbase + pi;
-                const int hp = __ldg(p.path_hops + path);  // bit 7: every neighbour term of this path is >= 0
+                const int hp = pt.hops_flags(p, path);  // bit 7: every neighbour term of this path is >= 0
                 const int hops = hp & 0x7f;
                 if (hops == 0) continue;
                 const bool prunable = (hp & 0x80) != 0;
-                const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+                const int mylink = pt.link(p, path, lane, hops);
                 const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, dm.RW()) : 0;
                 if (lane < hops) prefetch_l1(lists + (unsigned)(mylink * dm.CAP()));  // needed by the GN sum below
                 const uint32_t av = path_available(dm, bm, hops, mylink, lane);
@@ -686,8 +733,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             }
             if (POLICY == POLICY_LOAD_BALANCING && best_pi >= 0) {
                 const int path = pbase + best_pi;
-                const int hops = __ldg(p.path_hops + path) & 0x7f;
-                const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+                const int hops = pt.hops_flags(p, path) & 0x7f;
+                const int mylink = pt.link(p, path, lane, hops);
                 const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, dm.RW()) : 0;
                 const int nd = __shfl_sync(FULL, mynd, best_m);
                 const int n = nd & 0xff, ncls = nd >> 8;
@@ -717,7 +764,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             }
             __syncwarp();
             uint32_t n_rel = 0;
-            if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel))
+            if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, pt))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
         }
