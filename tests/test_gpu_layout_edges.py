@@ -92,3 +92,33 @@ def test_loud_failures():
     with pytest.raises(QRMSAError):
         eng.step_heuristic(7, 1)                           # unknown policy
     eng.close()
+
+
+@pytest.mark.parametrize("topo,policy", [("nobel-eu", "first_fit"), ("nsfnet", "load_balancing"), ("nobel-eu", "load_balancing_first_fit")])
+def test_shared_memory_staging_matches_global_state(topo, policy, monkeypatch):
+    """The step kernel keeps the link rows and a compact path table in shared memory when they fit (BMS variant,
+    qrmsa_create); QRMSA_BM_SMEM=0 selects the variant that reads everything through L1.  Same action words, bitmaps,
+    channel lists, env state and counters, across launch boundaries (rows are written back after every launch)."""
+    from optical_networking_gym_b200 import _lib
+    from optical_networking_gym_b200.engine import Engine
+    from optical_networking_gym_b200.tracegen import TraceGenerator
+
+    tb = load_tables(topo, 320)
+    n_envs, n = 70, 400
+    tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, 300.0 if topo == "nobel-eu" else 250.0, base_seed=99).next(n + 1)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("QRMSA_BM_SMEM", mode)   # read by qrmsa_create
+        eng = Engine(tb, n_envs, n + 1)
+        eng.reset(); eng.load_trace_host(*tr)
+        for c in (1, 7, 200, n - 208):
+            eng.step_heuristic(_lib.POLICIES[policy], c)
+        lists = [sorted(map(tuple, eng.export_link_list(e, l))) for e in (0, n_envs - 1) for l in range(tb.n_links)]
+        out[mode] = (eng.actions_host(0, n).copy(), eng.export_bitmaps(0, n_envs).copy(), eng.env_state().copy(),
+                     eng.counters().copy(), lists)
+        c = eng.counters_dict()
+        assert c["decided"] == n_envs * n and c["errors"] == 0
+        eng.close()
+    for i, what in enumerate(("action words", "bitmaps", "env state", "counters")):
+        assert np.array_equal(out["1"][i], out["0"][i]), what + " differ"
+    assert out["1"][4] == out["0"][4], "channel lists differ"
