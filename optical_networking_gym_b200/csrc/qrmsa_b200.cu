@@ -327,7 +327,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     // QRMSA_BM_SMEM=0 switches it off (experiments).
     ctx->bm_smem = 0;
     {
-        const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * E * kp.RW * 4 + ptab.size();
+        const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * (E * kp.RW * 4 + Streams<true>::BYTES) + ptab.size();
         const char *e = getenv("QRMSA_BM_SMEM");
         const char *lim = getenv("QRMSA_SMEM_LIMIT_KB");
         const size_t limit = lim && atoi(lim) > 0 ? (size_t)atoi(lim) * 1024 : (size_t)ctx->smem_optin;

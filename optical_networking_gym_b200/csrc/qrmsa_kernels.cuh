@@ -462,19 +462,80 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     return err;
 }
 
+// The request records and the schedule entries of an env are read in order.  Streams<false>: straight from global
+// memory.  Streams<true> (BMS step kernel): the current and the next 128-byte chunk of both streams sit in a per-warp
+// area of shared memory -- 16 records, then 32 schedule entries -- filled one chunk ahead by cp.async, so that the
+// per-request reads are LDS and the fill's latency is eight requests (sixteen releases) away from its first use.
+template <bool RING>
+struct Streams {
+    uint32_t base;   // shared-window address of this warp's 512-byte area (RING only)
+    static constexpr int BYTES = 512;
+    __device__ __forceinline__ void fill_tr(const uint4 *tr, int chunk, int lane, int T) const {
+        if (RING) {
+            if (lane < 8) {
+                const int i = min(chunk * 8 + lane, T - 1);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)(((chunk & 1) << 7) + (lane << 4))),
+                             "l"(tr + i) : "memory");
+            }
+        }
+    }
+    __device__ __forceinline__ void fill_pm(const unsigned long long *perm, int chunk, int lane, int T) const {
+        if (RING) {
+            if (lane < 16) {
+                const int i = min(chunk * 16 + lane, T - 1);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(base + 256u + (uint32_t)(((chunk & 1) << 7) + (lane << 3))),
+                             "l"(perm + i) : "memory");
+            }
+        }
+    }
+    __device__ __forceinline__ void wait() const {
+        if (RING) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ uint4 rec(const uint4 *tr, int i) const {
+        if (RING) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(base + (uint32_t)((i & 15) << 4)) : "memory");
+            return v;
+        }
+        return tr[i];
+    }
+    __device__ __forceinline__ uint32_t arrival_bits(const uint4 *tr, int i) const {
+        if (RING) {
+            uint32_t v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)((i & 15) << 4)) : "memory");
+            return v;
+        }
+        return tr[i].x;
+    }
+    __device__ __forceinline__ unsigned long long entry(const unsigned long long *perm, int i) const {
+        if (RING) {
+            unsigned long long v;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(base + 256u + (uint32_t)((i & 31) << 3)) : "memory");
+            return v;
+        }
+        return perm[i];
+    }
+};
+
 struct Head {
     int id;     // request id at the head of the release schedule, -1 = exhausted
     float rel;  // its release time, float32(arrival + holding)  (qrmsa.pyx:1329)
 };
 
-__device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, const unsigned long long *perm, int ptr) {
+template <class ST = Streams<false>>
+__device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, const unsigned long long *perm, int ptr,
+                                          const ST sm = ST()) {
     // one 8-byte load: the schedule entry carries the release key, so the head's request record is only read
     // when the service is actually released
     Head h;
     h.id = -1;
     h.rel = 0.f;
     if (ptr < p.n_req) {
-        const unsigned long long k = perm[ptr];
+        const unsigned long long k = sm.entry(perm, ptr);
         h.id = (int)(unsigned)k;
         h.rel = __uint_as_float((unsigned)(k >> 32));
         prefetch_l1(tr + h.id);   // the record is read when the service is released, usually a few requests later
@@ -485,13 +546,17 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
 // qrmsa.pyx:1067-1122 after a request has been decided: take the next request (clock := its arrival) and
 // release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
 // schedule exactly as they are absent from the reference heap.
-template <class DM, class PT = PathTab<false>>
+template <class DM, class PT = PathTab<false>, class ST = Streams<false>>
 __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
                                                    const unsigned long long *perm, uint32_t *bm, uint32_t *lists, uint8_t *pos,
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel,
-                                                   const PT pt = PT()) {
+                                                   const PT pt = PT(), const ST sm = ST()) {
     cur += 1;
-    const float now = __uint_as_float(tr[cur].x);
+    if ((cur & 7) == 0) {   // (no-ops without the ring) the chunk entered was requested eight requests ago
+        sm.wait();
+        sm.fill_tr(tr, (cur >> 3) + 1, lane, p.T);
+    }
+    const float now = __uint_as_float(sm.arrival_bits(tr, cur));
     int err = 0;
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];
@@ -500,7 +565,11 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
             n_rel += 1;
         }
         rel_ptr += 1;
-        head = load_head(p, tr, perm, rel_ptr);
+        if ((rel_ptr & 15) == 0) {
+            sm.wait();
+            sm.fill_pm(perm, (rel_ptr >> 4) + 1, lane, p.T);
+        }
+        head = load_head(p, tr, perm, rel_ptr, sm);
     }
     return err;
 }
@@ -549,6 +618,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         __syncthreads();
         pt.base = t.sb + off;
     }
+    Streams<BMS> sm;   // request / schedule chunks of this warp's env, after the path table
+    sm.base = BMS ? pt.base + (uint32_t)p.ptab_bytes + (uint32_t)((threadIdx.x >> 5) * Streams<BMS>::BYTES) : 0u;
 
     // envs are handed out by a ticket counter (zeroed before the launch): a warp that finishes early takes the next
     // env instead of idling behind a fixed share
@@ -589,13 +660,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         if (!BMS) __builtin_assume(__isGlobal(bm));
         __builtin_assume(__isGlobal(lists));
         __builtin_assume(__isGlobal(pos));
-        Head head = load_head(p, tr, perm, rel_ptr);
+        sm.fill_tr(tr, cur >> 3, lane, p.T);
+        sm.fill_tr(tr, (cur >> 3) + 1, lane, p.T);
+        sm.fill_pm(perm, rel_ptr >> 4, lane, p.T);
+        sm.fill_pm(perm, (rel_ptr >> 4) + 1, lane, p.T);
+        sm.wait();
+        Head head = load_head(p, tr, perm, rel_ptr, sm);
         uint32_t cnt_reg = 0;
 
         const int cur_end = min(cur + n_steps, p.n_req - 1);   // the last request of a trace is never decided
 #pragma unroll 1
         while (cur < cur_end && !err) {
-            const uint4 rq = tr[cur];
+            const uint4 rq = sm.rec(tr, cur);
             const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
             const int pbase = (src * p.N + dst) * K;
             // lane m holds (slots needed, slot class) of modulation m for this request's bit rate
@@ -764,7 +840,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             }
             __syncwarp();
             uint32_t n_rel = 0;
-            if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, pt))
+            if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, pt, sm))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
         }
