@@ -310,14 +310,16 @@ struct GnBase {
     __device__ __forceinline__ double with(double x) const { return ase + cn * (selfpb + x); }
 };
 
-__device__ __forceinline__ GnBase gn_base(const KParams &p, const Tab &t, int path, int s, int n, int ncls) {
-    const double2 pg = __ldg(p.path_gn + path);
+__device__ __forceinline__ GnBase gn_base(const KParams &p, const Tab &t, const double2 pg, int s, int n, int ncls) {
     const double fc = p.f0 + (p.sb * (double)s) + (p.sb * ((double)n / 2.0));  // heuristics.py:948-951
     GnBase b;
     b.ase = t.ASEC(ncls) * fc * pg.x;
     b.cn = t.CN(ncls);
     b.selfpb = t.SELF(ncls) * pg.y;
     return b;
+}
+__device__ __forceinline__ GnBase gn_base(const KParams &p, const Tab &t, int path, int s, int n, int ncls) {
+    return gn_base(p, t, __ldg(p.path_gn + path), s, n, ncls);
 }
 
 // one channel record against a candidate centred at c2 half-slots (core/osnr.pyx:64-94, table form)
@@ -438,19 +440,32 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int path = (src * p.N + dst) * dm.K() + pi;
     const int hops = pt.hops_flags(p, path) & 0x7f;
     const int mylink = pt.link(p, path, lane, hops);
+#ifdef QRMSA_VALIDATE_RELEASE
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12);   // centre and width identify the record
-    update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
-    int err = 0;
+#endif
+    // The position entry and the list's last record are fetched together (the count is at hand), the rows are updated
+    // while the two loads are in flight, and the swap-remove needs nothing else: the chain of a release is
+    // request record -> {position, last record} -> stores.  QRMSA_VALIDATE_RELEASE (debug builds) also reads the record
+    // the position names and compares its centre and width before removing it -- one more dependent load.
+    int err = 0, c = 0, fpos = 0;
+    uint32_t last = 0u;
+    uint32_t *lst = lists + (unsigned)(mylink * CAP);
+    uint32_t *cw = cnt_word(bm, mylink, dm.RW());
     if (lane < hops) {
-        uint32_t *cw = cnt_word(bm, mylink, dm.RW());
-        const int c = (int)*cw;
-        uint32_t *lst = lists + (unsigned)(mylink * CAP);
+        c = (int)*cw;
         const unsigned pidx = pos_index(p, mylink, s >> 1);
-        const int fpos = p.pos_bytes == 1 ? (int)pos[pidx] : (int)reinterpret_cast<const uint16_t *>(pos)[pidx];
-        if (fpos >= c || (lst[fpos] & 0xfffffu) != target) {
+        fpos = p.pos_bytes == 1 ? (int)pos[pidx] : (int)reinterpret_cast<const uint16_t *>(pos)[pidx];
+        last = lst[max(c - 1, 0)];
+    }
+    update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);
+    if (lane < hops) {
+        bool ok = fpos < c;
+#ifdef QRMSA_VALIDATE_RELEASE
+        ok = ok && (lst[fpos] & 0xfffffu) == target;
+#endif
+        if (!ok) {
             err = 1;
         } else {
-            const uint32_t last = lst[c - 1];
             lst[fpos] = last;
             lst[c - 1] = p.sentinel;   // entries past the count are always the zero-contribution filler
             pos_store(p, pos, mylink, rec_pair(last), fpos);
@@ -721,6 +736,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 const int mylink = pt.link(p, path, lane, hops);
                 const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, dm.RW()) : 0;
                 if (lane < hops) prefetch_l1(lists + (unsigned)(mylink * dm.CAP()));  // needed by the GN sum below
+
                 const uint32_t av = path_available(dm, bm, hops, mylink, lane);
                 QCNT(QRMSA_CNT_LINKS_READ, hops);
                 QCNT(QRMSA_CNT_PATHS_TRIED, 1);
