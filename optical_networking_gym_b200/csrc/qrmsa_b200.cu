@@ -327,7 +327,12 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     // QRMSA_BM_SMEM=0 switches it off (experiments).
     ctx->bm_smem = 0;
     {
-        const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * (E * kp.RW * 4 + Streams<true>::BYTES) + ptab.size();
+        kp.smem_warp_off = kp.blob_bytes;
+        kp.smem_warp_stride = WARP_STREAM_BYTES + E * kp.RW * 4;
+        kp.smem_pt_off = kp.smem_warp_off + (ctx->threads / 32) * kp.smem_warp_stride;
+        kp.smem_pt_hops = kp.smem_pt_off + kp.pt_hops_off;
+        kp.smem_pt_links = kp.smem_pt_off + kp.pt_links_off;
+        const size_t need = (size_t)kp.smem_pt_off + ptab.size();
         const char *e = getenv("QRMSA_BM_SMEM");
         const char *lim = getenv("QRMSA_SMEM_LIMIT_KB");
         const size_t limit = lim && atoi(lim) > 0 ? (size_t)atoi(lim) * 1024 : (size_t)ctx->smem_optin;

@@ -68,6 +68,9 @@ struct KParams {
     const unsigned char *blob;  // shared-memory image, 16-byte multiple
     const unsigned char *ptab;  // compact path table for shared memory: u16 offset[n_paths] | u8 hops[n_paths] | u8 links[sum hops]
     int ptab_bytes, pt_hops_off, pt_links_off;   // (16-byte multiple; byte offsets of the second and third part)
+    // BMS step kernel, byte offsets in dynamic shared memory: warp w owns [smem_warp_off + w * smem_warp_stride, ...):
+    // 512 bytes of request / schedule chunks, then its env's link rows; the path table starts at smem_pt_off
+    int smem_warp_off, smem_warp_stride, smem_pt_off, smem_pt_hops, smem_pt_links;
     const uint4 *prec;          // [N*N*K][4] path records (64 B): link ids u8[32] | {PA, PB} | hops (bit 7: prunable)
     int *work;                  // env-group ticket counter of k_step_sub (zeroed before each launch)
     uint8_t *pos;               // [n_envs][E][CAP] (u8 if CAP <= 256, else u16): list position of the channel that starts in
@@ -191,6 +194,23 @@ __device__ __forceinline__ void stage_tables(const KParams &p, uint64_t *mbar) {
 // (one 64-byte line, 4 lanes x 16 B) up to 479 slots, 32 words (8 lanes x 16 B) up to 991: the virtual slot at
 // index S must fall before the count word.
 __host__ __device__ constexpr int row_words(int S) { return S <= 479 ? 16 : 32; }
+// Link rows are reached through row_ld / row_st: a plain pointer (global memory), or RowsS -- the warp's copy in shared
+// memory (BMS), addressed from ONE pinned 32-bit register with the area's offset as an immediate.
+constexpr int WARP_STREAM_BYTES = 512;   // request / schedule chunks ahead of the rows in a warp's shared-memory area
+struct RowsS {
+    uint32_t wb;   // shared-window address of the warp's area
+};
+__device__ __forceinline__ uint32_t row_ld(const uint32_t *bm, unsigned i) { return bm[i]; }
+__device__ __forceinline__ void row_st(uint32_t *bm, unsigned i, uint32_t v) { bm[i] = v; }
+__device__ __forceinline__ uint32_t row_ld(const RowsS &r, unsigned i) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(r.wb + 4u * i), "n"(WARP_STREAM_BYTES));
+    return v;
+}
+__device__ __forceinline__ void row_st(const RowsS &r, unsigned i, uint32_t v) {
+    asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(r.wb + 4u * i), "n"(WARP_STREAM_BYTES), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned cnt_index(int l, int RW) { return (unsigned)(l * RW + RW - 1); }
 __device__ __forceinline__ uint32_t *cnt_word(uint32_t *bm, int l, int RW) { return bm + (unsigned)(l * RW + RW - 1); }
 __device__ __forceinline__ const uint32_t *cnt_word(const uint32_t *bm, int l, int RW) { return bm + (unsigned)(l * RW + RW - 1); }
 
@@ -258,11 +278,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // dependent table loads of every path visit and of every release become LDS, and ~19 KB of hot lines leave L1.
 template <bool SMEM>
 struct PathTab {
-    uint32_t base;   // shared-window address of the compact table (SMEM only)
+    uint32_t base;   // shared-window address of the dynamic shared block (SMEM only); the table's parts sit at the
+                     // KParams offsets smem_pt_off / smem_pt_hops / smem_pt_links
     __device__ __forceinline__ int hops_flags(const KParams &p, int path) const {
         if (SMEM) {
             uint32_t v;
-            asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)(p.pt_hops_off + path)));
+            asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p.smem_pt_hops + (uint32_t)path));
             return (int)v;
         }
         return __ldg(p.path_hops + path);
@@ -271,8 +292,8 @@ struct PathTab {
     __device__ __forceinline__ int link(const KParams &p, int path, int lane, int hops) const {
         if (SMEM) {
             uint32_t off, v = 0;
-            asm("ld.shared.u16 %0, [%1];" : "=r"(off) : "r"(base + 2u * (uint32_t)path));
-            if (lane < hops) asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p.pt_links_off + off + (uint32_t)lane));
+            asm("ld.shared.u16 %0, [%1];" : "=r"(off) : "r"(base + (uint32_t)p.smem_pt_off + 2u * (uint32_t)path));
+            if (lane < hops) asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p.smem_pt_links + off + (uint32_t)lane));
             return (int)v;
         }
         return lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
@@ -282,8 +303,8 @@ struct PathTab {
 // qrmsa.pyx:1482-1512: AND of the path's link rows; plus one virtual free slot at index S, which turns the
 // guard-band rule of qrmsa.pyx:529-540 ("n slots if the run touches the spectrum end, else n+1") into
 // "n+1 consecutive free slots".  32/W link rows are fetched per pass (3 at W=10), then folded with shuffles.
-template <class DM>
-__device__ __forceinline__ uint32_t path_available(const DM &dm, const uint32_t *bm, int hops, int mylink, int lane) {
+template <class DM, class BM>
+__device__ __forceinline__ uint32_t path_available(const DM &dm, const BM bm, int hops, int mylink, int lane) {
     const int W = dm.W(), S = dm.S(), RW = dm.RW();
     const int G = 32 / W;            // link rows per pass
     const int grp = lane / W, j = lane - grp * W;
@@ -292,7 +313,7 @@ __device__ __forceinline__ uint32_t path_available(const DM &dm, const uint32_t 
     for (int i0 = 0; i0 < hops; i0 += G) {
         const int i = i0 + grp;
         const int l = __shfl_sync(FULL, mylink, i & 31);
-        if (grp < G && i < hops) av &= bm[(unsigned)(l * RW + j)];  // mutable state: plain (coherent) load
+        if (grp < G && i < hops) av &= row_ld(bm, (unsigned)(l * RW + j));  // mutable state: plain (coherent) load
     }
     for (int g = 1; g < G; ++g) av &= __shfl_down_sync(FULL, av, g * W);
     if (lane >= W) av = 0u;
@@ -384,8 +405,8 @@ __device__ __forceinline__ double gn_neighbours(const DM &dm, const Tab &t, cons
 
 // Set (release) or clear (commit) bits [s, e) on every link of the path: lane -> (hop = lane>>2, word = lane&3),
 // a service spans at most 4 bitmap words (number_slots + guard <= 97).
-template <bool SET, class DM>
-__device__ __forceinline__ void update_bitmaps(const DM &dm, uint32_t *bm, int hops, int mylink, int s, int e,
+template <bool SET, class DM, class BM>
+__device__ __forceinline__ void update_bitmaps(const DM &dm, const BM bm, int hops, int mylink, int s, int e,
                                                int lane) {
     const int W = dm.W(), RW = dm.RW();
     const int w0 = s >> 5;
@@ -397,15 +418,16 @@ __device__ __forceinline__ void update_bitmaps(const DM &dm, uint32_t *bm, int h
         const int i = i0 + (lane >> 2);
         const int l = __shfl_sync(FULL, mylink, i & 31);
         if (i < hops && mask) {
-            uint32_t *wp = bm + (unsigned)(l * RW + j);
-            *wp = SET ? (*wp | mask) : (*wp & ~mask);
+            const unsigned wi = (unsigned)(l * RW + j);
+            const uint32_t w = row_ld(bm, wi);
+            row_st(bm, wi, SET ? (w | mask) : (w & ~mask));
         }
     }
 }
 
 // qrmsa.pyx:1288-1325 (the release key of :1327-1330 is implicit in the precomputed schedule)
-template <class DM>
-__device__ __forceinline__ int commit(const DM &dm, const KParams &p, uint32_t *bm, uint32_t *lists, uint8_t *pos, int hops,
+template <class DM, class BM>
+__device__ __forceinline__ int commit(const DM &dm, const KParams &p, const BM bm, uint32_t *lists, uint8_t *pos, int hops,
                                       int mylink, int mycnt, int s, int n, uint32_t rec, int lane) {
     int e = s + n;
     if (e < dm.S()) e += 1;
@@ -417,7 +439,7 @@ __device__ __forceinline__ int commit(const DM &dm, const KParams &p, uint32_t *
         } else {
             lists[(unsigned)(mylink * dm.CAP() + mycnt)] = rec;
             pos_store(p, pos, mylink, s >> 1, mycnt);
-            *cnt_word(bm, mylink, dm.RW()) = (uint32_t)(mycnt + 1);
+            row_st(bm, cnt_index(mylink, dm.RW()), (uint32_t)(mycnt + 1));
         }
     }
     return __any_sync(FULL, err);
@@ -425,8 +447,8 @@ __device__ __forceinline__ int commit(const DM &dm, const KParams &p, uint32_t *
 
 // qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record.
 // Lane i handles hop i: the record's place in the link's list comes from the position table, so there is no search.
-template <class DM, class PT = PathTab<false>>
-__device__ __forceinline__ int release_service(const DM &dm, const KParams &p, const Tab &t, uint32_t *bm,
+template <class DM, class BM, class PT = PathTab<false>>
+__device__ __forceinline__ int release_service(const DM &dm, const KParams &p, const Tab &t, const BM bm,
                                                uint32_t *lists, uint8_t *pos, const uint4 rq, int lane,
                                                const PT pt = PT()) {
     const int S = dm.S(), M = dm.M(), CAP = dm.CAP();
@@ -450,9 +472,9 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     int err = 0, c = 0, fpos = 0;
     uint32_t last = 0u;
     uint32_t *lst = lists + (unsigned)(mylink * CAP);
-    uint32_t *cw = cnt_word(bm, mylink, dm.RW());
+    const unsigned cw = cnt_index(mylink, dm.RW());
     if (lane < hops) {
-        c = (int)*cw;
+        c = (int)row_ld(bm, cw);
         const unsigned pidx = pos_index(p, mylink, s >> 1);
         fpos = p.pos_bytes == 1 ? (int)pos[pidx] : (int)reinterpret_cast<const uint16_t *>(pos)[pidx];
         last = lst[max(c - 1, 0)];
@@ -469,7 +491,7 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
             lst[fpos] = last;
             lst[c - 1] = p.sentinel;   // entries past the count are always the zero-contribution filler
             pos_store(p, pos, mylink, rec_pair(last), fpos);
-            *cw = (uint32_t)(c - 1);
+            row_st(bm, cw, (uint32_t)(c - 1));
         }
     }
     err = __any_sync(FULL, err);
@@ -484,7 +506,7 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
 template <bool RING>
 struct Streams {
     uint32_t base;   // shared-window address of this warp's 512-byte area (RING only)
-    static constexpr int BYTES = 512;
+    static constexpr int BYTES = WARP_STREAM_BYTES;
     __device__ __forceinline__ void fill_tr(const uint4 *tr, int chunk, int lane, int T) const {
         if (RING) {
             if (lane < 8) {
@@ -561,9 +583,9 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
 // qrmsa.pyx:1067-1122 after a request has been decided: take the next request (clock := its arrival) and
 // release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
 // schedule exactly as they are absent from the reference heap.
-template <class DM, class PT = PathTab<false>, class ST = Streams<false>>
+template <class DM, class BM, class PT = PathTab<false>, class ST = Streams<false>>
 __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
-                                                   const unsigned long long *perm, uint32_t *bm, uint32_t *lists, uint8_t *pos,
+                                                   const unsigned long long *perm, const BM bm, uint32_t *lists, uint8_t *pos,
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel,
                                                    const PT pt = PT(), const ST sm = ST()) {
     cur += 1;
@@ -611,6 +633,17 @@ __device__ __forceinline__ bool qot_ok(const Tab &t, int m, double acc, uint32_t
 // --------------------------------------------------------------------------------------------------------
 enum { POLICY_FIRST_FIT = 0, POLICY_LOAD_BALANCING = 1, POLICY_LB_FIRST_FIT = 3 };   // ids of include/qrmsa_b200.h
 
+template <bool BMS>
+struct RowHandle {
+    typedef uint32_t *type;
+    static __device__ __forceinline__ type make(uint32_t *g, uint32_t) { return g; }
+};
+template <>
+struct RowHandle<true> {
+    typedef RowsS type;
+    static __device__ __forceinline__ type make(uint32_t *, uint32_t wb) { RowsS r; r.wb = wb; return r; }
+};
+
 template <int S_, int M_, int K_, int POLICY, bool BMS = false>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p, const int n_steps) {
     __shared__ uint64_t mbar;
@@ -622,19 +655,22 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
 
     const int lane = threadIdx.x & 31;
     const int reject = K * M * S;
+    // BMS: shared memory = tables | per-warp areas (stream chunks, then the env's link rows) | compact path table.
+    // Everything is addressed from two pinned 32-bit registers (t.sb, wb) plus KParams offsets, which reach the
+    // instructions as constant-bank operands -- no per-access re-derivation of warp index times stride.
     PathTab<BMS> pt;
-    pt.base = 0;
+    pt.base = t.sb;
+    uint32_t wb = 0;
     if (BMS) {
-        // compact path table after the per-warp row areas
-        const unsigned off = (unsigned)p.blob_bytes + (unsigned)((blockDim.x >> 5) * (int)p.bm_stride * 4);
         const uint4 *src = reinterpret_cast<const uint4 *>(p.ptab);
-        uint4 *dst = reinterpret_cast<uint4 *>(qsmem + off);
+        uint4 *dst = reinterpret_cast<uint4 *>(qsmem + p.smem_pt_off);
         for (int i = threadIdx.x; i < (p.ptab_bytes >> 4); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
-        pt.base = t.sb + off;
+        wb = t.sb + (uint32_t)p.smem_warp_off + (uint32_t)((threadIdx.x >> 5) * p.smem_warp_stride);
+        asm volatile("" : "+r"(wb));
     }
-    Streams<BMS> sm;   // request / schedule chunks of this warp's env, after the path table
-    sm.base = BMS ? pt.base + (uint32_t)p.ptab_bytes + (uint32_t)((threadIdx.x >> 5) * Streams<BMS>::BYTES) : 0u;
+    Streams<BMS> sm;   // request / schedule chunks of this warp's env: the first 512 bytes of the warp's area
+    sm.base = wb;
 
     // envs are handed out by a ticket counter (zeroed before the launch): a warp that finishes early takes the next
     // env instead of idling behind a fixed share
@@ -650,15 +686,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         int cur = st.x, rel_ptr = st.y, err = 0;
         uint4 *tr = p.trace + (size_t)env * p.T;
         const unsigned long long *perm = p.perm + (size_t)env * p.T;
-        uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
-        uint32_t *const bm_global = bm;
+        uint32_t *bm_global = p.bm + (size_t)env * p.bm_stride;
+        typename RowHandle<BMS>::type bm = RowHandle<BMS>::make(bm_global, wb);
         if (BMS) {
             // BMS: the env's link rows (bitmaps + channel counts) live in shared memory for the whole launch -- every
             // row read, commit and release is an LDS/STS instead of a trip to L1/L2; 16-byte copies in and out
-            bm = reinterpret_cast<uint32_t *>(qsmem + p.blob_bytes) + (unsigned)((threadIdx.x >> 5) * (int)p.bm_stride);
             const uint4 *src = reinterpret_cast<const uint4 *>(bm_global);
-            uint4 *dst = reinterpret_cast<uint4 *>(bm);
-            for (int i = lane; i < (int)(p.bm_stride >> 2); i += 32) dst[i] = src[i];
+            for (int i = lane; i < (int)(p.bm_stride >> 2); i += 32) {
+                const uint4 v = src[i];
+                asm volatile("st.shared.v4.u32 [%0+%1], {%2,%3,%4,%5};" ::"r"(wb + 16u * (uint32_t)i), "n"(WARP_STREAM_BYTES),
+                             "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
             __syncwarp();
         }
         uint32_t *lists = p.lists + (size_t)env * p.E * dm.CAP();
@@ -667,12 +705,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         // re-derives env * stride (two IMADs, an IMAD.WIDE, LEA + LEA.HI.X and the constant loads) at most accesses
         asm volatile("" : "+l"(tr));
         asm volatile("" : "+l"(perm));
-        if (!BMS) asm volatile("" : "+l"(bm));
+        if (!BMS) asm volatile("" : "+l"(bm_global));
         asm volatile("" : "+l"(lists));
         asm volatile("" : "+l"(pos));
         __builtin_assume(__isGlobal(tr));
         __builtin_assume(__isGlobal(perm));
-        if (!BMS) __builtin_assume(__isGlobal(bm));
+        if (!BMS) __builtin_assume(__isGlobal(bm_global));
+        if (!BMS) bm = RowHandle<BMS>::make(bm_global, wb);
         __builtin_assume(__isGlobal(lists));
         __builtin_assume(__isGlobal(pos));
         sm.fill_tr(tr, cur >> 3, lane, p.T);
@@ -734,7 +773,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 if (hops == 0) continue;
                 const bool prunable = (hp & 0x80) != 0;
                 const int mylink = pt.link(p, path, lane, hops);
-                const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, dm.RW()) : 0;
+                const int mycnt = lane < hops ? (int)row_ld(bm, cnt_index(mylink, dm.RW())) : 0;
                 if (lane < hops) prefetch_l1(lists + (unsigned)(mylink * dm.CAP()));  // needed by the GN sum below
 
                 const uint32_t av = path_available(dm, bm, hops, mylink, lane);
@@ -827,7 +866,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 const int path = pbase + best_pi;
                 const int hops = pt.hops_flags(p, path) & 0x7f;
                 const int mylink = pt.link(p, path, lane, hops);
-                const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, dm.RW()) : 0;
+                const int mycnt = lane < hops ? (int)row_ld(bm, cnt_index(mylink, dm.RW())) : 0;
                 const int nd = __shfl_sync(FULL, mynd, best_m);
                 const int n = nd & 0xff, ncls = nd >> 8;
                 action = best_pi * M * S + ((M - 1) - best_m) * S + best_s;
@@ -862,9 +901,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         }
         if (BMS) {
             __syncwarp();
-            const uint4 *src = reinterpret_cast<const uint4 *>(bm);
             uint4 *dst = reinterpret_cast<uint4 *>(bm_global);
-            for (int i = lane; i < (int)(p.bm_stride >> 2); i += 32) dst[i] = src[i];
+            for (int i = lane; i < (int)(p.bm_stride >> 2); i += 32) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"(wb + 16u * (uint32_t)i), "n"(WARP_STREAM_BYTES));
+                dst[i] = v;
+            }
+            __syncwarp();   // the next env's rows overwrite the area
         }
         if (lane == 0) {   // estate.z (the accepted total) belongs to k_count_decisions
             int *es = reinterpret_cast<int *>(p.estate + env);
