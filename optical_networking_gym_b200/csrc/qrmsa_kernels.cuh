@@ -303,17 +303,28 @@ struct PathTab {
 // qrmsa.pyx:1482-1512: AND of the path's link rows; plus one virtual free slot at index S, which turns the
 // guard-band rule of qrmsa.pyx:529-540 ("n slots if the run touches the spectrum end, else n+1") into
 // "n+1 consecutive free slots".  32/W link rows are fetched per pass (3 at W=10), then folded with shuffles.
+template <class BM> struct RowUnroll { static constexpr int U = 4; };   // global rows: four row loads in flight per pass
+template <> struct RowUnroll<RowsS> { static constexpr int U = 1; };     // shared memory: latency is short, keep it lean
 template <class DM, class BM>
 __device__ __forceinline__ uint32_t path_available(const DM &dm, const BM bm, int hops, int mylink, int lane) {
     const int W = dm.W(), S = dm.S(), RW = dm.RW();
     const int G = 32 / W;            // link rows per pass
     const int grp = lane / W, j = lane - grp * W;
+    constexpr int U = RowUnroll<BM>::U;
     uint32_t av = 0xffffffffu;
 #pragma unroll 1
-    for (int i0 = 0; i0 < hops; i0 += G) {
-        const int i = i0 + grp;
-        const int l = __shfl_sync(FULL, mylink, i & 31);
-        if (grp < G && i < hops) av &= row_ld(bm, (unsigned)(l * RW + j));  // mutable state: plain (coherent) load
+    for (int i0 = 0; i0 < hops; i0 += U * G) {
+        // the U loads of a pass are independent: issued back to back, folded afterwards (at 640 slots a pass is one
+        // row, and a serial AND would make every hop its own L2 round trip)
+        uint32_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * G + grp;
+            const int l = __shfl_sync(FULL, mylink, i & 31);
+            v[u] = (grp < G && i < hops) ? row_ld(bm, (unsigned)(l * RW + j)) : 0xffffffffu;  // mutable state: plain (coherent) load
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) av &= v[u];
     }
     for (int g = 1; g < G; ++g) av &= __shfl_down_sync(FULL, av, g * W);
     if (lane >= W) av = 0u;
