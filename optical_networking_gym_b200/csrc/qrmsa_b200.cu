@@ -23,6 +23,7 @@ struct qrmsa_ctx {
     int sub_grid = 0;
     bool use_warp_kernel = false;
     size_t sub_smem = 0;
+    size_t ring_smem = 0;            // dynamic shared memory of the step kernel with the stream chunks only (0 = not used)
     size_t bm_smem = 0;              // dynamic shared memory of the step kernel with the bitmap rows staged (0 = not used)
     size_t cta_smem = 0;   // k_step_highest_snr (and k_observation): one CTA per env
     int cta_grid = 0, cta_epc = 0, cta_env_smem = 0;
@@ -338,12 +339,25 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         const size_t limit = lim && atoi(lim) > 0 ? (size_t)atoi(lim) * 1024 : (size_t)ctx->smem_optin;
         if (!(e && atoi(e) == 0) && ptab_ok && ctas_per_sm == 1 && need <= (size_t)ctx->smem_optin && need <= limit) {
             ctx->bm_smem = need;
-            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_FIRST_FIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        }
+    }
+    // rows do not fit (or are switched off): the stream chunks alone, 512 bytes per warp after the tables
+    ctx->ring_smem = 0;
+    if (!ctx->bm_smem && ctas_per_sm == 1) {
+        const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * WARP_STREAM_BYTES;
+        const char *e = getenv("QRMSA_RING_SMEM");
+        if (!(e && atoi(e) == 0) && need <= (size_t)ctx->smem_optin) {
+            ctx->ring_smem = need;
+            kp.smem_warp_off = kp.blob_bytes;
+            kp.smem_warp_stride = WARP_STREAM_BYTES;
+            CK(cudaFuncSetAttribute(k_step_policy<640, 6, 5, POLICY_FIRST_FIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         }
     }
     const int sub_smem_max = kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2);
@@ -671,6 +685,7 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
     cudaStream_t st = (cudaStream_t)stream;
     const int g = ctx->grid, th = ctx->threads, sm = kp.blob_bytes;
     const size_t bsm = ctx->bm_smem;   // != 0: the kernel variant with the bitmap rows staged in shared memory
+    const size_t rsm = ctx->ring_smem; // != 0: the variant with the stream chunks only
     // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
     const bool c320 = kp.S == 320 && kp.M == 6 && kp.K == 5, c640 = kp.S == 640 && kp.M == 6 && kp.K == 5;
     if (policy == QRMSA_POLICY_FIRST_FIT && !ctx->use_warp_kernel) {
@@ -685,25 +700,27 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
     } else if (policy == QRMSA_POLICY_FIRST_FIT) {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
-        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_FIRST_FIT, true><<<g, th, bsm, st>>>(kp, n_steps);
+        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_FIRST_FIT, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
+        else if (c640 && rsm) k_step_policy<640, 6, 5, POLICY_FIRST_FIT, 2><<<g, th, rsm, st>>>(kp, n_steps);
         else if (c640) k_step_policy<640, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
-        else if (bsm) k_step_policy<0, 0, 0, POLICY_FIRST_FIT, true><<<g, th, bsm, st>>>(kp, n_steps);
+        else if (bsm) k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 1><<<g, th, bsm, st>>>(kp, n_steps);
+        else if (rsm) k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 2><<<g, th, rsm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_LB_FIRST_FIT) {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
-        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT, true><<<g, th, bsm, st>>>(kp, n_steps);
+        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else if (c320) k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
-        else if (bsm) k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, true><<<g, th, bsm, st>>>(kp, n_steps);
+        else if (bsm) k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_HIGHEST_SNR) {
         if (!ctx->cta_grid) { ctx->err = "highest-SNR policy needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
         k_step_highest_snr<<<ctx->cta_grid, ctx->cta_epc * OBS_ENV_THREADS, ctx->cta_smem, st>>>(kp, n_steps, ctx->cta_epc, ctx->cta_env_smem);
     } else {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
-        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, true><<<g, th, bsm, st>>>(kp, n_steps);
+        if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else if (c320) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
-        else if (bsm) k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, true><<<g, th, bsm, st>>>(kp, n_steps);
+        else if (bsm) k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
     }
     if (policy != QRMSA_POLICY_FIRST_FIT || ctx->use_warp_kernel) {

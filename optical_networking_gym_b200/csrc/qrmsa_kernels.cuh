@@ -655,8 +655,12 @@ struct RowHandle<true> {
     static __device__ __forceinline__ type make(uint32_t *, uint32_t wb) { RowsS r; r.wb = wb; return r; }
 };
 
-template <int S_, int M_, int K_, int POLICY, bool BMS = false>
+// SM_: what the kernel keeps in shared memory beside the tables.  0 = nothing; 1 ("BMS") = per warp the env's link rows and
+// the request / schedule stream chunks, plus the compact path table; 2 = the stream chunks only (configurations whose
+// rows do not fit, e.g. 640 slots: the tables alone take 183 KB).
+template <int S_, int M_, int K_, int POLICY, int SM_ = 0>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p, const int n_steps) {
+    constexpr bool BMS = SM_ == 1, RING = SM_ != 0;
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
     Tab t;
@@ -677,10 +681,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
         uint4 *dst = reinterpret_cast<uint4 *>(qsmem + p.smem_pt_off);
         for (int i = threadIdx.x; i < (p.ptab_bytes >> 4); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
+    }
+    if (RING) {
         wb = t.sb + (uint32_t)p.smem_warp_off + (uint32_t)((threadIdx.x >> 5) * p.smem_warp_stride);
         asm volatile("" : "+r"(wb));
     }
-    Streams<BMS> sm;   // request / schedule chunks of this warp's env: the first 512 bytes of the warp's area
+    Streams<RING> sm;   // request / schedule chunks of this warp's env: the first 512 bytes of the warp's area
     sm.base = wb;
 
     // envs are handed out by a ticket counter (zeroed before the launch): a warp that finishes early takes the next
