@@ -4,9 +4,12 @@
 // bitmap, so the AND along a path, the contiguous-block search and the commit/release masks are
 // single warp-wide instructions; the GN-model sum deals the path's channel records to the lanes in
 // groups of four (one 16-byte load each).  A warp keeps its env for all n_steps of a launch, so the
-// env's state is pulled from HBM once per launch and then lives in L1/L2 -- the link rows (bitmaps + channel counts)
-// in shared memory when tables + 32 envs' rows leave L1 at least 64 KB (BMS variant).  No tensor cores: no stage
-// is a dense contraction.
+// env's state is pulled from HBM once per launch and then lives on chip: in the SM_ = 1 ("BMS") variant of the step
+// kernel the env's link rows (bitmaps + channel counts), the current and next 128-byte chunk of its request and
+// schedule streams (cp.async) and a compact copy of the path table sit in shared memory beside the GN tables
+// (227 KB on nobel-eu/320); the channel lists, the position table and the trace go through L1/L2.  SM_ = 2 keeps
+// only the stream chunks there (640 slots: the tables alone take 183 KB), SM_ = 0 nothing.  No tensor cores: no
+// stage is a dense contraction.
 //
 // HBM layout per env (all per-env blocks are contiguous, 64-byte aligned):
 //   bm      uint32 [E][RW]    link rows: words 0..W-1 = packed slots, 1 = free (reference:
