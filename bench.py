@@ -48,7 +48,9 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=256, help="requests per env per bench step (one launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-slices", type=int, default=4)
+    ap.add_argument("--e2e-slices", type=int, default=16,
+                    help="env slices of the pipelined episode; at most one wave of warps (148 SMs x 32 envs) per "
+                         "slice, so that slices interleave instead of leaving a tail: 65,536 envs -> 16")
     ap.add_argument("--ref-chunk", type=int, default=64, help="--impl reference: requests per env per step")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--topology", default=TOPOLOGY, help="other BASELINE configs (parity cases), e.g. germany50")
