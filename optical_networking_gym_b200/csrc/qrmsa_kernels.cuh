@@ -794,7 +794,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 const bool prunable = (hp & 0x80) != 0;
                 const int mylink = pt.link(p, path, lane, hops);
                 const int mycnt = lane < hops ? (int)row_ld(bm, cnt_index(mylink, dm.RW())) : 0;
-                if (lane < hops) prefetch_l1(lists + (unsigned)(mylink * dm.CAP()));  // needed by the GN sum below
+                // needed by the GN sum below; with the rows in shared memory L1 is down to 28 KB and a prefetched line
+                // does not survive until its use (measured: 9.15e8 with, 9.29e8 without)
+                if (!BMS && lane < hops) prefetch_l1(lists + (unsigned)(mylink * dm.CAP()));
 
                 const uint32_t av = path_available(dm, bm, hops, mylink, lane);
                 QCNT(QRMSA_CNT_LINKS_READ, hops);
