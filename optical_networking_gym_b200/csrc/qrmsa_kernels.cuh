@@ -222,11 +222,7 @@ __device__ __forceinline__ const uint32_t *cnt_word(const uint32_t *bm, int l, i
 // Laid out [pair][link]: the entries of one service on the links of its path share a 128-byte line (E <= 128), so a
 // commit or a release touches one line of the table instead of one per hop.
 __device__ __forceinline__ unsigned pos_index(const KParams &p, int l, int pair) {
-#ifdef QRMSA_POS_LINK_MAJOR
-    return (unsigned)(l * p.CAP + pair);
-#else
     return (unsigned)(pair * p.E + l);
-#endif
 }
 __device__ __forceinline__ void pos_store(const KParams &p, uint8_t *pos, int l, int pair, int v) {
     const unsigned i = pos_index(p, l, pair);
