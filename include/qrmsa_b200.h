@@ -121,6 +121,13 @@ void qrmsa_destroy(qrmsa_ctx *ctx);
 
 /* Env groups (contiguous, equal-sized) for per-load-point counters; default 1. */
 int qrmsa_set_groups(qrmsa_ctx *ctx, int n_groups);
+/*
+ * What the step kernel keeps in shared memory beside the GN tables.  2 (default): per warp the env's link rows and the
+ * request / schedule stream chunks plus a compact path table, whenever they fit (else as 1); 1: the stream chunks only
+ * (else as 0); 0: nothing -- all env state through L1/L2.  The three variants compute the same words; lowering the level
+ * is what a configuration with larger tables gets by itself, and is how tests hold the variants to each other.
+ */
+int qrmsa_set_staging(qrmsa_ctx *ctx, int level);
 /* Keep a per-request GSNR log (double, [n_envs][max_requests]); off by default. */
 int qrmsa_enable_gsnr_log(qrmsa_ctx *ctx, int enable);
 
@@ -230,6 +237,13 @@ int qrmsa_get_actions_host(qrmsa_ctx *ctx, int first, int count, int32_t *h_out,
 /* Asynchronous, strided variant: h_out is [count][row_stride] int32 (pinned), this context's envs start at h_out. */
 int qrmsa_get_actions_host_strided(qrmsa_ctx *ctx, int first, int count, int32_t *h_out, int64_t row_stride,
                                    void *stream);
+/*
+ * Request / service / decision records [first, first+count) of ONE env, uint32 [count][4] =
+ * {arrival float32 bits, holding float32 bits, src | dst << 8 | rate index << 16, action word} -- the env's request
+ * stream (Service fields of envs/qrmsa.pyx:29-116) and its decision log in one copy; used to replay sampled envs of a
+ * large batch through a checker.  Synchronises the device.
+ */
+int qrmsa_get_env_log_host(qrmsa_ctx *ctx, int env, int first, int count, uint32_t *h_records4);
 /* GSNR (dB) of the accepted candidate per request (0.0 on reject), needs qrmsa_enable_gsnr_log. */
 int qrmsa_get_gsnr_host(qrmsa_ctx *ctx, int first, int count, double *h_out, void *stream);
 /* ASE-only and NLI-only figures (dB) of the same candidates: the 2nd and 3rd value calculate_osnr returns

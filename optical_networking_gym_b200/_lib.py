@@ -13,9 +13,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.environ.get("QRMSA_LIB") or os.path.join(HERE, "libqrmsa_b200.so")
+LIB_PATH = os.path.join(HERE, "libqrmsa_b200.so")
 SOURCES = ("qrmsa_b200.cu", "tracegen.cpp")
-HEADERS = ("qrmsa_kernels.cuh", "qrmsa_step_sub.cuh", os.path.join("..", "..", "include", "qrmsa_b200.h"))
+HEADERS = ("qrmsa_kernels.cuh", os.path.join("..", "..", "include", "qrmsa_b200.h"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -48,8 +48,6 @@ def _nvcc() -> str:
 
 
 def needs_build() -> bool:
-    if os.environ.get("QRMSA_LIB"):
-        return False   # an explicitly selected prebuilt library (kernel experiments)
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
@@ -89,6 +87,7 @@ SIGNATURES = {
     "qrmsa_create": (_I, [C.POINTER(StaticTablesC), _I, _I, _I, C.POINTER(_P)]),
     "qrmsa_destroy": (None, [_P]),
     "qrmsa_set_groups": (_I, [_P, _I]),
+    "qrmsa_set_staging": (_I, [_P, _I]),
     "qrmsa_enable_gsnr_log": (_I, [_P, _I]),
     "qrmsa_reset": (_I, [_P, _P]),
     "qrmsa_load_trace": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
@@ -104,6 +103,7 @@ SIGNATURES = {
     "qrmsa_get_actions": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_actions_host": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_actions_host_strided": (_I, [_P, _I, _I, _P, C.c_int64, _P]),
+    "qrmsa_get_env_log_host": (_I, [_P, _I, _I, _I, _P]),
     "qrmsa_get_gsnr_host": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_ase_nli_host": (_I, [_P, _I, _I, _P, _P, _P]),
     "qrmsa_counters": (_I, [_P, _P, _P]),

@@ -9,7 +9,6 @@
 #include <vector>
 
 #include "qrmsa_kernels.cuh"
-#include "qrmsa_step_sub.cuh"
 
 using namespace qrmsa;
 
@@ -19,12 +18,11 @@ struct qrmsa_ctx {
     int smem_optin = 0;
     int threads = 512;
     int grid = 0;
-    int sub_threads = 0;   // k_step_sub: threads per CTA (one CTA per SM)
-    int sub_grid = 0;
-    bool use_warp_kernel = false;
-    size_t sub_smem = 0;
-    size_t ring_smem = 0;            // dynamic shared memory of the step kernel with the stream chunks only (0 = not used)
-    size_t bm_smem = 0;              // dynamic shared memory of the step kernel with the bitmap rows staged (0 = not used)
+    size_t ring_smem = 0;            // dynamic shared memory of the step kernel with the stream chunks only (0 = does not fit)
+    size_t bm_smem = 0;              // dynamic shared memory of the step kernel with the bitmap rows staged (0 = does not fit)
+    int staging = 2;                 // qrmsa_set_staging: 2 = rows + streams + paths when they fit, 1 = streams only, 0 = none
+    int warp_off_bms = 0, warp_stride_bms = 0;   // KParams.smem_warp_* of the two staged variants
+    int warp_off_ring = 0, warp_stride_ring = 0;
     size_t cta_smem = 0;   // k_step_highest_snr (and k_observation): one CTA per env
     int cta_grid = 0, cta_epc = 0, cta_env_smem = 0;
     // on-device request generator
@@ -301,89 +299,67 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         return QRMSA_ERR_UNSUPPORTED;
     }
     // one 1024-thread CTA per SM: the 32 warps share one copy of the GN tables, which leaves the rest of the
-    // 228 KB for L1 (env state is re-read from L1/L2 across the steps of a launch); QRMSA_CTAS_PER_SM=2 selects
-    // two 512-thread CTAs instead (same warps, two table copies) for experiments
-    int ctas_per_sm = 1;
+    // 228 KB for L1 (env state is re-read from L1/L2 across the steps of a launch)
     ctx->threads = MAX_THREADS;
-    const char *env_ctas = getenv("QRMSA_CTAS_PER_SM");
-    if (env_ctas && atoi(env_ctas) == 2 && 2 * (size_t)(kp.blob_bytes + 1024 + 64) <= (size_t)smem_sm) {
-        ctas_per_sm = 2;
-        ctx->threads = 512;
-    }
     const int wpc = ctx->threads / 32;
     const int want = (n_envs + wpc - 1) / wpc;
-    ctx->grid = want < ctx->sm_count * ctas_per_sm ? want : ctx->sm_count * ctas_per_sm;
-    CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_policy<640, 6, 5, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
-    CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    ctx->grid = want < ctx->sm_count ? want : ctx->sm_count;
+    // the step kernels keep an 8-byte mbarrier in static shared memory next to the dynamic block
+    cudaFuncAttributes fa{};
+    CK(cudaFuncGetAttributes(&fa, k_step_policy<0, 0, 0, POLICY_FIRST_FIT>));
+    const size_t smem_budget = (size_t)ctx->smem_optin - fa.sharedSizeBytes;
+    auto opt_in = [&](const void *fn, size_t bytes) { return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess; };
+    bool ok = true;
+    ok &= opt_in((const void *)k_step_policy<320, 6, 5, POLICY_FIRST_FIT>, kp.blob_bytes);
+    ok &= opt_in((const void *)k_step_policy<640, 6, 5, POLICY_FIRST_FIT>, kp.blob_bytes);
+    ok &= opt_in((const void *)k_step_policy<0, 0, 0, POLICY_FIRST_FIT>, kp.blob_bytes);
+    ok &= opt_in((const void *)k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING>, kp.blob_bytes);
+    ok &= opt_in((const void *)k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING>, kp.blob_bytes);
+    ok &= opt_in((const void *)k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT>, kp.blob_bytes);
+    ok &= opt_in((const void *)k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT>, kp.blob_bytes);
+    if (!ok) { (void)cudaGetLastError(); ctx->err = "GN tables exceed shared memory per block"; return QRMSA_ERR_UNSUPPORTED; }
     // Bitmap rows staged in shared memory (one area per warp after the tables): every row read, commit and release
     // becomes an LDS/STS; a compact copy of the path table (hop counts + link ids) follows them.  Used whenever
-    // tables + rows + paths fit the 227 KB a CTA may have: nobel-eu/320 = 96 + 84 + 31 KB, which leaves L1 only
-    // 28 KB for the lists, the position table and the trace -- measured 7.50e8 (all through L1, 156 KB) -> 7.85e8
-    // (rows in shared memory, 60 KB of L1) -> 8.03e8 (rows + paths).  QRMSA_SMEM_LIMIT_KB caps it (experiments).
-    // QRMSA_BM_SMEM=0 switches it off (experiments).
+    // tables + rows + paths fit what a CTA may have beside the kernel's static shared memory: nobel-eu/320 =
+    // 96 + 84 + 31 KB, which leaves L1 only 28 KB for the lists, the position table and the trace -- measured 7.50e8
+    // (all through L1, 156 KB) -> 7.85e8 (rows in shared memory, 60 KB of L1) -> 8.03e8 (rows + paths).
     ctx->bm_smem = 0;
+    kp.smem_pt_off = kp.smem_pt_hops = kp.smem_pt_links = 0;
     {
-        kp.smem_warp_off = kp.blob_bytes;
-        kp.smem_warp_stride = WARP_STREAM_BYTES + E * kp.RW * 4;
-        kp.smem_pt_off = kp.smem_warp_off + (ctx->threads / 32) * kp.smem_warp_stride;
-        kp.smem_pt_hops = kp.smem_pt_off + kp.pt_hops_off;
-        kp.smem_pt_links = kp.smem_pt_off + kp.pt_links_off;
-        const size_t need = (size_t)kp.smem_pt_off + ptab.size();
-        const char *e = getenv("QRMSA_BM_SMEM");
-        const char *lim = getenv("QRMSA_SMEM_LIMIT_KB");
-        const size_t limit = lim && atoi(lim) > 0 ? (size_t)atoi(lim) * 1024 : (size_t)ctx->smem_optin;
-        if (!(e && atoi(e) == 0) && ptab_ok && ctas_per_sm == 1 && need <= (size_t)ctx->smem_optin && need <= limit) {
-            ctx->bm_smem = need;
-            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_FIRST_FIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        ctx->warp_off_bms = kp.blob_bytes;
+        ctx->warp_stride_bms = WARP_STREAM_BYTES + E * kp.RW * 4;
+        const int pt_off = ctx->warp_off_bms + wpc * ctx->warp_stride_bms;
+        const size_t need = (size_t)pt_off + ptab.size();
+        if (ptab_ok && need <= smem_budget) {
+            bool fit = true;
+            fit &= opt_in((const void *)k_step_policy<320, 6, 5, POLICY_FIRST_FIT, 1>, need);
+            fit &= opt_in((const void *)k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 1>, need);
+            fit &= opt_in((const void *)k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, 1>, need);
+            fit &= opt_in((const void *)k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, 1>, need);
+            fit &= opt_in((const void *)k_step_policy<320, 6, 5, POLICY_LB_FIRST_FIT, 1>, need);
+            fit &= opt_in((const void *)k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, 1>, need);
+            if (fit) {
+                ctx->bm_smem = need;
+                kp.smem_pt_off = pt_off;
+                kp.smem_pt_hops = pt_off + kp.pt_hops_off;
+                kp.smem_pt_links = pt_off + kp.pt_links_off;
+            } else {
+                (void)cudaGetLastError();   // the attribute call refused: fall back to the smaller variants below
+            }
         }
     }
-    // rows do not fit (or are switched off): the stream chunks alone, 512 bytes per warp after the tables
+    // the stream chunks alone, 512 bytes per warp after the tables (configurations whose rows do not fit)
     ctx->ring_smem = 0;
-    if (!ctx->bm_smem && ctas_per_sm == 1) {
-        const size_t need = (size_t)kp.blob_bytes + (size_t)(ctx->threads / 32) * WARP_STREAM_BYTES;
-        const char *e = getenv("QRMSA_RING_SMEM");
-        if (!(e && atoi(e) == 0) && need <= (size_t)ctx->smem_optin) {
-            ctx->ring_smem = need;
-            kp.smem_warp_off = kp.blob_bytes;
-            kp.smem_warp_stride = WARP_STREAM_BYTES;
-            CK(cudaFuncSetAttribute(k_step_policy<640, 6, 5, POLICY_FIRST_FIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        }
-    }
-    const int sub_smem_max = kp.blob_bytes + 32 * 8 * SUB_HCAP * (int)sizeof(uint2);
-    const bool sub_fits = sub_smem_max <= ctx->smem_optin;   // the experiment kernel keeps a per-env link scratch after the tables
-    if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<4, 320, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
-    if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<8, 640, 6, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
-    if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<4, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
-    if (sub_fits) CK(cudaFuncSetAttribute(k_step_sub<8, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sub_smem_max));
     {
-        // k_step_sub: one CTA per SM, env groups (32/LPE envs per warp) handed out by a ticket counter.  The CTA
-        // size is the smallest that keeps the number of rounds: e.g. 65,536 envs / 8 per warp / 148 SMs = 55.4
-        // groups per SM -> 2 rounds of 28 warps rather than 2 rounds of 32 with the second one 73 % full.
-        const int lpe = kp.RW / 4, epw = 32 / lpe;
-        const int groups = (n_envs + epw - 1) / epw;
-        const int wmax = QRMSA_SUB_THREADS / 32;
-        int per_sm = (groups + ctx->sm_count - 1) / ctx->sm_count;
-        int rounds = (per_sm + wmax - 1) / wmax;
-        int w = (per_sm + rounds - 1) / rounds;
-        const char *env_w = getenv("QRMSA_SUB_WARPS");
-        if (env_w && atoi(env_w) >= 1 && atoi(env_w) <= wmax) w = atoi(env_w);
-        ctx->sub_threads = 32 * (w < 1 ? 1 : w);
-        ctx->sub_grid = groups < ctx->sm_count ? groups : ctx->sm_count;
-        const char *impl = getenv("QRMSA_STEP_IMPL");
-        // default: warp per env (k_step_policy); QRMSA_STEP_IMPL=sub selects the lanes-per-env experiment (k_step_sub)
-        ctx->use_warp_kernel = !(impl && !strcmp(impl, "sub")) || t->max_hops > SUB_HCAP || !sub_fits;
-        ctx->sub_smem = (size_t)kp.blob_bytes + (size_t)(ctx->sub_threads / 32) * epw * SUB_HCAP * sizeof(uint2);
+        const size_t need = (size_t)kp.blob_bytes + (size_t)wpc * WARP_STREAM_BYTES;
+        ctx->warp_off_ring = kp.blob_bytes;
+        ctx->warp_stride_ring = WARP_STREAM_BYTES;
+        if (need <= smem_budget) {
+            bool fit = opt_in((const void *)k_step_policy<640, 6, 5, POLICY_FIRST_FIT, 2>, need);
+            fit &= opt_in((const void *)k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 2>, need);
+            if (fit) ctx->ring_smem = need;
+            else (void)cudaGetLastError();
+        }
     }
     CK(cudaFuncSetAttribute(k_step_action, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     CK(cudaFuncSetAttribute(k_probe_gsnr, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
@@ -432,35 +408,6 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     if ((rc = dev_upload(ctx, &kp.path_links, t->path_links, n_paths * t->max_hops))) return rc;
     if ((rc = dev_upload(ctx, &kp.path_gn, pgn.data(), n_paths))) return rc;
     {
-        // 64-byte path records for k_step_sub: one line holds everything a path needs
-        std::vector<uint32_t> prec(n_paths * 16, 0u);
-        for (size_t pi_ = 0; pi_ < n_paths; pi_++) {
-            uint8_t *b = reinterpret_cast<uint8_t *>(&prec[pi_ * 16]);
-            for (int h = 0; h < t->path_hops[pi_]; h++) b[h] = t->path_links[pi_ * t->max_hops + h];
-            memcpy(&prec[pi_ * 16 + 8], &pgn[pi_].x, 8);
-            memcpy(&prec[pi_ * 16 + 10], &pgn[pi_].y, 8);
-            prec[pi_ * 16 + 12] = hops_dev[pi_];
-            // per bit rate r < 6: bit m = modulation m is refused on the empty-network bound for EVERY start slot,
-            // bit 8+m = for none (the bound is monotone in the centre frequency; the slack covers FMA contraction)
-            const bool prun = (hops_dev[pi_] & 0x80) != 0;
-            for (int r = 0; r < R && r < 6 && t->path_hops[pi_] > 0; r++) {
-                uint32_t mask = 0;
-                for (int m = 0; m < M; m++) {
-                    const int n = ctx->need[(size_t)r * M + m], c = ctx->cls[(size_t)r * M + m];
-                    if (n > S) continue;
-                    auto empty = [&](int s_) {
-                        const double fc = kp.f0 + (kp.sb * (double)s_) + (kp.sb * ((double)n / 2.0));
-                        return ASEC[c] * fc * pgn[pi_].x + CN[c] * (SELF[c] * pgn[pi_].y);
-                    };
-                    if (!prun || empty(S - n) < ACCHI[m] * (1.0 - 1e-12)) mask |= 1u << (8 + m);
-                    else if (empty(0) >= ACCHI[m] * (1.0 + 1e-12)) mask |= 1u << m;
-                }
-                prec[pi_ * 16 + 13 + (r >> 1)] |= mask << ((r & 1) * 16);
-            }
-        }
-        const uint32_t *d = nullptr;
-        if ((rc = dev_upload(ctx, &d, prec.data(), prec.size()))) return rc;
-        kp.prec = reinterpret_cast<const uint4 *>(d);
         if ((rc = dev_alloc(ctx, &kp.work, 4))) return rc;
         if ((rc = dev_alloc(ctx, &kp.counted, (size_t)n_envs))) return rc;
     }
@@ -468,7 +415,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     kp.bm_stride = (size_t)E * kp.RW;
     if ((rc = dev_alloc(ctx, &kp.bm, (size_t)n_envs * kp.bm_stride))) return rc;
     if ((rc = dev_alloc(ctx, &kp.lists, (size_t)n_envs * E * kp.CAP))) return rc;
-    kp.pos_bytes = kp.RW == 16 ? 1 : 2;   // k_step_sub<4>: u8, k_step_sub<8>: u16
+    kp.pos_bytes = kp.CAP <= 256 ? 1 : 2;   // list positions fit a byte up to 511 slots
     kp.pos_stride = (size_t)E * kp.CAP * kp.pos_bytes;
     if ((rc = dev_alloc(ctx, &kp.pos, (size_t)n_envs * kp.pos_stride))) return rc;
     if ((rc = dev_alloc(ctx, &kp.trace, (size_t)n_envs * kp.T))) return rc;
@@ -504,11 +451,13 @@ extern "C" int qrmsa_set_groups(qrmsa_ctx *ctx, int n_groups) {
     int rc = dev_alloc(ctx, &c, (size_t)QRMSA_N_COUNTERS * n_groups);
     if (rc) return rc;
     CK(cudaMemset(c, 0, sizeof(unsigned long long) * QRMSA_N_COUNTERS * n_groups));
+    int64_t *h = nullptr;   // the new pinned buffer first: a failed allocation leaves the context as it was
+    CK(cudaMallocHost((void **)&h, sizeof(int64_t) * QRMSA_N_COUNTERS * n_groups));
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    ctx->h_counters = h;
     ctx->kp.counters = c;
     ctx->n_groups = n_groups;
     ctx->kp.group_size = ctx->kp.n_envs / n_groups;
-    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-    CK(cudaMallocHost((void **)&ctx->h_counters, sizeof(int64_t) * QRMSA_N_COUNTERS * n_groups));
     return QRMSA_OK;
 }
 
@@ -602,8 +551,7 @@ static int build_schedule(qrmsa_ctx *ctx, int n_requests, cudaStream_t st) {
     int n_pad = 2;
     while (n_pad < n_requests) n_pad <<= 1;
     // barrier-heavy (one per compare-exchange stage): several small CTAs per SM overlap each other's waits
-    int cap = 256;
-    if (const char *e = getenv("QRMSA_SORT_THREADS")) cap = atoi(e) >= 32 ? atoi(e) : cap;
+    const int cap = 256;
     int threads = n_pad / 2 < cap ? (n_pad / 2 < 32 ? 32 : n_pad / 2) : cap;
     int blocks = kp.n_envs < ctx->sm_count * 16 ? kp.n_envs : ctx->sm_count * 16;
     k_build_schedule<<<blocks, threads, (size_t)n_pad * 8, st>>>(kp, n_requests, n_pad);
@@ -681,24 +629,18 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
     if (ctx->kp.n_req < 2) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
     if (n_steps == 0) return QRMSA_OK;
     CK(cudaSetDevice(ctx->device));
-    const KParams &kp = ctx->kp;
     cudaStream_t st = (cudaStream_t)stream;
-    const int g = ctx->grid, th = ctx->threads, sm = kp.blob_bytes;
-    const size_t bsm = ctx->bm_smem;   // != 0: the kernel variant with the bitmap rows staged in shared memory
-    const size_t rsm = ctx->ring_smem; // != 0: the variant with the stream chunks only
+    const int g = ctx->grid, th = ctx->threads, sm = ctx->kp.blob_bytes;
+    // what the kernel keeps in shared memory beside the tables: rows + stream chunks + paths when they fit, else the
+    // stream chunks, else nothing (qrmsa_set_staging lowers the level for the equivalence tests)
+    const size_t bsm = ctx->staging >= 2 ? ctx->bm_smem : 0;
+    const size_t rsm = (!bsm && ctx->staging >= 1) ? ctx->ring_smem : 0;
+    KParams kp = ctx->kp;
+    kp.smem_warp_off = bsm ? ctx->warp_off_bms : ctx->warp_off_ring;
+    kp.smem_warp_stride = bsm ? ctx->warp_stride_bms : ctx->warp_stride_ring;
     // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
     const bool c320 = kp.S == 320 && kp.M == 6 && kp.K == 5, c640 = kp.S == 640 && kp.M == 6 && kp.K == 5;
-    if (policy == QRMSA_POLICY_FIRST_FIT && !ctx->use_warp_kernel) {
-        CK(cudaMemsetAsync(kp.work, 0, 4, st));
-        const int sg = ctx->sub_grid, sth = ctx->sub_threads;
-        const size_t ssm = ctx->sub_smem;
-        if (c320) k_step_sub<4, 320, 6, 5><<<sg, sth, ssm, st>>>(kp, n_steps);
-        else if (c640) k_step_sub<8, 640, 6, 5><<<sg, sth, ssm, st>>>(kp, n_steps);
-        else if (kp.RW == 16) k_step_sub<4, 0, 0, 0><<<sg, sth, ssm, st>>>(kp, n_steps);
-        else k_step_sub<8, 0, 0, 0><<<sg, sth, ssm, st>>>(kp, n_steps);
-        CK(cudaGetLastError());
-        k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
-    } else if (policy == QRMSA_POLICY_FIRST_FIT) {
+    if (policy == QRMSA_POLICY_FIRST_FIT) {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
         if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_FIRST_FIT, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
@@ -723,11 +665,15 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         else if (bsm) k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LOAD_BALANCING><<<g, th, sm, st>>>(kp, n_steps);
     }
-    if (policy != QRMSA_POLICY_FIRST_FIT || ctx->use_warp_kernel) {
-        CK(cudaGetLastError());
-        k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
-    }
     CK(cudaGetLastError());
+    k_count_decisions<<<ctx->sm_count * 8, 256, 0, st>>>(kp);
+    CK(cudaGetLastError());
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_set_staging(qrmsa_ctx *ctx, int level) {
+    if (!ctx || level < 0 || level > 2) return QRMSA_ERR_ARG;
+    ctx->staging = level;
     return QRMSA_OK;
 }
 
@@ -780,6 +726,7 @@ extern "C" int qrmsa_get_actions(qrmsa_ctx *ctx, int first, int count, int32_t *
 extern "C" int qrmsa_get_actions_host(qrmsa_ctx *ctx, int first, int count, int32_t *h_out, void *stream) {
     if (!ctx || !h_out || first < 0 || count < 0 || first + count > ctx->kp.n_req) return QRMSA_ERR_ARG;
     if (count == 0) return QRMSA_OK;
+    CK(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)count * ctx->kp.n_envs * 4;
     int rc = ensure_stage(ctx, bytes);
     if (rc) return rc;
@@ -795,6 +742,7 @@ extern "C" int qrmsa_get_actions_host_strided(qrmsa_ctx *ctx, int first, int cou
     if (!ctx || !h_out || first < 0 || count < 0 || first + count > ctx->kp.n_req || row_stride < ctx->kp.n_envs)
         return QRMSA_ERR_ARG;
     if (count == 0) return QRMSA_OK;
+    CK(cudaSetDevice(ctx->device));
     const size_t ne = (size_t)ctx->kp.n_envs;
     int rc = ensure_stage(ctx, std::max((size_t)count * ne * 4, (size_t)ctx->kp.T * ne * 11 + 4096));
     if (rc) return rc;
@@ -802,6 +750,16 @@ extern "C" int qrmsa_get_actions_host_strided(qrmsa_ctx *ctx, int first, int cou
     if (rc) return rc;
     CK(cudaMemcpy2DAsync(h_out, (size_t)row_stride * 4, ctx->stage, ne * 4, ne * 4, count, cudaMemcpyDeviceToHost,
                          (cudaStream_t)stream));
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_get_env_log_host(qrmsa_ctx *ctx, int env, int first, int count, uint32_t *h_records4) {
+    if (!ctx || !h_records4 || env < 0 || env >= ctx->kp.n_envs || first < 0 || count < 0 || first + count > ctx->kp.n_req)
+        return QRMSA_ERR_ARG;
+    if (count == 0) return QRMSA_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h_records4, ctx->kp.trace + (size_t)env * ctx->kp.T + first, (size_t)count * sizeof(uint4), cudaMemcpyDeviceToHost));
     return QRMSA_OK;
 }
 

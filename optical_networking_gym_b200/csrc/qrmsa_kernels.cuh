@@ -74,8 +74,7 @@ struct KParams {
     // BMS step kernel, byte offsets in dynamic shared memory: warp w owns [smem_warp_off + w * smem_warp_stride, ...):
     // 512 bytes of request / schedule chunks, then its env's link rows; the path table starts at smem_pt_off
     int smem_warp_off, smem_warp_stride, smem_pt_off, smem_pt_hops, smem_pt_links;
-    const uint4 *prec;          // [N*N*K][4] path records (64 B): link ids u8[32] | {PA, PB} | hops (bit 7: prunable)
-    int *work;                  // env-group ticket counter of k_step_sub (zeroed before each launch)
+    int *work;                  // env ticket counter of the step kernel (zeroed before each launch)
     uint8_t *pos;               // [n_envs][E][CAP] (u8 if CAP <= 256, else u16): list position of the channel that starts in
                                 // slot pair s>>1 of the link -- lets a release drop its record without searching
     int pos_bytes;              // 1 or 2
@@ -1803,7 +1802,7 @@ __global__ void k_gather_gsnr(const KParams p, const int first, const int count,
 }
 
 // Counters that follow from the decision log (decided / accepted / rejected / bit rates / hops / modulation
-// histogram / near-threshold and blocked-by flags), summed after a k_step_sub launch over the requests each env
+// histogram / near-threshold and blocked-by flags), summed after a step launch over the requests each env
 // decided since the last count; also maintains the env's accepted total (estate.z).  One warp per env at a time,
 // coalesced reads of the 16-byte request records.
 __global__ void k_count_decisions(const KParams p) {
@@ -1814,16 +1813,30 @@ __global__ void k_count_decisions(const KParams p) {
     const int e0 = warp * per, e1 = min(e0 + per, p.n_envs);
     const int *rate_tab = reinterpret_cast<const int *>(p.blob + lay::RATE);
     const int MS = p.M * p.S;
+    // c[3] / c[4] (bit rate x 1000, up to 1e6 per request) stay unused: the two rate sums are kept and reduced in
+    // 64 bits (rate_req / rate_prov) -- a warp covers ceil(n_envs / warps) envs x every step since the last count,
+    // which overflows 32 bits from a few thousand decisions per lane on
     uint32_t c[NL];
+    unsigned long long rate_req = 0ull, rate_prov = 0ull;
     int grp = -1;
     auto flush = [&]() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rate_req += __shfl_xor_sync(FULL, rate_req, o);
+            rate_prov += __shfl_xor_sync(FULL, rate_prov, o);
+        }
+        if (lane == 0 && grp >= 0) {
+            if (rate_req) atomicAdd(p.counters + (size_t)grp * QRMSA_N_COUNTERS + QRMSA_CNT_RATE_REQUESTED, rate_req);
+            if (rate_prov) atomicAdd(p.counters + (size_t)grp * QRMSA_N_COUNTERS + QRMSA_CNT_RATE_PROVISIONED, rate_prov);
+        }
+        rate_req = rate_prov = 0ull;
 #pragma unroll
         for (int k = 0; k < NL; ++k) {
             uint32_t v = c[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
             const int slot = k == 0 ? QRMSA_CNT_DECIDED : k == 1 ? QRMSA_CNT_ACCEPTED : k == 2 ? QRMSA_CNT_REJECTED :
-                             k == 3 ? QRMSA_CNT_RATE_REQUESTED : k == 4 ? QRMSA_CNT_RATE_PROVISIONED :
+                             k == 3 ? -1 : k == 4 ? -1 :
                              k == 5 ? QRMSA_CNT_HOPS_ACCEPTED : k == 6 ? QRMSA_CNT_NEAR_THRESHOLD :
                              k == 7 ? QRMSA_CNT_BLOCKED_RESOURCES : k == 8 ? QRMSA_CNT_BLOCKED_OSNR :
                              k == 9 ? QRMSA_CNT_ERRORS : k == 10 ? -1 : k == 11 ? -1 : QRMSA_CNT_MOD_HIST + (k - 12);
@@ -1849,7 +1862,7 @@ __global__ void k_count_decisions(const KParams p) {
             if (!(rq.w & QRMSA_FLAG_DECIDED)) continue;
             const int rate = rate_tab[(rq.z >> 16) & 0xff];
             c[0] += 1u;
-            c[3] += (uint32_t)rate;
+            rate_req += (unsigned long long)rate;
             if (rq.w & QRMSA_FLAG_NEAR_THRESHOLD) c[6] += 1u;
             if (rq.w & QRMSA_FLAG_ACCEPTED) {
                 const uint32_t a = rq.w & QRMSA_ACTION_MASK;
@@ -1857,8 +1870,8 @@ __global__ void k_count_decisions(const KParams p) {
                 const int path = ((rq.z & 0xff) * p.N + ((rq.z >> 8) & 0xff)) * p.K + pi;
                 c[1] += 1u;
                 acc_here += 1u;
-                c[4] += (uint32_t)rate;
-                c[5] += __ldg(reinterpret_cast<const uint32_t *>(p.prec + (size_t)path * 4) + 12) & 0x7fu;
+                rate_prov += (unsigned long long)rate;
+                c[5] += (uint32_t)(__ldg(p.path_hops + path) & 0x7f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) c[12 + k] += (m == k) ? 1u : 0u;
             } else {

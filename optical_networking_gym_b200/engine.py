@@ -74,13 +74,12 @@ class Engine:
         except Exception:
             pass
 
-    @staticmethod
-    def _stream(stream) -> Optional[int]:
+    def _stream(self, stream) -> Optional[int]:
         if stream is None:
             try:
                 import torch
 
-                return torch.cuda.current_stream().cuda_stream or None
+                return torch.cuda.current_stream(self.device).cuda_stream or None
             except Exception:
                 return None
         return getattr(stream, "cuda_stream", stream) or None
@@ -89,6 +88,10 @@ class Engine:
     def set_groups(self, n_groups: int):
         check(self.lib.qrmsa_set_groups(self._h, int(n_groups)), self._h)
         self.n_groups = int(n_groups)
+
+    def set_staging(self, level: int):
+        """0 / 1 / 2: how much per-env state the step kernel stages in shared memory (include/qrmsa_b200.h)."""
+        check(self.lib.qrmsa_set_staging(self._h, int(level)), self._h)
 
     def enable_gsnr_log(self, enable: bool = True):
         check(self.lib.qrmsa_enable_gsnr_log(self._h, int(enable)), self._h)
@@ -195,6 +198,16 @@ class Engine:
         check(self.lib.qrmsa_get_actions(self._h, first, count, out.data_ptr(), self._stream(stream)), self._h)
         return out
 
+    def env_log(self, env: int, first: int = 0, count: Optional[int] = None):
+        """One env's request stream and decision log: (src, dst, rate, arrival, holding, action words) for requests
+        [first, first+count)."""
+        count = self.n_loaded - first if count is None else int(count)
+        rec = np.zeros((count, 4), np.uint32)
+        check(self.lib.qrmsa_get_env_log_host(self._h, int(env), int(first), count, _np_ptr(rec)), self._h)
+        z = rec[:, 2]
+        return ((z & 0xff).astype(np.uint8), ((z >> 8) & 0xff).astype(np.uint8), ((z >> 16) & 0xff).astype(np.uint8),
+                rec[:, 0].copy().view(np.float32), rec[:, 1].copy().view(np.float32), rec[:, 3].copy())
+
     def gsnr_host(self, first: int, count: int, stream=None) -> np.ndarray:
         out = np.empty((count, self.n_envs), np.float64)
         check(self.lib.qrmsa_get_gsnr_host(self._h, first, count, _np_ptr(out), self._stream(stream)), self._h)
@@ -257,9 +270,9 @@ class Engine:
         import torch
 
         if stream is None:
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream(self.device).synchronize()
         else:
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(self.device)
 
 
 def unpack_bitmaps(words: np.ndarray, n_slots: int) -> np.ndarray:

@@ -30,9 +30,11 @@ def first_divergence(a, b):
 
 
 def compare_decisions(actions, ref_actions, flagged, what=""):
-    """Bit-exact comparison with the north_star rule: a decision whose GSNR lies within 1e-3 dB of a
-    threshold is FLAGGED; divergence at or after a flagged step of that env is reported, not counted.
-    Returns (n_compared, n_excused)."""
+    """Bit-exact comparison with the north_star rule: a decision whose GSNR lies within 1e-3 dB of a threshold is
+    FLAGGED rather than counted as a mismatch.  Up to its first divergent step an env's decisions -- hence its network
+    state -- are identical to the reference's, so a legitimate divergence can only come from a QoT comparison made AT
+    that step: the first divergent step itself must carry the flag (an earlier flag excuses nothing).  What follows a
+    flagged divergence in that env is reported, not counted.  Returns (n_compared, n_excused)."""
     actions = np.asarray(actions); ref_actions = np.asarray(ref_actions); flagged = np.asarray(flagged, bool)
     assert actions.shape == ref_actions.shape
     if actions.ndim == 1:
@@ -43,9 +45,24 @@ def compare_decisions(actions, ref_actions, flagged, what=""):
         if d < 0:
             n_cmp += actions.shape[1]
             continue
-        fl = np.flatnonzero(flagged[e, : d + 1])
-        assert len(fl) > 0, (f"{what} env {e}: decision mismatch at step {d} "
-                             f"(got {actions[e, d]}, reference {ref_actions[e, d]}) with no near-threshold flag before it")
+        assert flagged[e, d], (f"{what} env {e}: decision mismatch at step {d} (got {actions[e, d]}, reference "
+                               f"{ref_actions[e, d]}) and that step carries no near-threshold flag")
         n_cmp += d
         n_exc += 1
+    if n_exc:
+        print(f"{what}: {n_exc} env(s) excused after a flagged near-threshold divergence ({n_cmp} decisions compared)")
     return n_cmp, n_exc
+
+
+def check_flags_against_recording(flagged_steps, g, tol_db=1e-3, what=""):
+    """Both directions of the flag rule against a recording that holds every QoT check of the reference
+    (qot_step / qot_gsnr / qot_thr): every step with a recorded check strictly inside the tolerance is flagged, and
+    every flagged step has a recorded check within the tolerance (1e-9 dB of slack for the two FP64 evaluations)."""
+    delta = np.abs(np.asarray(g["qot_gsnr"]) - np.asarray(g["qot_thr"]))
+    steps = np.asarray(g["qot_step"])
+    must = set(np.unique(steps[delta < tol_db - 1e-9]).tolist())
+    may = set(np.unique(steps[delta < tol_db + 1e-9]).tolist())
+    got = set(int(x) for x in np.flatnonzero(np.asarray(flagged_steps, bool)))
+    assert must <= got, f"{what}: near-threshold checks at steps {sorted(must - got)} were not flagged"
+    assert got <= may, f"{what}: steps {sorted(got - may)} are flagged without a QoT check within {tol_db} dB"
+    return len(got)

@@ -90,7 +90,7 @@ def test_step_parity_on_generated_stream():
         ref = o.run_first_fit(n_req - 1, log_qot=False)
         if not np.array_equal(ref["action"], actions[e]):
             d = int(np.flatnonzero(ref["action"] != actions[e])[0])
-            assert flagged[e, : d + 1].any(), f"env {e}: unflagged decision mismatch at step {d}"
+            assert flagged[e, d], f"env {e}: unflagged decision mismatch at step {d}"
             continue
         assert np.array_equal(o.slots(), slots[e])
     assert eng.counters_dict()["errors"] == 0
@@ -118,7 +118,7 @@ def test_batched_env_with_device_traffic():
         ref = o.run_first_fit(L - 1, log_qot=False)
         if not np.array_equal(ref["action"], actions[e]):
             d = int(np.flatnonzero(ref["action"] != actions[e])[0])
-            assert flagged[e, : d + 1].any()
+            assert flagged[e, d]
     env.reset()
     second = env.current_requests()
     assert (second[3][0] > first[3][-1]).all()        # the clocks run on across episodes (qrmsa.pyx:179, :1081)

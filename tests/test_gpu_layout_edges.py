@@ -33,7 +33,7 @@ def _check(tb, n_envs, n, load, seed, chunks):
         ref = o.run_first_fit(n, log_qot=False)
         if not np.array_equal(ref["action"], actions[e]):
             d = int(np.flatnonzero(ref["action"] != actions[e])[0])
-            assert flagged[e, : d + 1].any(), f"S={tb.n_slots} env {e}: unflagged mismatch at step {d}"
+            assert flagged[e, d], f"S={tb.n_slots} env {e}: unflagged mismatch at step {d}"
             continue
         assert np.array_equal(o.slots(), slots[e]), f"S={tb.n_slots} env {e}: bitmap mismatch"
         for l in range(tb.n_links):
@@ -94,31 +94,36 @@ def test_loud_failures():
     eng.close()
 
 
-@pytest.mark.parametrize("topo,policy", [("nobel-eu", "first_fit"), ("nsfnet", "load_balancing"), ("nobel-eu", "load_balancing_first_fit")])
-def test_shared_memory_staging_matches_global_state(topo, policy, monkeypatch):
-    """The step kernel keeps the link rows and a compact path table in shared memory when they fit (BMS variant,
-    qrmsa_create); QRMSA_BM_SMEM=0 selects the variant that reads everything through L1.  Same action words, bitmaps,
-    channel lists, env state and counters, across launch boundaries (rows are written back after every launch)."""
+@pytest.mark.parametrize("topo,S,policy,load", [("nobel-eu", 320, "first_fit", 300.0), ("nsfnet", 320, "load_balancing", 250.0),
+                                               ("nobel-eu", 320, "load_balancing_first_fit", 300.0),
+                                               ("germany50", 640, "first_fit", 800.0)])
+def test_shared_memory_staging_matches_global_state(topo, S, policy, load):
+    """The step kernel keeps the link rows, the request / schedule stream chunks and a compact path table in shared
+    memory when they fit (qrmsa_create; level 2), only the stream chunks when the rows do not fit (germany50/640: the
+    tables alone take 183 KB; level 1), and qrmsa_set_staging(0) reads everything through L1.  Same action words,
+    bitmaps, channel lists, env state and counters at every level, across launch boundaries (rows are written back
+    after every launch)."""
     from optical_networking_gym_b200 import _lib
     from optical_networking_gym_b200.engine import Engine
     from optical_networking_gym_b200.tracegen import TraceGenerator
 
-    tb = load_tables(topo, 320)
+    tb = load_tables(topo, S)
     n_envs, n = 70, 400
-    tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, 300.0 if topo == "nobel-eu" else 250.0, base_seed=99).next(n + 1)
+    tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, load, base_seed=99).next(n + 1)
     out = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("QRMSA_BM_SMEM", mode)   # read by qrmsa_create
+    for level in (2, 1, 0):
         eng = Engine(tb, n_envs, n + 1)
+        eng.set_staging(level)
         eng.reset(); eng.load_trace_host(*tr)
         for c in (1, 7, 200, n - 208):
             eng.step_heuristic(_lib.POLICIES[policy], c)
         lists = [sorted(map(tuple, eng.export_link_list(e, l))) for e in (0, n_envs - 1) for l in range(tb.n_links)]
-        out[mode] = (eng.actions_host(0, n).copy(), eng.export_bitmaps(0, n_envs).copy(), eng.env_state().copy(),
-                     eng.counters().copy(), lists)
+        out[level] = (eng.actions_host(0, n).copy(), eng.export_bitmaps(0, n_envs).copy(), eng.env_state().copy(),
+                      eng.counters().copy(), lists)
         c = eng.counters_dict()
         assert c["decided"] == n_envs * n and c["errors"] == 0
         eng.close()
-    for i, what in enumerate(("action words", "bitmaps", "env state", "counters")):
-        assert np.array_equal(out["1"][i], out["0"][i]), what + " differ"
-    assert out["1"][4] == out["0"][4], "channel lists differ"
+    for level in (1, 0):
+        for i, what in enumerate(("action words", "bitmaps", "env state", "counters")):
+            assert np.array_equal(out[2][i], out[level][i]), f"{what} differ between staging levels 2 and {level}"
+        assert out[2][4] == out[level][4], "channel lists differ"

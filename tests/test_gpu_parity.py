@@ -7,7 +7,7 @@ Bar: bit-exact path / modulation / initial-slot / accept decisions and slot bitm
 import numpy as np
 import pytest
 
-from helpers import TRACE_KEYS, compare_decisions, load_golden, load_tables, parse_tag
+from helpers import TRACE_KEYS, check_flags_against_recording, compare_decisions, load_golden, load_tables, parse_tag
 
 pytestmark = pytest.mark.gpu
 
@@ -59,23 +59,21 @@ def test_single_env_vs_reference(tag):
     chunks = [1, 2, 37] + [n_steps - 40]
     actions, flagged, accepted, gsnr = _run(eng, g, False, chunks)
     n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
-    if n_exc == 0:
-        assert np.array_equal(accepted[0], g["accepted"].astype(bool))
-        assert np.abs(gsnr[0] - g["gsnr"]).max() < GSNR_TOL_DB
-        slots = unpack_bitmaps(eng.export_bitmaps(0, 1), S)[0]
-        assert np.array_equal(slots, g["final_slots"])
-        st = eng.env_state()[0]
-        assert st[0] == n_steps and st[1] == int(g["accepted"].sum()) and st[3] == 0
-        c = eng.counters_dict()
-        assert c["decided"] == n_steps and c["accepted"] == int(g["accepted"].sum())
-        # every QoT check of the reference is either evaluated or refused on the empty-network bound
-        assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"])
-        assert c["errors"] == 0
-    # every near-threshold QoT check of the reference must have raised our flag on that step
-    near = np.abs(g["qot_gsnr"] - g["qot_thr"]) < GSNR_TOL_DB * 0.5
-    for s in np.unique(g["qot_step"][near]):
-        if s < n_cmp:
-            assert flagged[0, s]
+    # the fixtures are fixed files: no env of them diverges, so nothing below is conditional
+    assert n_exc == 0 and n_cmp == n_steps
+    assert np.array_equal(accepted[0], g["accepted"].astype(bool))
+    assert np.abs(gsnr[0] - g["gsnr"]).max() < GSNR_TOL_DB
+    slots = unpack_bitmaps(eng.export_bitmaps(0, 1), S)[0]
+    assert np.array_equal(slots, g["final_slots"])
+    st = eng.env_state()[0]
+    assert st[0] == n_steps and st[1] == int(g["accepted"].sum()) and st[3] == 0
+    c = eng.counters_dict()
+    assert c["decided"] == n_steps and c["accepted"] == int(g["accepted"].sum())
+    # every QoT check of the reference is either evaluated or refused on the empty-network bound
+    assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"])
+    assert c["errors"] == 0
+    # flags, both ways: a recorded check within 1e-3 dB of its threshold <=> our flag on that step
+    assert check_flags_against_recording(flagged[0], g, GSNR_TOL_DB, tag) == c["near_threshold"]
     eng.close()
 
 
@@ -90,14 +88,20 @@ def test_batched_envs_vs_reference(tag):
     eng = _engine(tb, n_envs, n_steps + 1)
     actions, flagged, accepted, gsnr = _run(eng, g, True, [n_steps])
     n_cmp, n_exc = compare_decisions(actions, g["action"], flagged, tag)
-    assert n_exc <= max(1, n_envs // 8)
-    clean = [e for e in range(n_envs) if np.array_equal(actions[e], g["action"][e])]
-    assert len(clean) >= n_envs - n_exc
+    assert n_exc == 0 and n_cmp == n_envs * n_steps          # fixed fixtures: every env agrees to the last step
+    assert np.array_equal(accepted, g["accepted"].astype(bool))
     slots = unpack_bitmaps(eng.export_bitmaps(0, n_envs), S)
     ref_slots = np.unpackbits(g["final_slots"], axis=2)[:, :, :S]
-    for e in clean:
+    off = np.concatenate([[0], np.cumsum(g["qot_count"])])
+    n_flags = 0
+    for e in range(n_envs):
         assert np.array_equal(slots[e], ref_slots[e]), f"env {e}: slot bitmap differs"
         assert np.abs(gsnr[e] - g["gsnr"][e]).max() < GSNR_TOL_DB
+        ge = {k: g[k][off[e]:off[e + 1]] for k in ("qot_step", "qot_gsnr", "qot_thr")}
+        n_flags += check_flags_against_recording(flagged[e], ge, GSNR_TOL_DB, f"{tag} env {e}")
+    c = eng.counters_dict()
+    assert c["near_threshold"] == n_flags and c["errors"] == 0
+    assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"])
     eng.close()
 
 
@@ -138,48 +142,13 @@ def test_load_balancing_policy_vs_reference(tag):
     actions = (words & _lib.ACTION_MASK).astype(np.int64).T
     flagged = ((words.view(np.uint32) & _lib.FLAG_NEAR_THRESHOLD) != 0).T
     n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
-    if n_exc == 0:
-        assert np.abs(eng.gsnr_host(0, n).T[0] - g["gsnr"]).max() < GSNR_TOL_DB
-        assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
-        c = eng.counters_dict()
-        assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
+    assert n_exc == 0 and n_cmp == n
+    assert np.abs(eng.gsnr_host(0, n).T[0] - g["gsnr"]).max() < GSNR_TOL_DB
+    assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
+    c = eng.counters_dict()
+    assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
+    assert check_flags_against_recording(flagged[0], g, GSNR_TOL_DB, tag) == c["near_threshold"]
     eng.close()
-
-
-@pytest.mark.parametrize("tag", ["multi_nobel-eu_320_l300_b50", "multi_germany50_640_l800_b50"])
-def test_lanes_per_env_experiment_matches_product_kernel(tag, monkeypatch):
-    """k_step_sub (QRMSA_STEP_IMPL=sub, csrc/qrmsa_step_sub.cuh) must reproduce the product kernel word for word:
-    action words including every flag, bitmaps, channel lists, env state and counters."""
-    from optical_networking_gym_b200.engine import Engine
-
-    topo, S = parse_tag(tag)
-    tb = load_tables(topo, S)
-    g = load_golden(tag)
-    tr = [np.ascontiguousarray(g[k].T) for k in TRACE_KEYS]
-    n_req, n_envs = tr[0].shape
-    out = {}
-    for impl in ("warp", "sub"):
-        monkeypatch.setenv("QRMSA_STEP_IMPL", impl)   # read by qrmsa_create
-        eng = Engine(tb, n_envs, n_req)
-        eng.reset()
-        eng.load_trace_host(*tr)
-        for c in (3, 50, n_req - 1 - 53):
-            eng.step_first_fit(c)
-        lists = [eng.export_link_list(e, l) for e in (0, n_envs - 1) for l in range(tb.n_links)]
-        out[impl] = (eng.actions_host(0, n_req - 1).copy(), eng.export_bitmaps(0, n_envs).copy(), eng.env_state().copy(),
-                     eng.counters().copy(), [sorted(map(tuple, x)) for x in lists])
-        eng.close()
-    a, b = out["warp"], out["sub"]
-    assert np.array_equal(a[0], b[0]), "action words differ"
-    assert np.array_equal(a[1], b[1]), "bitmaps differ"
-    assert np.array_equal(a[2], b[2]), "env state differs"
-    ca, cb = a[3].copy(), b[3].copy()
-    # the product kernel walks the lists once per slot count and reuses the sum for modulations that need the same
-    # number of slots; the experiment walks them once per QoT check.  Same checks, fewer terms summed.
-    assert (ca[:, 8] <= cb[:, 8]).all()
-    ca[:, 8] = cb[:, 8] = 0
-    assert np.array_equal(ca, cb), "counters differ"
-    assert a[4] == b[4], "channel lists differ"
 
 
 def test_blocked_by_flags_and_log_counters():
@@ -246,12 +215,12 @@ def test_highest_snr_policy_vs_reference(tag):
     n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
     # the tie flag must not be raised for the same channel met under several modulations (exact, deterministic ties)
     assert int(((w & _lib.FLAG_NEAR_TIE) != 0).sum()) <= int((g["best_gap_db"] < 2e-6).sum())
-    if n_exc == 0:
-        assert np.abs(eng.gsnr_host(0, n).T[0] - g["gsnr"]).max() < GSNR_TOL_DB
-        assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
-        c = eng.counters_dict()
-        assert c["gn_evals"] == int(g["n_checks"].sum())         # every QoT check of the reference, none skipped
-        assert c["decided"] == n and c["accepted"] == int(g["accepted"].sum()) and c["errors"] == 0
+    assert n_exc == 0 and n_cmp == n
+    assert np.abs(eng.gsnr_host(0, n).T[0] - g["gsnr"]).max() < GSNR_TOL_DB
+    assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
+    c = eng.counters_dict()
+    assert c["gn_evals"] == int(g["n_checks"].sum())         # every QoT check of the reference, none skipped
+    assert c["decided"] == n and c["accepted"] == int(g["accepted"].sum()) and c["errors"] == 0
     eng.close()
 
 
@@ -302,13 +271,14 @@ def test_lb_first_fit_policy_vs_reference(tag):
     actions = (words & _lib.ACTION_MASK).astype(np.int64).T
     flagged = ((w & _lib.FLAG_NEAR_THRESHOLD) != 0).T
     n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
-    if n_exc == 0:
-        assert np.abs(eng.gsnr_host(0, n).T[0] - g["gsnr"]).max() < GSNR_TOL_DB
-        assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
-        c = eng.counters_dict()
-        assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
-        rej = (w & _lib.FLAG_ACCEPTED) == 0                    # a reject always reports (True, False), heuristics.py:270
-        assert ((w[rej] & _lib.FLAG_BLOCKED_RESOURCES) != 0).all() and ((w[rej] & _lib.FLAG_BLOCKED_OSNR) == 0).all()
+    assert n_exc == 0 and n_cmp == n
+    assert np.abs(eng.gsnr_host(0, n).T[0] - g["gsnr"]).max() < GSNR_TOL_DB
+    assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
+    c = eng.counters_dict()
+    assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
+    assert check_flags_against_recording(flagged[0], g, GSNR_TOL_DB, tag) == c["near_threshold"]
+    rej = (w & _lib.FLAG_ACCEPTED) == 0                    # a reject always reports (True, False), heuristics.py:270
+    assert ((w[rej] & _lib.FLAG_BLOCKED_RESOURCES) != 0).all() and ((w[rej] & _lib.FLAG_BLOCKED_OSNR) == 0).all()
     eng.close()
 
 
@@ -328,14 +298,11 @@ def test_configuration_variants_vs_reference(tag):
     eng = _engine(tb, 1, n + 1)
     actions, flagged, accepted, gsnr = _run(eng, g, False, [7, 900, n - 907])
     n_cmp, n_exc = compare_decisions(actions, g["action"][None], flagged, tag)
-    if n_exc == 0:
-        assert np.array_equal(accepted[0], g["accepted"].astype(bool))
-        assert np.abs(gsnr[0] - g["gsnr"]).max() < GSNR_TOL_DB
-        assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), tb.n_slots)[0], g["final_slots"])
-        c = eng.counters_dict()
-        assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
-    near = np.abs(g["qot_gsnr"] - g["qot_thr"]) < GSNR_TOL_DB * 0.5
-    for s in np.unique(g["qot_step"][near]):
-        if s < n_cmp:
-            assert flagged[0, s]
+    assert n_exc == 0 and n_cmp == n
+    assert np.array_equal(accepted[0], g["accepted"].astype(bool))
+    assert np.abs(gsnr[0] - g["gsnr"]).max() < GSNR_TOL_DB
+    assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), tb.n_slots)[0], g["final_slots"])
+    c = eng.counters_dict()
+    assert c["gn_evals"] + c["gn_pruned"] == len(g["qot_gsnr"]) and c["errors"] == 0
+    assert check_flags_against_recording(flagged[0], g, GSNR_TOL_DB, tag) == c["near_threshold"]
     eng.close()
