@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """BASELINE config 5: rollout with on-device action masks and a PyTorch policy consuming them.
 
-    python examples/ppo_rollout.py [--envs 16384] [--steps 64] [--topology nsfnet]
+    python examples/ppo_rollout.py [--envs 16384] [--steps 1024] [--topology nsfnet]
+    torchrun --nproc-per-node N examples/ppo_rollout.py ...        # --envs per GPU, one policy replica per rank
 
 Mirrors the consumer of reference examples/ONDM_2025/train_multi_masked_ppo.py (MaskablePPO over
 SubprocVecEnv of 14 envs, policy pi=[512,256,128], :410-444): observation float32[368] and mask uint8[9601]
 stay in HBM, the MLP 368->512->256->128->9601 samples a masked categorical action, `BatchedQRMSAEnv.step`
-applies it.  Policy weights are random (no training here): this measures the environment side of the loop.
+applies it, and the rollout buffer (actions, rewards, statuses) is filled on the device.  Policy weights are random
+(no training here): this measures the environment side of the loop with the policy in it.  Across ranks the only
+traffic is the all-reduce of the counters at the end of the rollout.
 """
 import argparse
 import os
@@ -14,49 +17,91 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def make_policy(obs_dim: int, n_actions: int, device, seed: int = 0):
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    layers, dims = [], [obs_dim, 512, 256, 128, n_actions]       # train_multi_masked_ppo.py:440-441
+    for i in range(4):
+        lin = torch.nn.Linear(dims[i], dims[i + 1])
+        with torch.no_grad():
+            lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) / dims[i] ** 0.5)
+            lin.bias.zero_()
+        layers += [lin] + ([torch.nn.Tanh()] if i < 3 else [])
+    return torch.nn.Sequential(*layers).to(device).bfloat16()
+
+
+def rollout(env, policy, n_steps: int, buffers: dict = None, host_reward=None):
+    """n_steps of obs -> policy -> masked categorical sample -> env.step for every env of `env` (a BatchedQRMSAEnv with
+    gen_observation=True, already reset).  `buffers` (optional) receives the rollout buffer rows on the device:
+    "action" int64 [n_steps, n_envs], "status" uint8, "reward" float32.  `host_reward` (optional, pinned float32
+    [n_steps, n_envs]) gets every step's rewards by an asynchronous device->host copy (the end-to-end leg)."""
+    import torch
+
+    obs, mask = env._obs, env.action_masks()
+    total_reward = torch.zeros((), device=obs.device, dtype=torch.float64)
+    with torch.no_grad():
+        for t in range(n_steps):
+            logits = policy(obs.bfloat16()).float()
+            logits.masked_fill_(mask == 0, float("-inf"))
+            # masked categorical sample by the Gumbel-max trick: argmax(logits - log E), E ~ Exp(1); no normalisation pass
+            action = (logits - torch.empty_like(logits).exponential_().log_()).argmax(dim=1)
+            obs, reward, term, trunc, info = env.step(action)
+            mask = info["mask"]
+            if buffers is not None:
+                buffers["action"][t].copy_(action)
+                buffers["status"][t].copy_(info["status"])
+                buffers["reward"][t].copy_(reward)
+            if host_reward is not None:
+                host_reward[t].copy_(reward, non_blocking=True)
+            total_reward += reward.sum()
+    return total_reward
 
 
 def main():
     import torch
+    import torch.distributed as dist
 
+    from optical_networking_gym_b200 import sharding
     from optical_networking_gym_b200.env import BatchedQRMSAEnv
     from optical_networking_gym_b200.tables import StaticTables
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("--envs", type=int, default=16384)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--envs", type=int, default=16384, help="envs per GPU")
+    ap.add_argument("--steps", type=int, default=1024)
     ap.add_argument("--topology", default="nsfnet")
     ap.add_argument("--load", type=float, default=210.0)   # train_multi_masked_ppo.py:381
     args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tb = StaticTables.load(os.path.join(ROOT, "tests", "golden", f"tables_{args.topology}_320.npz"))
     env = BatchedQRMSAEnv(tb, args.envs, num_spectrum_resources=320, episode_length=args.steps + 1, load=args.load,
-                          bit_rates=(10, 40, 100, 400, 1000), launch_power_dbm=1.0, gen_observation=True, seed=10)
-    obs_dim, n_act = env.observation_space.shape[0], env.action_space.n
-    dev = torch.device("cuda")
-    policy = torch.nn.Sequential(torch.nn.Linear(obs_dim, 512), torch.nn.Tanh(), torch.nn.Linear(512, 256), torch.nn.Tanh(),
-                                 torch.nn.Linear(256, 128), torch.nn.Tanh(), torch.nn.Linear(128, n_act)).to(dev).bfloat16()
-    obs, info = env.reset()
+                          bit_rates=(10, 40, 100, 400, 1000), launch_power_dbm=1.0, gen_observation=True,
+                          seed=10 + rank * args.envs, device=local)
+    dev = torch.device("cuda", local)
+    policy = make_policy(env.observation_space.shape[0], env.action_space.n, dev, seed=rank)
+    env.reset()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    t_env = 0.0
-    total_reward = torch.zeros((), device=dev)
-    with torch.no_grad():
-        for _ in range(args.steps):
-            logits = policy(obs.bfloat16()).float()
-            logits.masked_fill_(info["mask"] == 0, float("-inf"))
-            # masked categorical sample by the Gumbel-max trick: argmax(logits - log E), E ~ Exp(1); no normalisation pass
-            action = (logits - torch.empty_like(logits).exponential_().log_()).argmax(dim=1)
-            torch.cuda.synchronize(); t1 = time.perf_counter()
-            obs, reward, term, trunc, info = env.step(action)
-            torch.cuda.synchronize(); t_env += time.perf_counter() - t1
-            total_reward += reward.sum()
+    total_reward = rollout(env, policy, args.steps)
+    counters = sharding.allreduce_counters(env.engine.counters())
+    torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    c = env.counters()
-    print(f"{args.envs} envs x {args.steps} steps on {args.topology}: {args.envs * args.steps / dt:,.0f} env-steps/s "
-          f"(env side {args.envs * args.steps / t_env:,.0f}/s), accepted {c['accepted']}/{c['decided']}, "
-          f"status errors {c['errors']}, mean reward {float(total_reward) / (args.envs * args.steps):.4f}")
+    if rank == 0:
+        c = counters.sum(0)
+        print(f"{world} GPU(s) x {args.envs} envs x {args.steps} steps on {args.topology}: "
+              f"{world * args.envs * args.steps / dt:,.0f} env-steps/s, accepted {int(c[1])}/{int(c[0])}, "
+              f"status errors {int(c[15])}, mean reward on rank 0 {float(total_reward) / (args.envs * args.steps):.4f}")
     env.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -232,6 +232,19 @@ class Engine:
         d["gn_pruned"] = int(row[24])
         return d
 
+    def counters_tensor(self):
+        """Zero-copy torch view (int64 CUDA [n_groups, N_COUNTERS]) of the device counters -- what the episode-end
+        NCCL all-reduce takes (clone it first; the kernels keep adding into this memory)."""
+        import torch
+
+        class _View:
+            pass
+
+        v = _View()
+        v.__cuda_array_interface__ = {"data": (self.counters_device_ptr(), False), "shape": (self.n_groups, _lib.N_COUNTERS),
+                                      "typestr": "<i8", "version": 2}
+        return torch.as_tensor(v, device=torch.device("cuda", self.device))
+
     def counters_device_ptr(self) -> int:
         p = C.c_void_p()
         check(self.lib.qrmsa_counters_device(self._h, C.byref(p)), self._h)

@@ -32,13 +32,16 @@ class PipelinedEpisodes:
         with torch.cuda.device(device):
             self.streams = [torch.cuda.Stream() for _ in range(self.slices)]
 
-    def run(self, trace: Sequence, out_actions, n_requests: int = None, launch_steps: int = 512) -> np.ndarray:
+    def run(self, trace: Sequence, out_actions=None, n_requests: int = None, launch_steps: int = 512,
+            per_slice: bool = False) -> np.ndarray:
         """trace: five PINNED torch tensors [n_requests, n_envs] (uint8 x3, float32 x2); out_actions: pinned int32
-        [n_requests-1, n_envs].  Everything is enqueued asynchronously; returns the summed counters after a sync."""
+        [n_requests-1, n_envs], or None when only the counters are wanted (load sweeps).  Everything is enqueued
+        asynchronously; returns the counters after a sync -- summed over the slices, or one matrix per slice
+        (`per_slice=True`: [slices][n_groups][N_COUNTERS], for per-load-point sums)."""
         import torch
 
         n_req = int(trace[0].shape[0] if n_requests is None else n_requests)
-        assert all(t.is_pinned() for t in trace) and out_actions.is_pinned()
+        assert all(t.is_pinned() for t in trace) and (out_actions is None or out_actions.is_pinned())
         esz = [t.element_size() for t in trace]
         cur = torch.cuda.current_stream(self.device)
         for (a, b), eng, st in zip(self.ranges, self.engines, self.streams):
@@ -50,15 +53,13 @@ class PipelinedEpisodes:
                 n = min(launch_steps, n_req - 1 - done)
                 eng.step_first_fit(n, stream=st)
                 done += n
-            eng.actions_host_strided(0, n_req - 1, out_actions.data_ptr() + a * 4, self.n_envs, stream=st)
+            if out_actions is not None:
+                eng.actions_host_strided(0, n_req - 1, out_actions.data_ptr() + a * 4, self.n_envs, stream=st)
         for st in self.streams:
             cur.wait_stream(st)
-        total = None
-        for eng, st in zip(self.engines, self.streams):
-            c = eng.counters(stream=st)
-            total = c if total is None else total + c
+        each = [eng.counters(stream=st) for eng, st in zip(self.engines, self.streams)]
         torch.cuda.synchronize(self.device)
-        return total
+        return np.stack(each) if per_slice else sum(each[1:], each[0])
 
     def close(self):
         for e in self.engines:

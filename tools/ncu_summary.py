@@ -36,6 +36,17 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio']
 
 
+def kernel_source_hash():
+    """sha256 over the CUDA sources of the library (same function as bench.py's): bench.py only claims these numbers
+    for a library built from the very sources that were profiled.  Run this tool BEFORE editing the kernels again."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in ("qrmsa_kernels.cuh", "qrmsa_b200.cu"):
+        h.update(open(os.path.join(ROOT, "optical_networking_gym_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
 def ncu(args):
     return subprocess.run(["ncu"] + args, capture_output=True, text=True).stdout
 
@@ -68,23 +79,34 @@ def main():
     inst = num("smsp__inst_executed.sum")
     traffic = {"kernel": m.get("Kernel Name", ("", ""))[0], "dram_bytes_per_launch": dram,
                "duration_s_under_ncu": dur, "warp_instructions_per_launch": inst, "source": os.path.basename(rep),
-               "tag": tag}
+               "tag": tag, "kernel_source_sha256": kernel_source_hash()}
     if env_steps:
         traffic.update(env_steps_per_launch=env_steps, dram_bytes_per_env_step=dram / env_steps,
                        warp_instructions_per_env_step=inst / env_steps)
-    json.dump(traffic, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
 
+    # ---- exact totals from the SASS-only page (every instruction once): opcode mix, lane utilisation
+    sass = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "sass"]))))
+    sh = next(r for r in sass if len(r) > 5 and r[0] == "Address")
+    iI, iT, iP = sh.index("Instructions Executed"), sh.index("Thread Instructions Executed"), sh.index("Predicated-On Thread Instructions Executed")
+    ops, per_addr, tot, thr, pon = collections.Counter(), {}, 0, 0, 0
+    for r in sass:
+        if len(r) <= iP or not r[0].startswith("0x"):
+            continue
+        n = int(r[iI]); tot += n; thr += int(r[iT]); pon += int(r[iP])
+        p = r[1].split()
+        op = (p[1] if p[0].startswith("@") else p[0]).split(".")[0]
+        ops[op] += n
+        per_addr[r[0]] = (n, int(r[iT]), int(r[iP]))
+    # ---- attribution to source lines from the CUDA+SASS page.  Inlined code is listed under its own line AND under
+    # the lines of its callers, so every SASS address is counted ONCE, for the first line it appears under (the page
+    # lists a file's lines in order, which puts a callee's own line before its call sites further down the file).
     src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
-    ops, lines, text = collections.Counter(), collections.Counter(), {}
-    fname = ''
-    stall = collections.Counter()
-    infile, cur, tot, hdr_row = False, None, 0, None
+    lines, lanes, text, seen = collections.Counter(), collections.Counter(), {}, set()
+    fname, cur, infile = "", None, False
     for r in src:
         if len(r) >= 2 and r[0] == "File Path":
-            infile = r[1].endswith(".cuh"); fname = os.path.basename(r[1]); cur = None; continue
-        if len(r) >= 8 and r[0] == "Line No":
-            hdr_row = r; continue
-        if len(r) < 8:
+            infile = r[1].endswith(".cuh") or r[1].endswith(".cu"); fname = os.path.basename(r[1]); cur = None; continue
+        if len(r) < 8 or r[0] == "Line No":
             continue
         if r[0] != "":
             try:
@@ -92,26 +114,57 @@ def main():
             except ValueError:
                 cur = None
             continue
-        try:
-            n = int(r[7])
-        except ValueError:
+        if not r[2].startswith("0x") or r[2] in seen or r[2] not in per_addr:
             continue
-        p = r[3].split()
-        if not p:
-            continue
-        op = (p[1] if p[0].startswith("@") else p[0]).split(".")[0]
-        ops[op] += n; tot += n
+        seen.add(r[2])
         if infile and cur:
-            lines[cur] += n
+            lines[cur] += per_addr[r[2]][0]
+            lanes[cur] += per_addr[r[2]][1]
+    attributed = sum(lines.values())
+    # ---- stages = the device function a line belongs to (definitions parsed from the source file)
+    stage_of = {}
+    try:
+        import re
+        path = os.path.join(ROOT, "optical_networking_gym_b200", "csrc", "qrmsa_kernels.cuh")
+        name, struct = "(file scope)", None
+        for i, l in enumerate(open(path), 1):
+            ms = re.match(r"^(?:template.*>\s*)?struct\s+([A-Za-z_0-9]+)", l)
+            if ms and l.rstrip().endswith("{"):
+                struct = ms.group(1)
+            if l.startswith("};"):
+                struct = None
+            mk = re.search(r"\b(k_[a-z_0-9]+)\s*\(", l)
+            md = re.match(r"^(\s*)(?:template.*>\s*)?(?:static\s+)?(?:__host__\s+)?(?:__device__|__global__).*?\b([A-Za-z_][A-Za-z_0-9]*)\s*\(", l)
+            if mk and ("__global__" in l or l.startswith("    k_")):
+                name = mk.group(1)
+            elif md and md.group(2) not in ("__launch_bounds__", "__align__"):
+                name = (struct + "::" if struct and md.group(1) else "") + md.group(2)
+            stage_of[("qrmsa_kernels.cuh", i)] = name
+    except Exception:
+        pass
+    stages, stage_lanes = collections.Counter(), collections.Counter()
+    for ln, n in lines.items():
+        stages[stage_of.get(ln, ln[0])] += n
+        stage_lanes[stage_of.get(ln, ln[0])] += lanes[ln]
     per = env_steps or 1.0
+    traffic.update(warp_instructions_per_launch_sass_page=tot, avg_threads_per_instruction=thr / max(tot, 1),
+                   avg_predicated_on_threads_per_instruction=pon / max(tot, 1))
+    json.dump(traffic, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
     with open(os.path.join(out_dir, f"{tag}_hot_lines.md"), "w") as f:
         f.write(f"# {tag}: {m.get('Kernel Name', ('', ''))[0]}\n\n")
-        f.write(f"warp-instructions per launch {tot:.4g}" + (f" = {tot / per:.0f} per env-step" if env_steps else "") + "\n\n")
+        f.write(f"warp-instructions per launch {tot:.4g}" + (f" = {tot / per:.1f} per env-step" if env_steps else "") +
+                f" (SASS page, every instruction once; smsp__inst_executed.sum = {inst:.4g}); "
+                f"{thr / max(tot, 1):.2f} threads active per instruction, {pon / max(tot, 1):.2f} predicated on; "
+                f"{100.0 * attributed / max(tot, 1):.1f} % attributed to source lines below\n\n")
         f.write("## SASS opcode mix (per env-step)\n\n" if env_steps else "## SASS opcode mix\n\n")
         f.write(", ".join(f"{o} {n / per:.1f}" for o, n in ops.most_common(30)) + "\n\n")
-        f.write("## hottest source lines (warp-instructions per env-step, csrc/*.cuh)\n\n| line | instr | source |\n|---|---|---|\n")
+        f.write("## stages (device function owning the line; warp-instructions per env-step, active lanes per instruction)\n\n"
+                "| function | instr | lanes |\n|---|---|---|\n")
+        for st, n in stages.most_common(40):
+            f.write(f"| {st} | {n / per:.1f} | {stage_lanes[st] / max(n, 1):.1f} |\n")
+        f.write("\n## hottest source lines (warp-instructions per env-step, active lanes per instruction)\n\n| line | instr | lanes | source |\n|---|---|---|---|\n")
         for ln, n in lines.most_common(70):
-            f.write(f"| {ln[0].replace('qrmsa_', '').replace('.cuh', '')}:{ln[1]} | {n / per:.1f} | `{text[ln][:110]}` |\n")
+            f.write(f"| {ln[0].replace('qrmsa_', '').replace('.cuh', '')}:{ln[1]} | {n / per:.1f} | {lanes[ln] / max(n, 1):.1f} | `{text[ln][:110]}` |\n")
     print(json.dumps(traffic))
 
 
