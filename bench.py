@@ -765,11 +765,11 @@ def run_c5(cx, args):
         return {k: v[a:a + n] for k, v in b.items()}
 
     env.reset()
-    rollout(env, policy, Wm, sub(buf, 0, Wm))             # warm-up steps of the same episode
+    rollout(env, policy, Wm, sub(buf, 0, Wm), seed=1000 + rank)   # warm-up steps of the same episode
     cx.barrier()
     e0, e1 = cx.events(2)
     e0.record(stream)
-    rollout(env, policy, n_steps, sub(buf, Wm, n_steps))
+    rollout(env, policy, n_steps, sub(buf, Wm, n_steps), seed=1000 + rank, first_step=Wm)
     c = env.engine.counters_tensor().clone()
     if world > 1:
         cx.dist.all_reduce(c, op=cx.dist.ReduceOp.SUM)
@@ -798,7 +798,7 @@ def run_c5(cx, args):
         cx.barrier()
         t0 = time.perf_counter()
         env.reset()                                       # next episode: host streams -> device (H2D), schedule build
-        rollout(env, policy, n_steps, None, host_reward)
+        rollout(env, policy, n_steps, None, host_reward, seed=2000 + rank)
         cc = env.engine.counters_tensor().clone()
         if world > 1:
             cx.dist.all_reduce(cc, op=cx.dist.ReduceOp.SUM)
@@ -815,13 +815,13 @@ def run_c5(cx, args):
     per_step = n_envs * (obs_dim * 4 + n_act)             # bytes written by the observation kernel per rollout step
     return {"workload": f"PPO-style rollout, NSFNET/320/k=5, load 210, {n_envs} envs per GPU x {n_steps} steps, observation "
                         f"f32[{obs_dim}] + action mask u8[{n_act}] built on the device every step, torch MLP "
-                        f"{obs_dim}-512-256-128-{n_act} (bf16) sampling a masked categorical action, rollout buffer on the device",
+                        f"{obs_dim}-512-256-128-{n_act} (bf16), masked categorical sample by qrmsa_sample_masked_actions, rollout buffer on the device",
             "scaling": "weak", "value": world * n_envs * n_steps / (elapsed_ms * 1e-3), "unit": UNIT,
-            "ms_per_step": elapsed_ms / n_steps, "steps": n_steps, "warmup": Wm, "gpu_launches": 2 * n_steps,
+            "ms_per_step": elapsed_ms / n_steps, "steps": n_steps, "warmup": Wm, "gpu_launches": 4 * n_steps,
             "accepted": int(cnt[1]), "decided": int(cnt[0]),
             "roofline": {"bound": "hbm", "achieved": per_step * n_steps / (elapsed_ms * 1e-3) / 1e9, "peak": cx.peak,
                          "unit": "GB/s", "frac": per_step * n_steps / (elapsed_ms * 1e-3) / 1e9 / cx.peak, "traffic": None,
-                         "kernel": "k_observation + k_step_action (+ the policy's torch kernels inside the step)",
+                         "kernel": "k_observation_links + k_step_action + k_sample_masked (+ the policy's four torch GEMMs inside the step)",
                          "algorithmic_bytes_per_env_step": per_step / n_envs, "peak_source": cx.peak_src},
             "e2e": e2e, "parity_sample": parity}
 

@@ -25,31 +25,46 @@ def make_policy(obs_dim: int, n_actions: int, device, seed: int = 0):
     import torch
 
     g = torch.Generator(device="cpu").manual_seed(seed)
-    layers, dims = [], [obs_dim, 512, 256, 128, n_actions]       # train_multi_masked_ppo.py:440-441
+    # the action head is padded to a multiple of 8 outputs (9,601 -> 9,608): an odd row length takes the GEMM off its
+    # aligned path; `policy_logits` returns the [n_envs, n_actions] view of the padded rows and the sampler reads it in place
+    padded = (n_actions + 7) // 8 * 8
+    layers, dims = [], [obs_dim, 512, 256, 128, padded]          # train_multi_masked_ppo.py:440-441
     for i in range(4):
         lin = torch.nn.Linear(dims[i], dims[i + 1])
         with torch.no_grad():
             lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) / dims[i] ** 0.5)
             lin.bias.zero_()
         layers += [lin] + ([torch.nn.Tanh()] if i < 3 else [])
-    return torch.nn.Sequential(*layers).to(device).bfloat16()
+    net = torch.nn.Sequential(*layers).to(device).bfloat16()
+    net.n_actions = n_actions
+    return net
 
 
-def rollout(env, policy, n_steps: int, buffers: dict = None, host_reward=None):
+def policy_logits(policy, obs):
+    """bf16 logits [n_envs, n_actions] (a view of the padded action head's output)."""
+    return policy(obs.bfloat16())[:, : policy.n_actions]
+
+
+def rollout(env, policy, n_steps: int, buffers: dict = None, host_reward=None, seed: int = 0, first_step: int = 0,
+            torch_sampler: bool = False):
     """n_steps of obs -> policy -> masked categorical sample -> env.step for every env of `env` (a BatchedQRMSAEnv with
     gen_observation=True, already reset).  `buffers` (optional) receives the rollout buffer rows on the device:
     "action" int64 [n_steps, n_envs], "status" uint8, "reward" float32.  `host_reward` (optional, pinned float32
     [n_steps, n_envs]) gets every step's rewards by an asynchronous device->host copy (the end-to-end leg)."""
     import torch
 
+    from optical_networking_gym_b200.sampling import sample_masked_actions
+
     obs, mask = env._obs, env.action_masks()
     total_reward = torch.zeros((), device=obs.device, dtype=torch.float64)
     with torch.no_grad():
         for t in range(n_steps):
-            logits = policy(obs.bfloat16()).float()
-            logits.masked_fill_(mask == 0, float("-inf"))
-            # masked categorical sample by the Gumbel-max trick: argmax(logits - log E), E ~ Exp(1); no normalisation pass
-            action = (logits - torch.empty_like(logits).exponential_().log_()).argmax(dim=1)
+            logits = policy_logits(policy, obs)                  # bf16 [n_envs, n_actions], read in place by the sampler
+            if torch_sampler:   # the same sample spelled with torch ops (seven passes over an fp32 copy of the logits)
+                lf = logits.float().masked_fill_(mask == 0, float("-inf"))
+                action = (lf - torch.empty_like(lf).exponential_().log_()).argmax(dim=1)
+            else:               # one pass over the logits and the mask (Gumbel-max, Philox keyed by seed / step / env / action)
+                action = sample_masked_actions(logits, mask, seed, first_step + t)
             obs, reward, term, trunc, info = env.step(action)
             mask = info["mask"]
             if buffers is not None:

@@ -228,6 +228,19 @@ int qrmsa_observation(qrmsa_ctx *ctx, float *d_obs, uint8_t *d_mask, void *strea
 int qrmsa_observation_dims(const qrmsa_ctx *ctx, int *obs_dim, int *n_actions);
 
 /*
+ * Replaces: the masked categorical sample sb3_contrib's MaskablePPO draws from the policy's logits and the wrapper's
+ * action_masks() (wrappers/qrmsa_gym.py:74-75, examples/ONDM_2025/train_multi_masked_ppo.py:410-444), for every env in one
+ * pass: d_action[e] ~ Categorical(softmax(d_logits[e]) restricted to d_mask[e] != 0), drawn by the Gumbel-max identity from
+ * a Philox4x32-10 stream keyed by (seed, step) and counted by (env, action): reproducible, independent of the launch shape.
+ * d_logits: [n_envs][logit_row_stride] float32 or bfloat16 (QRMSA_LOGITS_*); d_mask: uint8 [n_envs][mask_row_stride] as
+ * written by qrmsa_observation; d_action: int64 [n_envs].  No context: the call only needs a device.
+ */
+enum { QRMSA_LOGITS_F32 = 0, QRMSA_LOGITS_BF16 = 1 };
+int qrmsa_sample_masked_actions(const void *d_logits, int logits_dtype, const uint8_t *d_mask, int n_envs, int n_actions,
+                                int64_t logit_row_stride, int64_t mask_row_stride, uint64_t seed, uint64_t step,
+                                int64_t *d_action, int device, void *stream);
+
+/*
  * Decisions of requests [first, first+count) as int32 action words, [count][n_envs] request-major:
  * low 24 bits = the reference's action index p*M*S + (max_mod_idx - m)*S + slot, reject = k*M*S
  * (heuristics.py:36-54, qrmsa.pyx:319-321), high bits = QRMSA_FLAG_*.

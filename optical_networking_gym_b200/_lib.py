@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libqrmsa_b200.so")
 SOURCES = ("qrmsa_b200.cu", "tracegen.cpp")
-HEADERS = ("qrmsa_kernels.cuh", os.path.join("..", "..", "include", "qrmsa_b200.h"))
+HEADERS = ("qrmsa_kernels.cuh", "qrmsa_sampler.cuh", os.path.join("..", "..", "include", "qrmsa_b200.h"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -100,6 +100,7 @@ SIGNATURES = {
     "qrmsa_step_action": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "qrmsa_observation": (_I, [_P, _P, _P, _P]),
     "qrmsa_observation_dims": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
+    "qrmsa_sample_masked_actions": (_I, [_P, _I, _P, _I, _I, C.c_int64, C.c_int64, _U64, _U64, _P, _I, _P]),
     "qrmsa_get_actions": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_actions_host": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_actions_host_strided": (_I, [_P, _I, _I, _P, C.c_int64, _P]),

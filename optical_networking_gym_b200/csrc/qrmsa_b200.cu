@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "qrmsa_kernels.cuh"
+#include "qrmsa_sampler.cuh"
 
 using namespace qrmsa;
 
@@ -43,6 +44,8 @@ struct qrmsa_ctx {
     double inv_max_rate = 0.0;
     int obs_grid = 0, obs_epc = 0, obs_env_smem = 0;   // k_observation: envs per CTA, shared memory per env
     size_t obs_smem = 0;
+    int obs2_grid = 0, obs2_epc = 0, obs2_env_smem = 0;   // k_observation_links (spectra up to 320 slots)
+    size_t obs2_smem = 0;
     std::string err;
 };
 
@@ -400,6 +403,22 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
             const int per_sm = std::max(1, std::min((int)((size_t)smem_sm / (ctx->obs_smem + 1024)), 2048 / (epc * OBS_ENV_THREADS)));
             ctx->obs_grid = std::min((n_envs + epc - 1) / epc, ctx->sm_count * per_sm);
         }
+        // link-major variant: spectra up to 320 slots and at most 8 paths per pair (one bit per path in the link sets)
+        if (D <= OBS2_MAX_D && K <= 8) {
+            ctx->obs2_env_smem = obs2_env_smem(K, D, kp.W, E);
+            int e2 = OBS_MAX_EPC;
+            while (e2 > 1 && (size_t)kp.blob_bytes + (size_t)e2 * ctx->obs2_env_smem > smem_budget) e2 >>= 1;
+            const size_t need2 = (size_t)kp.blob_bytes + (size_t)e2 * ctx->obs2_env_smem;
+            if (need2 <= smem_budget &&
+                cudaFuncSetAttribute(k_observation_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need2) == cudaSuccess) {
+                ctx->obs2_epc = e2;
+                ctx->obs2_smem = need2;
+                const int per_sm = std::max(1, std::min((int)((size_t)smem_sm / (need2 + 1024)), 2048 / (e2 * OBS_ENV_THREADS)));
+                ctx->obs2_grid = std::min((n_envs + e2 - 1) / e2, ctx->sm_count * per_sm);
+            } else {
+                (void)cudaGetLastError();
+            }
+        }
     }
 
     // ---- uploads and state
@@ -703,14 +722,40 @@ extern "C" int qrmsa_observation(qrmsa_ctx *ctx, float *d_obs, uint8_t *d_mask, 
     if (!ctx || !d_obs || !d_mask) return QRMSA_ERR_ARG;
     if (ctx->kp.n_req < 1) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
     if (!ctx->d_path_len_norm) { ctx->err = "path_length_km / link_length_km were not given to qrmsa_create"; return QRMSA_ERR_STATE; }
-    if (!ctx->obs_grid) { ctx->err = "observation kernel needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
+    if (!ctx->obs_grid && !ctx->obs2_grid) { ctx->err = "observation kernel needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
     CK(cudaSetDevice(ctx->device));
     int obs_dim = 0, n_actions = 0;
     qrmsa_observation_dims(ctx, &obs_dim, &n_actions);
-    k_observation<<<ctx->obs_grid, ctx->obs_epc * OBS_ENV_THREADS, ctx->obs_smem, (cudaStream_t)stream>>>(
-        ctx->kp, ctx->d_path_len_norm, ctx->inv_max_rate, d_obs, d_mask, obs_dim, n_actions, ctx->obs_epc, ctx->obs_env_smem);
+    if (ctx->obs2_grid)
+        k_observation_links<<<ctx->obs2_grid, ctx->obs2_epc * OBS_ENV_THREADS, ctx->obs2_smem, (cudaStream_t)stream>>>(
+            ctx->kp, ctx->d_path_len_norm, ctx->inv_max_rate, d_obs, d_mask, obs_dim, n_actions, ctx->obs2_epc, ctx->obs2_env_smem);
+    else
+        k_observation<<<ctx->obs_grid, ctx->obs_epc * OBS_ENV_THREADS, ctx->obs_smem, (cudaStream_t)stream>>>(
+            ctx->kp, ctx->d_path_len_norm, ctx->inv_max_rate, d_obs, d_mask, obs_dim, n_actions, ctx->obs_epc, ctx->obs_env_smem);
     CK(cudaGetLastError());
     return QRMSA_OK;
+}
+
+extern "C" int qrmsa_sample_masked_actions(const void *d_logits, int logits_dtype, const uint8_t *d_mask, int n_envs,
+                                           int n_actions, int64_t logit_row_stride, int64_t mask_row_stride, uint64_t seed,
+                                           uint64_t step, int64_t *d_action, int device, void *stream) {
+    if (!d_logits || !d_mask || !d_action || n_envs < 1 || n_actions < 1 || logit_row_stride < n_actions ||
+        mask_row_stride < n_actions || (logits_dtype != QRMSA_LOGITS_F32 && logits_dtype != QRMSA_LOGITS_BF16))
+        return QRMSA_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return QRMSA_ERR_NO_DEVICE;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return QRMSA_ERR_CUDA;
+    const int rows_per_cta = SAMPLER_THREADS / 32;          // a warp per row
+    const int want = (n_envs + rows_per_cta - 1) / rows_per_cta;
+    const int grid = want < sms * 8 ? want : sms * 8;       // up to 8 CTAs of 256 threads per SM, rows strided over the warps
+    cudaStream_t st = (cudaStream_t)stream;
+    if (logits_dtype == QRMSA_LOGITS_BF16)
+        k_sample_masked<__nv_bfloat16><<<grid, SAMPLER_THREADS, 0, st>>>((const __nv_bfloat16 *)d_logits, d_mask, n_envs, n_actions,
+                                                                        logit_row_stride, mask_row_stride, seed, step, (long long *)d_action);
+    else
+        k_sample_masked<float><<<grid, SAMPLER_THREADS, 0, st>>>((const float *)d_logits, d_mask, n_envs, n_actions, logit_row_stride,
+                                                                 mask_row_stride, seed, step, (long long *)d_action);
+    return cudaGetLastError() == cudaSuccess ? QRMSA_OK : QRMSA_ERR_CUDA;
 }
 
 extern "C" int qrmsa_get_actions(qrmsa_ctx *ctx, int first, int count, int32_t *d_out, void *stream) {

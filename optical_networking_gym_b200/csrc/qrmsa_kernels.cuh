@@ -1372,6 +1372,343 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
 }
 
 // --------------------------------------------------------------------------------------------------------
+// k_observation_links: the same observation + mask for spectra up to 320 slots (D = 2S <= 4 * OBS_ENV_THREADS), built
+// LINK-major.  The k paths of a node pair share links (NSFNET: 20.4 hop visits but 12.1 distinct links per request,
+// nobel-eu: 25.1 / 13.3), and the neighbour sum of a link does not depend on the path it is reached by, so the sums
+// are made once per DISTINCT link and added into X[p][c2] of every path p that crosses it.  Thread t owns the four
+// centres c2 = t, t + 160, t + 320, t + 480 for the whole request: one channel record is fetched (broadcast) and
+// decoded once for four table lookups, and the sums of a link stay in registers.  The kernel is bound by the
+// shared-memory bandwidth of the G / INV lookups (16 bytes per term); this layout takes it from 6 to 4.25 wavefronts per
+// 32 terms and cuts the terms by the link sharing.  Afterwards warp w owns path w (round robin): free-block
+// statistics, GSNR per valid start, mask bytes and the 12 features per modulation need warp shuffles only -- three
+// env-wide barriers per request instead of seven per path.
+// --------------------------------------------------------------------------------------------------------
+template <int V> struct IntC { static constexpr int value = V; };
+constexpr int OBS2_NJ = 4;                          // centres per thread
+constexpr int OBS2_MAX_D = OBS2_NJ * OBS_ENV_THREADS;
+constexpr int OBS2_NIT = (OBS2_MAX_D / 2 + 31) / 32;   // starts per lane in the per-path phase (320 slots / 32 lanes)
+
+__host__ __device__ inline int obs2_env_smem(int K, int D, int W, int E) {
+    const int VW = W + 1, NW = (D + 31) >> 5, S = D / 2, NWARP = OBS_ENV_THREADS / 32;
+    const int words = K * 8 * VW + K * NW + K * VW + K * 32 + K + E + 4 + (NWARP * S + 1) / 2;
+    return ((8 * K * D + 8 * 3 * K + 4 * words) + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {   // bit i -> bit 2i
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+__global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
+    k_observation_links(const KParams p, const double *__restrict__ path_len_norm, const double inv_max_rate,
+                        float *__restrict__ obs_out, uint8_t *__restrict__ mask_out, const int obs_dim, const int n_actions,
+                        const int epc, const int env_smem) {
+    __shared__ uint64_t mbar;
+    stage_tables(p, &mbar);
+    Tab t;
+    t.init();
+    const Dim<0, 0, 0> dm(p);
+    const int S = p.S, W = p.W, M = p.M, K = p.K, D = p.D, CAP = p.CAP, E = p.E;
+    const int VW = W + 1, NW = (D + 31) >> 5;
+    const int slot = threadIdx.x / OBS_ENV_THREADS;
+    auto env_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(OBS_ENV_THREADS) : "memory"); };
+    unsigned char *base = qsmem + p.blob_bytes + (size_t)slot * env_smem;
+    double *X = reinterpret_cast<double *>(base);                       // [K][D]   neighbour sum per path and centre
+    double *pstat = X + (size_t)K * D;                                  // [K][3]   free slots, mean / std of the free blocks
+    uint32_t *validM = reinterpret_cast<uint32_t *>(pstat + 3 * K);     // [K][8][VW] valid-start bitmaps per modulation
+    uint32_t *need = validM + K * 8 * VW;                               // [K][NW]  centres some modulation can use
+    uint32_t *avs = need + K * NW;                                      // [K][VW]  path availability (+ the virtual slot)
+    int *plink = reinterpret_cast<int *>(avs + K * VW);                 // [K][32]  link ids
+    int *phops = plink + K * 32;                                        // [K]
+    uint32_t *lmask = reinterpret_cast<uint32_t *>(phops + K);          // [E]      paths crossing link l (0: none)
+    int *tick = reinterpret_cast<int *>(lmask + E);                     // [1]      work ticket of the per-path phase
+    const int tid = threadIdx.x - slot * OBS_ENV_THREADS, lane = tid & 31, warp = tid >> 5;
+    constexpr int nw = OBS_ENV_THREADS >> 5;
+    uint16_t *slist = reinterpret_cast<uint16_t *>(tick + 4) + warp * S;   // [nw][S]  valid starts of the open unit, compacted
+    const double inv_S = 1.0 / (double)S, inv_S1 = 1.0 / (double)(S - 1);
+
+    for (int i = tid; i < E; i += OBS_ENV_THREADS) lmask[i] = 0u;
+    env_sync();
+    for (int env = blockIdx.x * epc + slot; env < p.n_envs; env += gridDim.x * epc) {
+        const int4 st = p.estate[env];
+        float *obs = obs_out + (size_t)env * obs_dim;
+        uint8_t *mask = mask_out + (size_t)env * n_actions;
+        const int cur = st.x < p.n_req ? st.x : p.n_req - 1;
+        const uint4 rq = p.trace[(size_t)env * p.T + cur];
+        const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+        const uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
+        const uint32_t *lists = p.lists + (size_t)env * E * CAP;
+        const int pbase = (src * p.N + dst) * K;
+        if (tid == 0) {
+            obs[0] = (float)((double)t.rate(rate) * inv_max_rate);                       // qrmsa.pyx:654-665
+            obs[1] = (float)(p.N > 1 ? (double)src / (double)(p.N - 1) : 0.0);
+            obs[2] = (float)(p.N > 1 ? (double)dst / (double)(p.N - 1) : 0.0);
+            mask[n_actions - 1] = 1;                                                        // qrmsa.pyx:766
+            *tick = 0;
+        }
+        for (int i = tid; i < K * D; i += OBS_ENV_THREADS) X[i] = 0.0;   // (its readers passed the barrier that ends the loop)
+
+        // ---- phase 0, warp per path: links, availability, free blocks, valid starts of every modulation, usable centres
+        for (int pi = warp; pi < K; pi += nw) {
+            const int path = pbase + pi;
+            const int hops = __ldg(p.path_hops + path) & 0x7f;
+            if (lane == 0) { phops[pi] = hops; obs[3 + pi] = hops ? (float)path_len_norm[path] : 0.f; }
+            for (int w = lane; w < NW; w += 32) need[pi * NW + w] = 0u;
+            if (hops == 0) {   // fewer than k paths for this pair: features stay -1, no valid action (qrmsa.pyx:697)
+                for (int i = lane; i < M * 12; i += 32) obs[3 + K + pi * M * 12 + i] = -1.f;
+                for (int i = lane; i < M * S; i += 32) mask[(size_t)pi * M * S + i] = 0;
+                continue;
+            }
+            const int l = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+            plink[pi * 32 + lane] = l;
+            if (lane < hops) atomicOr(&lmask[l], 1u << pi);
+            const uint32_t a = path_available(dm, bm, hops, l, lane);
+            if (lane < VW) avs[pi * VW + lane] = a;
+            uint32_t r = a;
+            int aa = 1;
+            for (int mi = 0; mi < M; ++mi) {
+                const int L = t.need(rate * M + (M - 1) - mi) + 1;
+                if (L < aa) { r = a; aa = 1; }
+                while (aa < L) { const int b = min(aa, L - aa); r &= shr_multi(r, b); aa += b; }
+                if (lane < VW) validM[(pi * 8 + mi) * VW + lane] = r;
+            }
+            __syncwarp();
+            // need[c2] = some modulation has a valid start s with 2 s + n == c2: for the 32 centres of word w and a
+            // modulation of n slots these are the 16 starts from 16 w - (n >> 1), spread to every other bit
+            for (int w = lane; w < NW; w += 32) {
+                uint32_t bits = 0u;
+                for (int mi = 0; mi < M; ++mi) {
+                    const int n = t.need(rate * M + (M - 1) - mi);
+                    int s0 = 16 * w - (n >> 1), sh = 0;
+                    if (s0 < 0) { sh = -s0; s0 = 0; }
+                    if (sh >= 16) continue;
+                    const uint32_t *row = validM + (pi * 8 + mi) * VW;
+                    const int q = s0 >> 5;
+                    const uint32_t lo = q < VW ? row[q] : 0u, hi = q + 1 < VW ? row[q + 1] : 0u;
+                    const uint32_t v16 = ((__funnelshift_r(lo, hi, s0 & 31) & 0xffffu) << sh) & 0xffffu;
+                    bits |= spread16(v16) << (n & 1);
+                }
+                if (w == NW - 1 && (D & 31)) bits &= (1u << (D & 31)) - 1u;
+                need[pi * NW + w] = bits;
+            }
+            // free blocks of the path availability (qrmsa.pyx:631-646): lane j looks at word j; a block is counted in the
+            // word that holds its last slot, its first slot is the nearest block start at or below it
+            int b_free = 0, b_n = 0, b_len = 0, b_len2 = 0;
+            if (lane < W) {
+                const uint32_t *av = avs + pi * VW;
+                auto real = [&](int j) -> uint32_t {   // word j of the availability without the virtual slot at S
+                    if (j < 0 || j >= W) return 0u;
+                    uint32_t v = av[j];
+                    if (j == (S >> 5)) v &= (1u << (S & 31)) - 1u;
+                    return v;
+                };
+                const uint32_t wv = real(lane), up = real(lane + 1);
+                b_free = __popc(wv);
+                uint32_t ends = wv & ~((wv >> 1) | (up << 31));
+                while (ends) {
+                    const int eb = __ffs(ends) - 1;
+                    ends &= ends - 1u;
+                    int j = lane, start;
+                    uint32_t cand = wv & ((eb == 31) ? 0xffffffffu : ((2u << eb) - 1u));
+                    for (;;) {   // block start: highest free slot at or below the end whose lower neighbour is occupied
+                        const uint32_t word = j == lane ? wv : real(j);
+                        const uint32_t starts = cand & ~((word << 1) | (real(j - 1) >> 31));
+                        if (starts) { start = (j << 5) + 31 - __clz(starts); break; }
+                        j -= 1;
+                        cand = real(j);
+                    }
+                    const int len = (lane << 5) + eb - start + 1;
+                    b_n += 1; b_len += len; b_len2 += len * len;
+                }
+            }
+            b_free = __reduce_add_sync(FULL, b_free); b_n = __reduce_add_sync(FULL, b_n);
+            b_len = __reduce_add_sync(FULL, b_len); b_len2 = __reduce_add_sync(FULL, b_len2);
+            if (lane == 0) {
+                double mean_block = 0.0, std_block = 0.0;
+                if (b_n > 0) {
+                    const double nb = (double)b_n, mb = (double)b_len / nb;
+                    mean_block = ((mb - 4.0) / 4.0) / 100.0;
+                    std_block = sqrt(fmax((double)b_len2 / nb - mb * mb, 0.0)) / 100.0;
+                }
+                pstat[pi * 3 + 0] = (double)b_free; pstat[pi * 3 + 1] = mean_block; pstat[pi * 3 + 2] = std_block;
+            }
+        }
+        env_sync();
+        // ---- phase 1, thread per four centres: neighbour sums link by link (core/osnr.pyx:64-94, table form)
+        {
+            int c2j[OBS2_NJ];
+            uint32_t myneed[OBS2_NJ];   // bit pi: path pi uses this centre
+#pragma unroll
+            for (int j = 0; j < OBS2_NJ; ++j) {
+                c2j[j] = tid + j * OBS_ENV_THREADS;
+                uint32_t mset = 0u;
+                if (c2j[j] < D)
+                    for (int pi = 0; pi < K; ++pi) mset |= ((need[pi * NW + (c2j[j] >> 5)] >> (c2j[j] & 31)) & 1u) << pi;
+                myneed[j] = mset;
+            }
+#pragma unroll 1
+            for (int l = 0; l < E; ++l) {
+                const uint32_t pm = lmask[l];
+                if (!pm) continue;      // no path of this request crosses the link
+                bool want[OBS2_NJ], wany[OBS2_NJ];
+                bool some = false;
+#pragma unroll
+                for (int j = 0; j < OBS2_NJ; ++j) {
+                    want[j] = (myneed[j] & pm) != 0u;
+                    wany[j] = __any_sync(FULL, want[j]);
+                    some |= wany[j];
+                }
+                if (!some) continue;
+                const int cnt = (int)bm[(unsigned)(l * p.RW + p.RW - 1)];
+                const uint32_t *lst = lists + (unsigned)(l * CAP);
+                double s1[OBS2_NJ], s2[OBS2_NJ];
+#pragma unroll
+                for (int j = 0; j < OBS2_NJ; ++j) s1[j] = s2[j] = 0.0;
+#pragma unroll 2
+                for (int q = 0; q < cnt; ++q) {
+                    const uint32_t rec = lst[q];                              // same address on every lane: one broadcast
+                    const int c2r = (int)(rec & 0xfffu);
+                    const uint32_t goff = ((rec >> 23) + 1u) * (8u * (uint32_t)D);
+                    const double phin = t.PHIN(rec >> 20);
+#pragma unroll
+                    for (int j = 0; j < OBS2_NJ; ++j) {
+                        if (!wany[j]) continue;                                 // warp-uniform
+                        const uint32_t a_inv = t.sb + 8u * (uint32_t)abs(c2r - c2j[j]);
+                        double g, inv;
+                        asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(a_inv + goff), "n"(lay::INV));
+                        asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(a_inv), "n"(lay::INV));
+                        s1[j] += g;
+                        s2[j] = fma(phin, inv, s2[j]);
+                    }
+                }
+                const double w1 = t.W1(l), w2 = t.W2(l);   // W2 is stored negated
+#pragma unroll
+                for (int j = 0; j < OBS2_NJ; ++j) {
+                    if (!want[j]) continue;
+                    const double y = fma(w2, s2[j], w1 * s1[j]);
+                    uint32_t ps = myneed[j] & pm;
+                    while (ps) {
+                        const int pi = __ffs(ps) - 1;
+                        ps &= ps - 1u;
+                        X[pi * D + c2j[j]] += y;                                // this thread owns the centre: no race
+                    }
+                }
+            }
+        }
+        env_sync();   // X complete
+        for (int i = tid; i < E; i += OBS_ENV_THREADS) lmask[i] = 0u;   // (read above, set again after the closing barrier)
+        // ---- phase 2: units = (path, run of modulations that need the same number of slots), handed to the warps by a
+        // ticket.  The unit's valid starts are compacted so that every lane holds one; GSNR once per start, then mask
+        // bytes and the 12 features per modulation of the unit (qrmsa.pyx:583-781).
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(tick, 1);
+            u = __shfl_sync(FULL, u, 0);
+            if (u >= K * M) break;
+            const int pi = u / M, mi0 = u - pi * M;
+            if (phops[pi] == 0) continue;
+            const int n = t.need(rate * M + (M - 1) - mi0);
+            if (mi0 > 0 && t.need(rate * M + (M - 1) - (mi0 - 1)) == n) continue;   // not the head of its run
+            int mi1 = mi0 + 1;
+            while (mi1 < M && t.need(rate * M + (M - 1) - mi1) == n) ++mi1;
+            const int ncls = t.cls(rate * M + (M - 1) - mi0);
+            const int path = pbase + pi;
+            const double2 pg = __ldg(p.path_gn + path);
+            const uint32_t *vrow = validM + (pi * 8 + mi0) * VW;
+            const double *Xp = X + pi * D + n;
+            // compaction (a word of the bitmap is its own ballot) and the all-zero mask rows of the unit
+            int cnt = 0;
+            for (int it = 0; it * 32 < S; ++it) {
+                const uint32_t w = vrow[it];
+                if ((w >> lane) & 1u) slist[cnt + __popc(w & ((1u << lane) - 1u))] = (uint16_t)(lane + it * 32);
+                cnt += __popc(w);
+            }
+            for (int mi = mi0; mi < mi1; ++mi) {
+                uint8_t *mrow = mask + (size_t)pi * M * S + (size_t)mi * S;
+                for (int s = lane; s < S; s += 32) mrow[s] = 0;
+            }
+            __syncwarp();
+            double g_cached[OBS2_NIT];
+            int s_cached[OBS2_NIT];
+#pragma unroll
+            for (int c = 0; c < OBS2_NIT; ++c) {
+                g_cached[c] = 0.0;
+                s_cached[c] = -1;
+                if (c * 32 < cnt) {   // warp-uniform
+                    const int idx = c * 32 + lane;
+                    if (idx < cnt) {
+                        const int s = slist[idx];
+                        const double acc = gn_base(p, t, pg, s, n, ncls).with(Xp[2 * s]);
+                        g_cached[c] = 10.0 * log10(1.0 / acc);
+                        s_cached[c] = s;
+                    }
+                }
+            }
+            // lane j keeps the reduced statistics of the unit's j-th modulation; the features are finished side by side
+            int k_n = 0, k_s = 0, k_max = -1;
+            long long k_s2 = 0;
+            double k_sum = 0.0, k_vmax = -1e300, k_sq = 0.0;
+            for (int mi = mi0; mi < mi1; ++mi) {
+                const double th = p.mod_thr_nomargin[(M - 1) - mi], ath = fabs(th);
+                uint8_t *mrow = mask + (size_t)pi * M * S + (size_t)mi * S;
+                // count, sum s, sum s^2, max s in integers; sum norm, max norm, sum norm^2 in FP64
+                int c_n = 0, c_s = 0, c_max = -1;
+                long long c_s2 = 0;
+                double v_sum = 0.0, v_max = -1e300, v_sq = 0.0;
+#pragma unroll
+                for (int c = 0; c < OBS2_NIT; ++c) {
+                    const int s = s_cached[c];
+                    if (s >= 0) {
+                        // np.round(x, 10) (osnr.pyx:366): rint(x * 1e10) / 1e10; its sign decides the mask bit
+                        const double r10 = rint(((g_cached[c] - th) / ath) * 1e10);
+                        const double nrm = r10 / 1e10;
+                        if (r10 >= 0.0) mrow[s] = 1;
+                        c_n += 1; c_s += s; c_s2 += (long long)s * s; c_max = max(c_max, s);
+                        v_sum += nrm; v_max = fmax(v_max, nrm); v_sq = fma(nrm, nrm, v_sq);
+                    }
+                }
+                c_n = __reduce_add_sync(FULL, c_n); c_s = __reduce_add_sync(FULL, c_s); c_max = __reduce_max_sync(FULL, c_max);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    c_s2 += __shfl_xor_sync(FULL, c_s2, o);
+                    v_sum += __shfl_xor_sync(FULL, v_sum, o);
+                    v_sq += __shfl_xor_sync(FULL, v_sq, o);
+                    v_max = fmax(v_max, __shfl_xor_sync(FULL, v_max, o));
+                }
+                if (lane == mi - mi0) { k_n = c_n; k_s = c_s; k_max = c_max; k_s2 = c_s2; k_sum = v_sum; k_vmax = v_max; k_sq = v_sq; }
+            }
+            if (lane < mi1 - mi0) {
+                const double cntv = (double)k_n, total_av = pstat[pi * 3 + 0];
+                double f_avg = 0, f_std = 0, f_max = 0, best = 0, omean = 0, ovar = 0;
+                if (k_n > 0) {
+                    f_avg = (double)k_s / cntv; omean = k_sum / cntv; f_max = (double)k_max; best = fmax(k_vmax, 0.0);
+                    f_std = sqrt(fmax((double)k_s2 / cntv - f_avg * f_avg, 0.0));
+                    ovar = fmax(k_sq / cntv - omean * omean, 0.0);
+                }
+                float *o = obs + 3 + K + (pi * M + mi0 + lane) * 12;
+                o[0] = (float)(cntv * inv_S);
+                o[1] = (float)(f_avg * inv_S1);
+                o[2] = (float)(f_std * inv_S1);
+                o[3] = (float)fmax(((double)n - 5.5) / 3.5, 0.0);
+                o[4] = (float)(2.0 * (total_av - 0.5 * (double)S) * inv_S);
+                o[5] = (float)pstat[pi * 3 + 1];
+                o[6] = (float)pstat[pi * 3 + 2];
+                o[7] = (float)best;
+                o[8] = (float)omean;
+                o[9] = (float)ovar;
+                o[10] = (float)(2.0 * ((total_av * inv_S) - 0.5));
+                o[11] = (float)(f_max * inv_S1);
+            }
+            __syncwarp();   // slist is rewritten by the next unit
+        }
+        env_sync();   // the next request rewrites X, need, lmask and the path scratch
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
 // heuristic_highest_snr (heuristics.py:272-328, benchmark heuristic #2) + env.step, n_steps requests per env.
 // The reference QoT-checks EVERY valid start of every (path, modulation) and takes the acceptable candidate with
 // the highest GSNR.  One CTA per env: per path the neighbour sum X[c2] is built once for every centre frequency

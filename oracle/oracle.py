@@ -271,3 +271,27 @@ def generate_trace_philox(n_envs: int, n_requests: int, load, seed: int, src_cum
         r = np.searchsorted(rate_cum[: R - 1], (b[2].astype(np.float64) / 4294967296.0) * rate_cum[R - 1], side="right")
         src[kk], dst[kk], rate[kk], arrival[kk], holding[kk] = s, d, r, at, ht
     return src, dst, rate, arrival, holding
+
+
+def sample_masked_actions_numpy(logits, mask, seed: int, step: int):
+    """numpy restatement of k_sample_masked (csrc/qrmsa_sampler.cuh): Gumbel-max over the masked logits with the
+    Philox4x32-10 stream keyed by (seed, step) and counted by (env, action / 4).  Returns (actions int64 [n_envs],
+    keys float32 [n_envs, n_actions] with -inf where masked)."""
+    logits = np.asarray(logits, np.float32)
+    mask = np.asarray(mask) != 0
+    n_envs, n_actions = logits.shape
+    seed &= (1 << 64) - 1
+    k0 = (seed & 0xFFFFFFFF) ^ (((step * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)) >> 32)
+    k1 = ((seed >> 32) & 0xFFFFFFFF) ^ (step & 0xFFFFFFFF)
+    n_groups = (n_actions + 3) // 4
+    g = np.broadcast_to(np.arange(n_groups, dtype=np.uint64)[None, :], (n_envs, n_groups)).ravel()
+    e = np.broadcast_to(np.arange(n_envs, dtype=np.uint64)[:, None], (n_envs, n_groups)).ravel()
+    z = np.zeros_like(g)
+    r = philox4x32_10((g, z, e, z), (k0, k1))
+    bits = np.stack([x.astype(np.uint32) for x in r], axis=1).reshape(n_envs, n_groups * 4)[:, :n_actions]
+    u = ((bits >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    gum = -np.log(-np.log(u, dtype=np.float32), dtype=np.float32)
+    keys = np.where(mask, logits + gum, -np.inf).astype(np.float32)
+    act = keys.argmax(axis=1).astype(np.int64)
+    act[~mask.any(axis=1)] = n_actions - 1
+    return act, keys

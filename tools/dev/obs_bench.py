@@ -3,7 +3,7 @@ sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from helpers import load_tables
 from optical_networking_gym_b200.env import BatchedQRMSAEnv
 tb = load_tables("nsfnet", 320)
-n = 8192
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 env = BatchedQRMSAEnv(tb, n, num_spectrum_resources=320, episode_length=400, load=210.0, bit_rates=(10, 40, 100, 400, 1000),
                       launch_power_dbm=1.0, gen_observation=False, seed=10, request_source="device")
 env.step_first_fit(300)

@@ -88,6 +88,7 @@ def main():
     sass = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "sass"]))))
     sh = next(r for r in sass if len(r) > 5 and r[0] == "Address")
     iI, iT, iP = sh.index("Instructions Executed"), sh.index("Thread Instructions Executed"), sh.index("Predicated-On Thread Instructions Executed")
+    iS = sh.index("# Samples")
     ops, per_addr, tot, thr, pon = collections.Counter(), {}, 0, 0, 0
     for r in sass:
         if len(r) <= iP or not r[0].startswith("0x"):
@@ -96,12 +97,13 @@ def main():
         p = r[1].split()
         op = (p[1] if p[0].startswith("@") else p[0]).split(".")[0]
         ops[op] += n
-        per_addr[r[0]] = (n, int(r[iT]), int(r[iP]))
+        per_addr[r[0]] = (n, int(r[iT]), int(r[iP]), int(r[iS] or 0))
     # ---- attribution to source lines from the CUDA+SASS page.  Inlined code is listed under its own line AND under
     # the lines of its callers, so every SASS address is counted ONCE, for the first line it appears under (the page
     # lists a file's lines in order, which puts a callee's own line before its call sites further down the file).
     src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
     lines, lanes, text, seen = collections.Counter(), collections.Counter(), {}, set()
+    samples = collections.Counter()
     fname, cur, infile = "", None, False
     for r in src:
         if len(r) >= 2 and r[0] == "File Path":
@@ -120,6 +122,7 @@ def main():
         if infile and cur:
             lines[cur] += per_addr[r[2]][0]
             lanes[cur] += per_addr[r[2]][1]
+            samples[cur] += per_addr[r[2]][3]
     attributed = sum(lines.values())
     # ---- stages = the device function a line belongs to (definitions parsed from the source file)
     stage_of = {}
@@ -142,10 +145,12 @@ def main():
             stage_of[("qrmsa_kernels.cuh", i)] = name
     except Exception:
         pass
-    stages, stage_lanes = collections.Counter(), collections.Counter()
+    stages, stage_lanes, stage_samples = collections.Counter(), collections.Counter(), collections.Counter()
     for ln, n in lines.items():
         stages[stage_of.get(ln, ln[0])] += n
         stage_lanes[stage_of.get(ln, ln[0])] += lanes[ln]
+        stage_samples[stage_of.get(ln, ln[0])] += samples[ln]
+    all_samples = max(sum(v[3] for v in per_addr.values()), 1)
     per = env_steps or 1.0
     traffic.update(warp_instructions_per_launch_sass_page=tot, avg_threads_per_instruction=thr / max(tot, 1),
                    avg_predicated_on_threads_per_instruction=pon / max(tot, 1))
@@ -159,9 +164,12 @@ def main():
         f.write("## SASS opcode mix (per env-step)\n\n" if env_steps else "## SASS opcode mix\n\n")
         f.write(", ".join(f"{o} {n / per:.1f}" for o, n in ops.most_common(30)) + "\n\n")
         f.write("## stages (device function owning the line; warp-instructions per env-step, active lanes per instruction)\n\n"
-                "| function | instr | lanes |\n|---|---|---|\n")
+                "| function | instr | lanes | % of stall samples |\n|---|---|---|---|\n")
         for st, n in stages.most_common(40):
-            f.write(f"| {st} | {n / per:.1f} | {stage_lanes[st] / max(n, 1):.1f} |\n")
+            f.write(f"| {st} | {n / per:.1f} | {stage_lanes[st] / max(n, 1):.1f} | {100.0 * stage_samples[st] / all_samples:.1f} |\n")
+        f.write("\n## source lines by warp-stall samples (where the time goes)\n\n| line | % samples | instr | source |\n|---|---|---|---|\n")
+        for ln, n in samples.most_common(40):
+            f.write(f"| {ln[0].replace('qrmsa_', '').replace('.cuh', '')}:{ln[1]} | {100.0 * n / all_samples:.1f} | {lines[ln] / per:.1f} | `{text[ln][:110]}` |\n")
         f.write("\n## hottest source lines (warp-instructions per env-step, active lanes per instruction)\n\n| line | instr | lanes | source |\n|---|---|---|---|\n")
         for ln, n in lines.most_common(70):
             f.write(f"| {ln[0].replace('qrmsa_', '').replace('.cuh', '')}:{ln[1]} | {n / per:.1f} | {lanes[ln] / max(n, 1):.1f} | `{text[ln][:110]}` |\n")
