@@ -93,6 +93,7 @@ enum {
 #define QRMSA_FLAG_ACCEPTED 0x20000000u
 #define QRMSA_FLAG_BLOCKED_RESOURCES 0x01000000u /* rejected: the heuristic's blocked_due_to_resources (heuristics.py:966) */
 #define QRMSA_FLAG_BLOCKED_OSNR 0x02000000u      /* rejected: blocked_due_to_osnr                                     */
+#define QRMSA_FLAG_RELEASE_CANCELLED 0x08000000u /* accepted, but its release event was dropped (qrmsa.pyx:433, :461-464)  */
 #define QRMSA_FLAG_NEAR_TIE 0x04000000u          /* highest-SNR policy: a runner-up within 1e-6 dB of the chosen candidate */
 
 /* step_action status per env (qrmsa.pyx:838-1065) */
@@ -138,6 +139,14 @@ int qrmsa_enable_gsnr_log(qrmsa_ctx *ctx, int enable);
  * `_next_service()`, qrmsa.pyx:499-500).
  */
 int qrmsa_reset(qrmsa_ctx *ctx, void *stream);
+
+/*
+ * Replaces: the `self._events = []` of QRMSAEnv.reset(options={"only_episode_counters": True}) (envs/qrmsa.pyx:433,
+ * :461-464): the episode counters restart while the network is left as it is -- and, because the release heap is emptied,
+ * every service that is running at that moment is never released.  Marks those services
+ * (QRMSA_FLAG_RELEASE_CANCELLED in their action word); the request stream and the current request are untouched.
+ */
+int qrmsa_cancel_pending_releases(qrmsa_ctx *ctx, void *stream);
 
 /*
  * Replaces: the per-request draws of QRMSAEnv._next_service/_get_node_pair
@@ -286,6 +295,10 @@ int qrmsa_export_link_list(qrmsa_ctx *ctx, int env, int link, int32_t *h_out3, i
  */
 int qrmsa_probe_gsnr(qrmsa_ctx *ctx, int env, int src, int dst, int p, int initial_slot, int number_slots,
                      double *h_gsnr_db);
+/* The same call with all three values calculate_osnr returns (core/osnr.pyx:133-142): h_out[0] = GSNR, h_out[1] = the
+ * ASE-only figure, h_out[2] = the NLI-only figure, in dB. */
+int qrmsa_probe_qot(qrmsa_ctx *ctx, int env, int src, int dst, int p, int initial_slot, int number_slots,
+                    double *h_gsnr_ase_nli_db);
 
 /*
  * Host-side request generator reproducing CPython 3.12 `random.Random(seed)` draw for draw
@@ -298,6 +311,10 @@ int qrmsa_probe_gsnr(qrmsa_ctx *ctx, int env, int src, int dst, int p, int initi
 int qrmsa_tracegen_create(int n_envs, uint64_t base_seed, int n_nodes, int n_rates, const double *h_load,
                           double mean_holding_time, const double *h_src_cum, const double *h_dst_cum,
                           const double *h_rate_cum, qrmsa_tracegen **out);
+/* bit_rate_selection="continuous" (qrmsa.pyx:246-254, :1086-1087): the bit rate is `rng.randint(lower, higher)` instead
+ * of `choices(bit_rates, probs)`; the generated rate index is (bit rate - lower), i.e. an index into the table
+ * (lower, lower+1, ..., higher), which must have at most 255 entries.  Call before the first qrmsa_tracegen_next. */
+int qrmsa_tracegen_set_randint_rates(qrmsa_tracegen *gen, int lower, int higher);
 /* Next n_requests of every env, arrays [n_requests][n_envs]; the clock persists across calls. */
 int qrmsa_tracegen_next(qrmsa_tracegen *gen, int n_requests, uint8_t *h_src, uint8_t *h_dst, uint8_t *h_rate,
                         float *h_arrival, float *h_holding, int n_threads);

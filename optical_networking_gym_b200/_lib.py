@@ -30,6 +30,7 @@ FLAG_DECIDED = 0x40000000
 FLAG_ACCEPTED = 0x20000000
 FLAG_BLOCKED_RESOURCES = 0x01000000   # rejected requests: the heuristic's blocked_due_to_resources
 FLAG_BLOCKED_OSNR = 0x02000000        # rejected requests: blocked_due_to_osnr
+FLAG_RELEASE_CANCELLED = 0x08000000   # accepted, release event dropped by reset(options={"only_episode_counters": True})
 FLAG_NEAR_TIE = 0x04000000            # highest-SNR policy: runner-up within 1e-6 dB of the chosen candidate
 POLICY_FIRST_FIT, POLICY_LOAD_BALANCING, POLICY_HIGHEST_SNR, POLICY_LB_FIRST_FIT = 0, 1, 2, 3
 POLICIES = {"first_fit": 0, "load_balancing": 1, "highest_snr": 2, "load_balancing_first_fit": 3}
@@ -90,6 +91,7 @@ SIGNATURES = {
     "qrmsa_set_staging": (_I, [_P, _I]),
     "qrmsa_enable_gsnr_log": (_I, [_P, _I]),
     "qrmsa_reset": (_I, [_P, _P]),
+    "qrmsa_cancel_pending_releases": (_I, [_P, _P]),
     "qrmsa_load_trace": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "qrmsa_load_trace_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "qrmsa_load_trace_host_strided": (_I, [_P, _P, _P, _P, _P, _P, _I, C.c_int64, _P]),
@@ -114,7 +116,9 @@ SIGNATURES = {
     "qrmsa_export_bitmaps": (_I, [_P, _I, _I, _P]),
     "qrmsa_export_link_list": (_I, [_P, _I, _I, _P, _I, C.POINTER(_I)]),
     "qrmsa_probe_gsnr": (_I, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_double)]),
+    "qrmsa_probe_qot": (_I, [_P, _I, _I, _I, _I, _I, _I, _P]),
     "qrmsa_tracegen_create": (_I, [_I, _U64, _I, _I, _P, C.c_double, _P, _P, _P, C.POINTER(_P)]),
+    "qrmsa_tracegen_set_randint_rates": (_I, [_P, _I, _I]),
     "qrmsa_tracegen_next": (_I, [_P, _I, _P, _P, _P, _P, _P, _I]),
     "qrmsa_tracegen_destroy": (None, [_P]),
 }

@@ -502,6 +502,15 @@ extern "C" int qrmsa_reset(qrmsa_ctx *ctx, void *stream) {
     return QRMSA_OK;
 }
 
+extern "C" int qrmsa_cancel_pending_releases(qrmsa_ctx *ctx, void *stream) {
+    if (!ctx) return QRMSA_ERR_ARG;
+    if (ctx->kp.n_req < 1) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    k_cancel_releases<<<(ctx->kp.n_envs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ctx->kp);
+    CK(cudaGetLastError());
+    return QRMSA_OK;
+}
+
 static int build_schedule(qrmsa_ctx *ctx, int n_requests, cudaStream_t st);
 
 extern "C" int qrmsa_load_trace(qrmsa_ctx *ctx, const uint8_t *d_src, const uint8_t *d_dst, const uint8_t *d_rate,
@@ -906,9 +915,9 @@ extern "C" int qrmsa_export_link_list(qrmsa_ctx *ctx, int env, int link, int32_t
     return QRMSA_OK;
 }
 
-extern "C" int qrmsa_probe_gsnr(qrmsa_ctx *ctx, int env, int src, int dst, int p, int initial_slot, int number_slots,
-                                double *h_gsnr_db) {
-    if (!ctx || !h_gsnr_db || env < 0 || env >= ctx->kp.n_envs) return QRMSA_ERR_ARG;
+extern "C" int qrmsa_probe_qot(qrmsa_ctx *ctx, int env, int src, int dst, int p, int initial_slot, int number_slots,
+                               double *h_gsnr_ase_nli_db) {
+    if (!ctx || !h_gsnr_ase_nli_db || env < 0 || env >= ctx->kp.n_envs) return QRMSA_ERR_ARG;
     const KParams &kp = ctx->kp;
     if (src < 0 || src >= kp.N || dst < 0 || dst >= kp.N || p < 0 || p >= kp.K || initial_slot < 0 ||
         number_slots < 1 || initial_slot + number_slots > kp.S)
@@ -918,6 +927,15 @@ extern "C" int qrmsa_probe_gsnr(qrmsa_ctx *ctx, int env, int src, int dst, int p
     if (rc) return rc;
     k_probe_gsnr<<<1, 32, kp.blob_bytes>>>(kp, env, src, dst, p, initial_slot, number_slots, (double *)ctx->stage);
     CK(cudaGetLastError());
-    CK(cudaMemcpy(h_gsnr_db, ctx->stage, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_gsnr_ase_nli_db, ctx->stage, 24, cudaMemcpyDeviceToHost));
     return QRMSA_OK;
+}
+
+extern "C" int qrmsa_probe_gsnr(qrmsa_ctx *ctx, int env, int src, int dst, int p, int initial_slot, int number_slots,
+                                double *h_gsnr_db) {
+    double v[3];
+    if (!h_gsnr_db) return QRMSA_ERR_ARG;
+    int rc = qrmsa_probe_qot(ctx, env, src, dst, p, initial_slot, number_slots, v);
+    if (!rc) *h_gsnr_db = v[0];
+    return rc;
 }

@@ -606,7 +606,7 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
     int err = 0;
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
         const uint4 rq = tr[head.id];
-        if (rq.w & QRMSA_FLAG_ACCEPTED) {
+        if ((rq.w & (QRMSA_FLAG_ACCEPTED | QRMSA_FLAG_RELEASE_CANCELLED)) == QRMSA_FLAG_ACCEPTED) {
             err |= release_service(dm, p, t, bm, lists, pos, rq, lane, pt);
             n_rel += 1;
         }
@@ -2228,6 +2228,21 @@ __global__ void k_count_decisions(const KParams p) {
     flush();
 }
 
+// reset(options={"only_episode_counters": True}) empties the release heap (qrmsa.pyx:433): every accepted service whose
+// schedule entry is still ahead of the release pointer stays in the network for good.  One warp per env.
+__global__ void k_cancel_releases(const KParams p) {
+    const int lane = threadIdx.x & 31;
+    const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= p.n_envs) return;
+    const int4 st = p.estate[env];
+    uint4 *tr = p.trace + (size_t)env * p.T;
+    const unsigned long long *perm = p.perm + (size_t)env * p.T;
+    for (int i = st.y + lane; i < p.n_req; i += 32) {
+        const int id = (int)(unsigned)perm[i];
+        if (id < st.x && (tr[id].w & QRMSA_FLAG_ACCEPTED)) tr[id].w |= QRMSA_FLAG_RELEASE_CANCELLED;
+    }
+}
+
 // calculate_osnr for a hypothetical channel on one env (core/osnr.pyx:21-142); one warp.
 __global__ void k_probe_gsnr(const KParams p, const int env, const int src, const int dst, const int pi, const int s,
                              const int n, double *out) {
@@ -2247,13 +2262,16 @@ __global__ void k_probe_gsnr(const KParams p, const int env, const int src, cons
     int ncls = -1;
     for (int i = 0; i < p.R * p.M; ++i)
         if (t.need(i) == n) ncls = t.cls(i);
-    double g = nan("");
+    double g = nan(""), g_ase = nan(""), g_nli = nan("");
     if (ncls >= 0 && hops > 0) {
         uint32_t terms = 0;
-        g = -10.0 * log10(gn_base(p, t, path, s, n, ncls).with(
-            gn_neighbours(Dim<0, 0, 0>(p), t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms)));
+        const GnBase gb = gn_base(p, t, path, s, n, ncls);
+        const double acc = gb.with(gn_neighbours(Dim<0, 0, 0>(p), t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms));
+        g = -10.0 * log10(acc);                  // total, ASE-only and NLI-only figures (osnr.pyx:133-140)
+        g_ase = -10.0 * log10(gb.ase);
+        g_nli = -10.0 * log10(acc - gb.ase);
     }
-    if (lane == 0) *out = g;
+    if (lane == 0) { out[0] = g; out[1] = g_ase; out[2] = g_nli; }
 }
 
 }  // namespace qrmsa

@@ -6,7 +6,7 @@
 //     at  = float32(current_time + expovariate(1/mean_iat));  current_time = at
 //     ht  = float32(expovariate(1/mean_holding))
 //     src = choices(nodes, weights)            dst = choices(nodes, weights with src zeroed, renormalised)
-//     bit_rate = choices(bit_rates, probs, k=1)
+//     bit_rate = choices(bit_rates, probs, k=1)        ("continuous": randint(lower, higher), qrmsa.pyx:246-254)
 // This file restates the published algorithms those stdlib calls use so that a batch of envs can
 // replay "a request trace the reference generated from the same seeds" without 10^6 draws/s
 // CPython in the loop:
@@ -103,6 +103,7 @@ struct qrmsa_tracegen {
     std::vector<double> now;       // env clock (a float32 value held in a double, qrmsa.pyx:179)
     std::vector<double> lam_iat;   // 1 / mean_service_inter_arrival_time
     std::vector<double> src_cum, dst_cum, rate_cum;
+    int randint_n = 0, randint_bits = 0;   // continuous bit rates: randint(lower, higher) -> _randbelow(higher - lower + 1)
 };
 
 extern "C" int qrmsa_tracegen_create(int n_envs, uint64_t base_seed, int n_nodes, int n_rates, const double *h_load,
@@ -131,6 +132,14 @@ extern "C" int qrmsa_tracegen_create(int n_envs, uint64_t base_seed, int n_nodes
     return QRMSA_OK;
 }
 
+extern "C" int qrmsa_tracegen_set_randint_rates(qrmsa_tracegen *g, int lower, int higher) {
+    if (!g || lower < 0 || higher < lower || higher - lower + 1 > 255) return QRMSA_ERR_ARG;
+    g->randint_n = higher - lower + 1;
+    g->randint_bits = 0;
+    for (int n = g->randint_n; n; n >>= 1) g->randint_bits++;   // n.bit_length()
+    return QRMSA_OK;
+}
+
 extern "C" int qrmsa_tracegen_next(qrmsa_tracegen *g, int n_requests, uint8_t *h_src, uint8_t *h_dst, uint8_t *h_rate,
                                    float *h_arrival, float *h_holding, int n_threads) {
     if (!g || n_requests < 0 || !h_src || !h_dst || !h_rate || !h_arrival || !h_holding) return QRMSA_ERR_ARG;
@@ -155,7 +164,16 @@ extern "C" int qrmsa_tracegen_next(qrmsa_tracegen *g, int n_requests, uint8_t *h
                     int s = bisect_right(g->src_cum.data(), rng.random() * (g->src_cum[N - 1] + 0.0), 0, N - 1);
                     const double *dc = g->dst_cum.data() + (size_t)s * N;
                     int d = bisect_right(dc, rng.random() * (dc[N - 1] + 0.0), 0, N - 1);
-                    int br = bisect_right(g->rate_cum.data(), rng.random() * (g->rate_cum[R - 1] + 0.0), 0, R - 1);
+                    int br;
+                    if (g->randint_n) {
+                        // Random.randint(a, b) = a + _randbelow_with_getrandbits(b - a + 1): k = n.bit_length();
+                        // r = getrandbits(k) (one 32-bit output, top k bits) until r < n
+                        uint32_t r32;
+                        do { r32 = rng.next32() >> (32 - g->randint_bits); } while (r32 >= (uint32_t)g->randint_n);
+                        br = (int)r32;
+                    } else {
+                        br = bisect_right(g->rate_cum.data(), rng.random() * (g->rate_cum[R - 1] + 0.0), 0, R - 1);
+                    }
                     const size_t o = row + e;
                     h_arrival[o] = at; h_holding[o] = ht;
                     h_src[o] = (uint8_t)s; h_dst[o] = (uint8_t)d; h_rate[o] = (uint8_t)br;

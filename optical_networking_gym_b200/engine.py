@@ -101,6 +101,10 @@ class Engine:
         check(self.lib.qrmsa_reset(self._h, self._stream(stream)), self._h)
         self.n_loaded = 0
 
+    def cancel_pending_releases(self, stream=None):
+        """The `self._events = []` of reset(options={"only_episode_counters": True}) (qrmsa.pyx:433)."""
+        check(self.lib.qrmsa_cancel_pending_releases(self._h, self._stream(stream)), self._h)
+
     def load_trace_host(self, src, dst, rate, arrival, holding, stream=None):
         """Host arrays shaped [n_requests, n_envs] (request-major)."""
         arrs = [np.ascontiguousarray(src, np.uint8), np.ascontiguousarray(dst, np.uint8),
@@ -278,6 +282,13 @@ class Engine:
         check(self.lib.qrmsa_probe_gsnr(self._h, int(env), int(src), int(dst), int(p), int(initial_slot),
                                         int(number_slots), C.byref(g)), self._h)
         return g.value
+
+    def probe_qot(self, env: int, src: int, dst: int, p: int, initial_slot: int, number_slots: int):
+        """(GSNR, ASE-only, NLI-only) in dB for a hypothetical channel: the three values of core.osnr.calculate_osnr."""
+        v = np.zeros(3, np.float64)
+        check(self.lib.qrmsa_probe_qot(self._h, int(env), int(src), int(dst), int(p), int(initial_slot),
+                                       int(number_slots), _np_ptr(v)), self._h)
+        return float(v[0]), float(v[1]), float(v[2])
 
     def _sync(self, stream=None):
         import torch

@@ -20,8 +20,11 @@ harness patches in reproduces *that* run bit for bit.
 (qrmsa.pyx:583-781) from the device kernel `qrmsa_observation`; with `gen_observation=False` both are zeros, as in
 the reference (qrmsa.pyx:584-587).
 
-Not implemented yet (SURVEY §8f "next" rows): `measure_disruptions`, `defragmentation`, `bands`, continuous bit
-rates, per-service CSV; they raise.
+`file_name=` writes the reference's per-service CSV (qrmsa.pyx:387-406, :967-990); `bit_rate_selection="continuous"`
+draws `rng.randint(lower, higher)` like the reference (qrmsa.pyx:246-254); `reset(options={"only_episode_counters":
+True})` restarts the episode counters on the live network and drops the pending release events (qrmsa.pyx:433, :461-464).
+
+Not implemented (SURVEY §8f "next" rows): `measure_disruptions`, `defragmentation`, `bands`; they raise.
 """
 from __future__ import annotations
 
@@ -101,8 +104,17 @@ def _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, 
         _unsupported("defragmentation=True")
     if bands:
         _unsupported("bands (multiband)")
-    if bit_rate_selection != "discrete":
-        _unsupported("bit_rate_selection='continuous'")
+    if bit_rate_selection not in ("discrete", "continuous"):
+        raise ValueError("bit_rate_selection must be 'discrete' or 'continuous'")
+
+
+def _continuous_rates(lower, higher):
+    """bit_rate_selection="continuous": rng.randint(int(lower), int(higher)) (qrmsa.pyx:246-254) -- integer rates, i.e.
+    the table (lower, lower+1, ..., higher) indexed by (rate - lower)."""
+    lo, hi = int(lower), int(higher)
+    if lo < 1 or hi < lo or hi - lo + 1 > 255:
+        raise ValueError("continuous bit rates: need 1 <= lower <= higher and at most 255 integer rates")
+    return tuple(range(lo, hi + 1)), (lo, hi)
 
 
 class _Common:
@@ -166,8 +178,10 @@ class QRMSAEnv(_Common):
         _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, bit_rate_selection)
         if seed is not None and not isinstance(seed, (int, np.integer)):
             raise ValueError("Seed must be an integer.")                       # qrmsa.pyx:342
-        if file_name:
-            _unsupported("per-service CSV (file_name)")
+        self.bit_rate_selection = bit_rate_selection
+        randint_rates = None
+        if bit_rate_selection == "continuous":
+            bit_rates, randint_rates = _continuous_rates(bit_rate_lower_bound, bit_rate_higher_bound)
         self._setup(topology, num_spectrum_resources, bit_rates, launch_power_dbm, margin, frequency_start,
                     frequency_slot_bandwidth, channel_width, k_paths, modulations_to_consider, bandwidth)
         self.episode_length = int(episode_length)
@@ -179,9 +193,24 @@ class QRMSAEnv(_Common):
         tb = self.tables
         self._gen = TraceGenerator(1, tb.n_nodes, tb.n_rates, self.load, self.mean_service_holding_time,
                                    base_seed=self.input_seed, node_request_probabilities=node_request_probabilities,
-                                   bit_rate_probabilities=bit_rate_probabilities, n_threads=1)
-        self._eng = Engine(tb, 1, max(self.episode_length, 2), device=device)
+                                   bit_rate_probabilities=bit_rate_probabilities, n_threads=1, randint_rates=randint_rates)
+        # the device holds the next `_horizon` requests of the stream: one episode plus head-room for episodes that are
+        # continued on the live network by reset(options={"only_episode_counters": True})
+        self._horizon = int(min(16384, max(4 * self.episode_length, self.episode_length + 1, 2)))
+        self._eng = Engine(tb, 1, self._horizon, device=device)
         self._eng.enable_gsnr_log(True)
+        self._running = []           # release keys of the running services (active_services column of the CSV)
+        self.file_stats = None
+        if file_name != "":          # qrmsa.pyx:387-406
+            name = str(self.topology.graph["name"]) if self.topology is not None else "topology"
+            self.final_file_name = "_".join([file_name, name, str(self.launch_power_dbm), str(self.load), str(seed) + ".csv"])
+            d = os.path.dirname(self.final_file_name)
+            if d and not os.path.exists(d):
+                os.makedirs(d, exist_ok=True)
+            self.file_stats = open(self.final_file_name, "wt", encoding="UTF-8")
+            self.file_stats.write("# Service stats file from simulator\n")
+            self.file_stats.write("id,source,destination,bit_rate,path_k,path_length,modulation,min_osnr,osnr,ase,nli,"
+                                  "disrupted_services,active_services\n")
         self._block = None
         self._cur = 0
         self.current_time = 0.0
@@ -220,13 +249,16 @@ class QRMSAEnv(_Common):
     def _service_from_block(self, i: int) -> Service:
         b = self._block
         src, dst = int(b[0][i]), int(b[1][i])
-        return Service(service_id=i, source=self._nodes[src], source_id=src, destination=self._nodes[dst],
+        # service_id = episode_services_processed when the request is drawn (qrmsa.pyx:1092): the index within the episode
+        return Service(service_id=self.episode_services_processed, source=self._nodes[src], source_id=src, destination=self._nodes[dst],
                        destination_id=dst, arrival_time=b[3][i], holding_time=b[4][i],
                        bit_rate=self.bit_rates[int(b[2][i])])
 
     def _account_new_service(self):
         svc = self.current_service
         self.current_time = svc.arrival_time
+        now = np.float32(svc.arrival_time)            # releases due at the new request's arrival (qrmsa.pyx:1113-1122)
+        self._running = [k for k in self._running if not (k <= now)]
         self.services_processed += 1
         self.episode_services_processed += 1
         self.bit_rate_requested += svc.bit_rate
@@ -234,9 +266,20 @@ class QRMSAEnv(_Common):
 
     def reset(self, seed=None, options=None):
         """qrmsa.pyx:427-504.  Wipes the network, keeps the clock and the request stream running."""
+        self.episode_services_processed = self.episode_services_accepted = 0
+        self.episode_bit_rate_requested = self.episode_bit_rate_provisioned = 0.0
+        self.bl_resource = self.bl_osnr = self.bl_reject = 0
+        self.episode_modulation_histogram = {int(se): 0 for se in self.tables.mod_se}
         if options is not None and options.get("only_episode_counters"):
-            _unsupported("reset(options={'only_episode_counters': True})")
-        L = self.episode_length
+            # qrmsa.pyx:433, :461-464: counters restart, the network and the current request stay -- and because the
+            # reference empties its release heap here, the services running now are never released
+            if self._block is None:
+                raise RuntimeError("reset(options={'only_episode_counters': True}) before the first full reset")
+            self._eng.cancel_pending_releases()
+            self._running = []
+            obs, _ = self._observation()
+            return obs, {}
+        L = self._horizon
         if self._block is None:
             leftover = [np.zeros(0, a) for a in (np.uint8, np.uint8, np.uint8, np.float32, np.float32)]
         else:  # requests generated but never made current keep their place in the stream
@@ -247,11 +290,8 @@ class QRMSAEnv(_Common):
         self._eng.reset()
         self._eng.load_trace_host(*[np.ascontiguousarray(a[:, None]) for a in self._block])
         self._cur = 0
-        self.episode_services_processed = self.episode_services_accepted = 0
-        self.episode_bit_rate_requested = self.episode_bit_rate_provisioned = 0.0
+        self._running = []
         self.bit_rate_requested = self.bit_rate_provisioned = 0.0            # :466-467 (full reset)
-        self.bl_resource = self.bl_osnr = self.bl_reject = 0
-        self.episode_modulation_histogram = {int(se): 0 for se in self.tables.mod_se}
         self.current_service = self._service_from_block(0)
         self._account_new_service()
         obs, mask = self._observation()
@@ -290,6 +330,9 @@ class QRMSAEnv(_Common):
             n = int(tb.slots_needed[int(self._block[2][self._cur]) * tb.n_mods + modulation_idx])
             svc.accepted = True
             svc.OSNR = gsnr
+            ase, nli = self._eng.ase_nli_host(self._cur, 1)                    # osnr.pyx:133-140, stored at :930-932
+            svc.ASE, svc.NLI = float(ase[0, 0]), float(nli[0, 0])
+            self._running.append(np.float32(np.float32(svc.arrival_time) + np.float32(svc.holding_time)))   # :1327-1330
             svc.initial_slot, svc.number_slots = initial_slot, n
             svc.center_frequency = (self.frequency_start + (self.frequency_slot_bandwidth * initial_slot)
                                     + (self.frequency_slot_bandwidth * (n / 2.0)))
@@ -306,6 +349,21 @@ class QRMSAEnv(_Common):
         else:
             svc.accepted = False
             self.bl_reject += 1
+        if self.file_stats is not None:                                        # qrmsa.pyx:967-990
+            line = "{},{},{},{},".format(svc.service_id, svc.source_id, svc.destination_id, svc.bit_rate)
+            if svc.accepted:
+                if self.k_shortest_paths is not None:
+                    pk, plen = svc.path.k, svc.path.length
+                    se, mo = svc.current_modulation.spectral_efficiency, svc.current_modulation.minimum_osnr
+                else:
+                    pk = route
+                    plen = float(tb.path_length_km[tb.path_index(svc.source_id, int(svc.destination_id), route)])
+                    se, mo = int(tb.mod_se[modulation_idx]), float(tb.mod_min_osnr[modulation_idx])
+                line += "{},{},{},{},{},{},{},{},{}".format(pk, plen, se, mo, svc.OSNR, svc.ASE, svc.NLI, 0, len(self._running))
+            else:
+                line += "-1,-1,-1,-1,-1,-1,-1,-1,-1"
+            self.file_stats.write(line + "\n")
+            self.file_stats.flush()
         info = {
             "episode_services_accepted": self.episode_services_accepted,
             "service_blocking_rate": 0.0, "episode_service_blocking_rate": 0.0,
@@ -329,10 +387,12 @@ class QRMSAEnv(_Common):
             info["modulation_{}".format(str(float(se)))] = self.episode_modulation_histogram.get(int(se), 0)
         # next request (qrmsa.pyx:1052-1054)
         self._cur += 1
+        if self._cur >= len(self._block[0]) - 1:
+            raise RuntimeError(f"the {self._horizon} requests loaded on the device are used up (episodes continued with "
+                               "reset(options={'only_episode_counters': True})); a full reset() attaches the next ones")
         self.current_service = self._service_from_block(self._cur)
         self._account_new_service()
         terminated = self.episode_services_processed == self.episode_length
-        assert terminated == bool(self._t_term[0])
         if terminated:
             info["blocked_due_to_resources"] = self.bl_resource
             info["blocked_due_to_osnr"] = self.bl_osnr
@@ -412,18 +472,19 @@ class QRMSAEnv(_Common):
         return self._eng.export_link_list(0, link_index)
 
     def calculate_osnr(self, service):
-        """core.osnr.calculate_osnr(env, service) for the candidate written on `service` (path, initial_slot,
-        number_slots); returns (gsnr_dB, None, None) -- ASE-only / NLI-only figures are not produced."""
-        svc = self.current_service
-        paths = self.k_shortest_paths[svc.source, svc.destination]
+        """core.osnr.calculate_osnr(env, service) (osnr.pyx:21-142) for the candidate written on `service` (path,
+        initial_slot, number_slots): (GSNR, ASE-only, NLI-only) in dB."""
+        paths = self.k_shortest_paths[service.source, service.destination]
         p = next(i for i, pth in enumerate(paths) if pth is service.path)
-        g = self._eng.probe_gsnr(0, svc.source_id, int(svc.destination_id), p, service.initial_slot,
-                                 service.number_slots)
-        return g, None, None
+        return self._eng.probe_qot(0, service.source_id, int(service.destination_id), p, service.initial_slot,
+                                   service.number_slots)
 
     def close(self):
         self._eng.close()
         self._gen.close()
+        if self.file_stats is not None:
+            self.file_stats.close()
+            self.file_stats = None
 
 
 def calculate_osnr(env, service):
@@ -453,6 +514,8 @@ class BatchedQRMSAEnv(_Common):
                  gen_observation: bool = False, bands=None, device: int = 0, n_groups: int = 1, n_threads: int = 0,
                  request_source: str = "replay", env_offset: int = 0):
         _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, bit_rate_selection)
+        if bit_rate_selection != "discrete":
+            _unsupported("bit_rate_selection='continuous' on BatchedQRMSAEnv (QRMSAEnv supports it)")
         self._setup(topology, num_spectrum_resources, bit_rates, launch_power_dbm, margin, frequency_start,
                     frequency_slot_bandwidth, channel_width, k_paths, modulations_to_consider, bandwidth)
         import torch

@@ -43,7 +43,9 @@ class TraceGenerator:
 
     def __init__(self, n_envs: int, n_nodes: int, n_rates: int, load, mean_holding_time: float = 10800.0,
                  base_seed: int = 50, node_request_probabilities=None, bit_rate_probabilities=None,
-                 n_threads: int = 0):
+                 n_threads: int = 0, randint_rates=None):
+        """randint_rates=(lower, higher): bit_rate_selection="continuous" -- the rate index drawn is
+        rng.randint(lower, higher) - lower (qrmsa.pyx:246-254) instead of a choice among n_rates."""
         self.lib = _lib.load()
         self.n_envs = int(n_envs)
         self.n_threads = int(n_threads)
@@ -54,6 +56,8 @@ class TraceGenerator:
                                              load.ctypes.data, float(mean_holding_time), src_cum.ctypes.data,
                                              dst_cum.ctypes.data, rate_cum.ctypes.data, C.byref(h)))
         self._h = h
+        if randint_rates is not None:
+            check(self.lib.qrmsa_tracegen_set_randint_rates(self._h, int(randint_rates[0]), int(randint_rates[1])))
 
     def next(self, n_requests: int, out: Optional[Sequence[np.ndarray]] = None):
         """Next n_requests requests of every env.  `out` may hold 5 preallocated (e.g. pinned) arrays."""

@@ -55,6 +55,7 @@ def lib():
         _lib.orc_step_action.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int), C.c_int]
         _lib.orc_get_slots.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_reset_episode_counters.argtypes = [C.c_void_p]
         _lib.orc_observation.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         _lib.orc_get_link_list.restype = C.c_int
         _lib.orc_get_link_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -152,6 +153,10 @@ class OracleEnv:
         st = lib().orc_step_action(self._h, int(action), C.byref(rw), C.byref(g), C.byref(term), int(episode_length))
         return st, rw.value, g.value, bool(term.value)
 
+    def reset_episode_counters(self):
+        """reset(options={"only_episode_counters": True}): pending releases dropped, network and request kept."""
+        lib().orc_reset_episode_counters(self._h)
+
     def observation(self):
         """(obs float32[1+2+k+12kM], mask uint8[kMS+1]) for the current request (gen_observation=True mode)."""
         tb = self.tables
@@ -196,7 +201,7 @@ class OracleEnv:
 #   choices(bit_rates, probs, k=1)
 # ------------------------------------------------------------------------------------------------
 def generate_trace_python(n_nodes: int, n_rates: int, load: float, mean_holding: float, seed: int, n_requests: int,
-                          start_time: float = 0.0, rng=None):
+                          start_time: float = 0.0, rng=None, randint_rates=None):
     import random
 
     rng = rng if rng is not None else random.Random(seed)
@@ -220,7 +225,10 @@ def generate_trace_python(n_nodes: int, n_rates: int, load: float, mean_holding:
         w2[s] = 0.0
         w2 /= np.sum(w2)
         d = rng.choices(nodes, weights=w2)[0]
-        r = rng.choices(list(range(n_rates)), probs, k=1)[0]
+        if randint_rates is not None:      # bit_rate_selection="continuous": rng.randint(lower, higher) (qrmsa.pyx:246-254)
+            r = rng.randint(int(randint_rates[0]), int(randint_rates[1])) - int(randint_rates[0])
+        else:
+            r = rng.choices(list(range(n_rates)), probs, k=1)[0]
         src[i], dst[i], rate[i], arrival[i], holding[i] = s, d, r, at, ht
     return dict(src=src, dst=dst, rate=rate, arrival=arrival, holding=holding), rng, now
 

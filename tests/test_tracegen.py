@@ -95,3 +95,18 @@ def test_skewed_bit_rate_mix_vs_reference():
     for i, k in enumerate(TRACE_KEYS):
         assert np.array_equal(out[i][:, 0], g[k]), k
     assert abs((g["rate"] == 0).mean() - 0.5) < 0.05
+
+
+def test_randint_rates_vs_cpython():
+    """bit_rate_selection="continuous" (qrmsa.pyx:246-254): the fifth draw of a request is rng.randint(lower, higher),
+    restated in csrc/tracegen.cpp (_randbelow_with_getrandbits) and checked against CPython's own random.Random."""
+    from oracle import oracle as orc
+
+    g = TraceGenerator(4, 14, 76, 210.0, base_seed=321, n_threads=1, randint_rates=(25, 100))
+    tr = g.next(400)
+    for e in range(4):
+        ref, _, _ = orc.generate_trace_python(14, 76, 210.0, 10800.0, 321 + e, 400, randint_rates=(25, 100))
+        for k, a in zip(("src", "dst", "rate", "arrival", "holding"), tr):
+            assert np.array_equal(ref[k], a[:, e]), (e, k)
+    assert tr[2].min() >= 0 and tr[2].max() <= 75
+    g.close()
