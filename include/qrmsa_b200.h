@@ -83,6 +83,9 @@ enum {
     QRMSA_CNT_ERRORS = 15,        /* envs that hit an error state (list overflow, ValueError path)   */
     QRMSA_CNT_MOD_HIST = 16,      /* [16..23] accepted services per modulation index                 */
     QRMSA_CNT_GN_PRUNED = 24,     /* QoT checks refused on the empty-network bound without a GN sum   */
+    QRMSA_CNT_DISRUPTED = 25,     /* disrupted_services           (qrmsa.pyx:937-952)                */
+    QRMSA_CNT_DEFRAG_CYCLES = 26, /* episode_defrag_cicles        (qrmsa.pyx:1546)                   */
+    QRMSA_CNT_REALLOCATIONS = 27, /* episode_service_realocations (qrmsa.pyx:1635)                   */
     QRMSA_N_COUNTERS = 32
 };
 
@@ -93,6 +96,7 @@ enum {
 #define QRMSA_FLAG_ACCEPTED 0x20000000u
 #define QRMSA_FLAG_BLOCKED_RESOURCES 0x01000000u /* rejected: the heuristic's blocked_due_to_resources (heuristics.py:966) */
 #define QRMSA_FLAG_BLOCKED_OSNR 0x02000000u      /* rejected: blocked_due_to_osnr                                     */
+#define QRMSA_FLAG_DISRUPTED 0x10000000u        /* in disrupted_services_list: GSNR fell below minimum_osnr (qrmsa.pyx:937-952) */
 #define QRMSA_FLAG_RELEASE_CANCELLED 0x08000000u /* accepted, but its release event was dropped (qrmsa.pyx:433, :461-464)  */
 #define QRMSA_FLAG_NEAR_TIE 0x04000000u          /* highest-SNR policy: a runner-up within 1e-6 dB of the chosen candidate */
 
@@ -129,6 +133,22 @@ int qrmsa_set_groups(qrmsa_ctx *ctx, int n_groups);
  * is what a configuration with larger tables gets by itself, and is how tests hold the variants to each other.
  */
 int qrmsa_set_staging(qrmsa_ctx *ctx, int level);
+/*
+ * Replaces: the constructor switches measure_disruptions / defragmentation / n_defrag_services (envs/qrmsa.pyx:206-237).
+ *   measure_disruptions  after every accepted service, each running service on the links of its path that is not yet
+ *                        marked disrupted is re-evaluated against all current channels; GSNR below its modulation's
+ *                        minimum_osnr (no margin) marks it (QRMSA_FLAG_DISRUPTED) and counts it once (qrmsa.pyx:937-952)
+ *   defragmentation      after every release -- every n_defrag_services-th processed request, or every one when 0 --
+ *                        each running service, in provisioning order, moves to the lowest valid start below its own
+ *                        where its GSNR still meets minimum_osnr (qrmsa.pyx:1113-1122, :1545-1639); the start slot in
+ *                        its action word changes with it
+ * Applies to qrmsa_step_action and to the first-fit policy of qrmsa_step_heuristic (a general-dimension kernel: these
+ * switches cost 10-100x per request, as they do in the reference).  Not combinable with qrmsa_cancel_pending_releases.
+ */
+int qrmsa_set_features(qrmsa_ctx *ctx, int measure_disruptions, int defragmentation, int n_defrag_services);
+/* Services found disrupted by the LAST decided request of every env (the disrupted_services column of the per-service
+ * CSV, qrmsa.pyx:983): int32 [n_envs]; needs measure_disruptions. */
+int qrmsa_get_step_disrupted_host(qrmsa_ctx *ctx, int32_t *h_out, void *stream);
 /* Keep a per-request GSNR log (double, [n_envs][max_requests]); off by default. */
 int qrmsa_enable_gsnr_log(qrmsa_ctx *ctx, int enable);
 

@@ -30,6 +30,7 @@ FLAG_DECIDED = 0x40000000
 FLAG_ACCEPTED = 0x20000000
 FLAG_BLOCKED_RESOURCES = 0x01000000   # rejected requests: the heuristic's blocked_due_to_resources
 FLAG_BLOCKED_OSNR = 0x02000000        # rejected requests: blocked_due_to_osnr
+FLAG_DISRUPTED = 0x10000000            # the service's GSNR fell below its modulation's minimum_osnr (measure_disruptions)
 FLAG_RELEASE_CANCELLED = 0x08000000   # accepted, release event dropped by reset(options={"only_episode_counters": True})
 FLAG_NEAR_TIE = 0x04000000            # highest-SNR policy: runner-up within 1e-6 dB of the chosen candidate
 POLICY_FIRST_FIT, POLICY_LOAD_BALANCING, POLICY_HIGHEST_SNR, POLICY_LB_FIRST_FIT = 0, 1, 2, 3
@@ -89,6 +90,8 @@ SIGNATURES = {
     "qrmsa_destroy": (None, [_P]),
     "qrmsa_set_groups": (_I, [_P, _I]),
     "qrmsa_set_staging": (_I, [_P, _I]),
+    "qrmsa_set_features": (_I, [_P, _I, _I, _I]),
+    "qrmsa_get_step_disrupted_host": (_I, [_P, _P, _P]),
     "qrmsa_enable_gsnr_log": (_I, [_P, _I]),
     "qrmsa_reset": (_I, [_P, _P]),
     "qrmsa_cancel_pending_releases": (_I, [_P, _P]),

@@ -206,7 +206,13 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
         W1[l] = t->link_n_spans[l] * leff[l];
         W2[l] = -(t->link_n_spans[l] * leff[l] * (5.0 / 3.0) * (leff[l] / len));  // stored negated
     }
-    for (int m = 0; m < M; m++) kp.mod_thr_nomargin[m] = t->mod_min_osnr[m];
+    for (int m = 0; m < M; m++) {
+        kp.mod_thr_nomargin[m] = t->mod_min_osnr[m];
+        kp.acct0[m] = pow(10.0, -t->mod_min_osnr[m] / 10.0);                  // gsnr < minimum_osnr  <=>  acc > acct0
+        kp.acct0_lo[m] = pow(10.0, -(t->mod_min_osnr[m] + 1e-3) / 10.0);
+        kp.acct0_hi[m] = pow(10.0, -(t->mod_min_osnr[m] - 1e-3) / 10.0);
+    }
+    kp.feat = 0; kp.n_defrag = 0; kp.step_disrupted = nullptr;
     for (int m = 0; m < M; m++) {
         // accept iff gsnr_dB >= thr (heuristics.py:957-958)  <=>  acc = 1/GSNR <= 10^(-thr/10);
         // near-threshold flag: |gsnr_dB - thr| < 1e-3 dB
@@ -480,6 +486,34 @@ extern "C" int qrmsa_set_groups(qrmsa_ctx *ctx, int n_groups) {
     return QRMSA_OK;
 }
 
+extern "C" int qrmsa_set_features(qrmsa_ctx *ctx, int measure_disruptions, int defragmentation, int n_defrag_services) {
+    if (!ctx || n_defrag_services < 0) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    KParams &kp = ctx->kp;
+    kp.feat = (measure_disruptions ? 1 : 0) | (defragmentation ? 2 : 0);
+    kp.n_defrag = n_defrag_services;
+    if ((kp.feat & 1) && !kp.step_disrupted) {
+        int rc = dev_alloc(ctx, &kp.step_disrupted, (size_t)kp.n_envs);
+        if (rc) return rc;
+        CK(cudaMemset(kp.step_disrupted, 0, sizeof(int) * (size_t)kp.n_envs));
+    }
+    if (kp.feat) {
+        CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+        CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+        CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
+    }
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_get_step_disrupted_host(qrmsa_ctx *ctx, int32_t *h_out, void *stream) {
+    if (!ctx || !h_out) return QRMSA_ERR_ARG;
+    if (!ctx->kp.step_disrupted) { ctx->err = "measure_disruptions is not enabled"; return QRMSA_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(h_out, ctx->kp.step_disrupted, sizeof(int32_t) * (size_t)ctx->kp.n_envs, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return QRMSA_OK;
+}
+
 extern "C" int qrmsa_enable_gsnr_log(qrmsa_ctx *ctx, int enable) {
     if (!ctx) return QRMSA_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -504,6 +538,7 @@ extern "C" int qrmsa_reset(qrmsa_ctx *ctx, void *stream) {
 
 extern "C" int qrmsa_cancel_pending_releases(qrmsa_ctx *ctx, void *stream) {
     if (!ctx) return QRMSA_ERR_ARG;
+    if (ctx->kp.feat) { ctx->err = "not combinable with measure_disruptions / defragmentation"; return QRMSA_ERR_UNSUPPORTED; }
     if (ctx->kp.n_req < 1) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
     k_cancel_releases<<<(ctx->kp.n_envs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ctx->kp);
@@ -668,7 +703,16 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
     kp.smem_warp_stride = bsm ? ctx->warp_stride_bms : ctx->warp_stride_ring;
     // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
     const bool c320 = kp.S == 320 && kp.M == 6 && kp.K == 5, c640 = kp.S == 640 && kp.M == 6 && kp.K == 5;
-    if (policy == QRMSA_POLICY_FIRST_FIT) {
+    if (kp.feat && policy != QRMSA_POLICY_FIRST_FIT) {
+        ctx->err = "measure_disruptions / defragmentation are built for the first-fit policy and for qrmsa_step_action";
+        return QRMSA_ERR_UNSUPPORTED;
+    }
+    if (policy == QRMSA_POLICY_FIRST_FIT && kp.feat) {
+        CK(cudaMemsetAsync(kp.work, 0, 4, st));
+        if (kp.feat == 1) k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 0, 1><<<g, th, sm, st>>>(kp, n_steps);
+        else if (kp.feat == 2) k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 0, 2><<<g, th, sm, st>>>(kp, n_steps);
+        else k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 0, 3><<<g, th, sm, st>>>(kp, n_steps);
+    } else if (policy == QRMSA_POLICY_FIRST_FIT) {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
         if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_FIRST_FIT, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else if (c320) k_step_policy<320, 6, 5, POLICY_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);

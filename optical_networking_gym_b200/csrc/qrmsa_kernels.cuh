@@ -63,6 +63,9 @@ struct KParams {
     int n_envs, N, E, K, M, Mc, R, S, W, RW, Hmax, NC, D, CAP, T, n_req, group_size;
     uint32_t sentinel;          // list filler record: class NC (all-zero G row, PHIN 0) -> contributes exactly 0
     double mod_thr_nomargin[8];  // Modulation.minimum_osnr (no margin): the observation's threshold (qrmsa.pyx:743-758)
+    double acct0[8], acct0_lo[8], acct0_hi[8];   // 10^(-minimum_osnr/10) and its +-1e-3 dB band: disruption / defragmentation test
+    int feat, n_defrag;          // bit 0 measure_disruptions, bit 1 defragmentation; n_defrag_services (qrmsa.pyx:206-237)
+    int *step_disrupted;         // [n_envs] services found disrupted by the last decided request (nullable)
     int need_monotone;  // slots_needed never decreases as the modulation index falls (true for SE-sorted tables)
     // static tables in global memory
     const uint8_t *path_hops;   // [N*N*K]
@@ -352,8 +355,13 @@ __device__ __forceinline__ GnBase gn_base(const KParams &p, const Tab &t, int pa
     return gn_base(p, t, __ldg(p.path_gn + path), s, n, ncls);
 }
 
-// one channel record against a candidate centred at c2 half-slots (core/osnr.pyx:64-94, table form)
-__device__ __forceinline__ void gn_term(const Tab &t, const int D, const uint32_t rec, const int c2, double &s1, double &s2) {
+// one channel record against a candidate centred at c2 half-slots (core/osnr.pyx:64-94, table form).
+// SKIP: the candidate is a service that is already in the lists (measure_disruptions, defragment); its own record
+// (centre and width in `self_key`) is left out, as calculate_osnr skips the service's own id (osnr.pyx:64-66)
+template <bool SKIP = false>
+__device__ __forceinline__ void gn_term(const Tab &t, const int D, const uint32_t rec, const int c2, double &s1, double &s2,
+                                        const uint32_t self_key = 0u) {
+    if (SKIP && (rec & 0xfffffu) == self_key) return;
     const int d = abs((int)(rec & 0xfffu) - c2);
     // INV[d] and G[class][d] from one scaled index: a_inv = base + 8 d, a_g = a_inv + (class + 1) * 8 D
     const uint32_t a_inv = t.sb + 8u * (uint32_t)d;
@@ -370,9 +378,9 @@ __device__ __forceinline__ void gn_term(const Tab &t, const int D, const uint32_
 // to the lanes in one flat sequence: lane t of pass b takes group b + t, which belongs to the hop whose group range
 // [start, end) contains it.  A typical path (4 hops x 28 channels = 30 groups) is one pass with every lane busy.
 // Lists are padded with the zero-contribution filler record, so the last group of a link needs no bounds test.
-template <class DM>
+template <class DM, bool SKIP = false>
 __device__ __forceinline__ double gn_neighbours(const DM &dm, const Tab &t, const uint32_t *lists, int hops, int mylink, int mycnt,
-                                                int c2, int lane, uint32_t &terms) {
+                                                int c2, int lane, uint32_t &terms, const uint32_t self_key = 0u) {
     const int D = dm.D(), CAP = dm.CAP();
     const int cnt = lane < hops ? mycnt : 0;
     terms += (uint32_t)__reduce_add_sync(FULL, cnt);
@@ -401,10 +409,10 @@ __device__ __forceinline__ double gn_neighbours(const DM &dm, const Tab &t, cons
         if (b + lane < total) {
             const uint4 v = *reinterpret_cast<const uint4 *>(lists + (unsigned)(l * CAP) + 4 * off);
             double s1 = 0.0, s2 = 0.0;
-            gn_term(t, D, v.x, c2, s1, s2);
-            gn_term(t, D, v.y, c2, s1, s2);
-            gn_term(t, D, v.z, c2, s1, s2);
-            gn_term(t, D, v.w, c2, s1, s2);
+            gn_term<SKIP>(t, D, v.x, c2, s1, s2, self_key);
+            gn_term<SKIP>(t, D, v.y, c2, s1, s2, self_key);
+            gn_term<SKIP>(t, D, v.z, c2, s1, s2, self_key);
+            gn_term<SKIP>(t, D, v.w, c2, s1, s2, self_key);
             x = fma(t.W1(l), s1, x);
             x = fma(t.W2(l), s2, x);  // W2 is stored negated
         }
@@ -589,14 +597,154 @@ __device__ __forceinline__ Head load_head(const KParams &p, const uint4 *tr, con
     return h;
 }
 
+// --------------------------------------------------------------------------------------------------------
+// measure_disruptions and defragmentation (qrmsa.pyx:937-952, :1545-1639).  Both walk the RUNNING services, which the
+// device does not keep as objects: a running service is a request record whose action word says "accepted" and whose
+// release has not happened yet.  Rows, lists and the path table are read from global memory (general-dimension
+// kernels only): the switches multiply the work per request by 10-100, as they do in the reference.
+// --------------------------------------------------------------------------------------------------------
+struct SvcView {   // a provisioned service decoded from its request record
+    int path, hops, link, s, n, m, ncls;
+    uint32_t key;   // its channel record's centre | width << 12
+};
+template <class DM>
+__device__ __forceinline__ SvcView decode_service(const DM &dm, const KParams &p, const Tab &t, const uint4 rq, int lane) {
+    const int S = dm.S(), M = dm.M();
+    const uint32_t a = rq.w & QRMSA_ACTION_MASK;
+    const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+    SvcView v;
+    v.s = a % S;
+    v.m = (M - 1) - (int)((a / S) % M);
+    v.n = t.need(rate * M + v.m);
+    v.ncls = t.cls(rate * M + v.m);
+    v.path = (src * p.N + dst) * dm.K() + (int)(a / (S * M));
+    v.hops = __ldg(p.path_hops + v.path) & 0x7f;
+    v.link = lane < v.hops ? __ldg(p.path_links + v.path * p.Hmax + lane) : 0;
+    v.key = (uint32_t)(2 * v.s + v.n) | ((uint32_t)v.n << 12);
+    return v;
+}
+
+// 1/GSNR of service v placed at start slot s (its own slot, or a defragmentation candidate), its own record skipped
+template <class DM>
+__device__ __forceinline__ double acc_of_service(const DM &dm, const KParams &p, const Tab &t, const uint32_t *bm,
+                                                 const uint32_t *lists, const SvcView &v, int s, int lane) {
+    const int cnt = lane < v.hops ? (int)bm[cnt_index(v.link, dm.RW())] : 0;
+    uint32_t terms = 0;
+    const double x = gn_neighbours<DM, true>(dm, t, lists, v.hops, v.link, cnt, 2 * s + v.n, lane, terms, v.key);
+    return gn_base(p, t, v.path, s, v.n, v.ncls).with(x);
+}
+
+// qrmsa.pyx:937-952, after request `cur` has been provisioned (its action word is written).  Running services = the
+// accepted requests among the schedule entries still ahead of the release pointer; the ones that share a link with the
+// new service and are not yet marked are re-evaluated.  Returns how many were found disrupted now.
+template <class DM>
+__device__ __forceinline__ int measure_disruptions(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
+                                                   const unsigned long long *perm, const uint32_t *bm, const uint32_t *lists,
+                                                   int cur, int rel_ptr, int lane, uint32_t &flags) {
+    const SvcView me = decode_service(dm, p, t, tr[cur], lane);
+    int local = 0;
+    for (int i0 = rel_ptr; i0 < p.n_req; i0 += 32) {
+        const int i = i0 + lane;
+        int id = -1;
+        uint32_t w = 0u;
+        if (i < p.n_req) {
+            id = (int)(unsigned)perm[i];
+            if (id <= cur) w = tr[id].w;
+        }
+        const bool cand = id >= 0 && id <= cur && (w & QRMSA_FLAG_ACCEPTED) &&
+                          !(w & (QRMSA_FLAG_DISRUPTED | QRMSA_FLAG_RELEASE_CANCELLED));
+        unsigned todo = __ballot_sync(FULL, cand);
+        while (todo) {
+            const int sl = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int xid = __shfl_sync(FULL, id, sl);
+            const uint4 rq = tr[xid];
+            const SvcView v = decode_service(dm, p, t, rq, lane);
+            bool share = false;
+            for (int h = 0; h < me.hops; ++h) {
+                const int l = __shfl_sync(FULL, me.link, h);
+                share |= (lane < v.hops && v.link == l);
+            }
+            if (!__any_sync(FULL, share)) continue;
+            const double acc = acc_of_service(dm, p, t, bm, lists, v, v.s, lane);
+            if (acc > p.acct0_lo[v.m] && acc < p.acct0_hi[v.m]) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+            if (acc > p.acct0[v.m]) {   // osnr < minimum_osnr
+                local += 1;
+                if (lane == 0) tr[xid].w = rq.w | QRMSA_FLAG_DISRUPTED;
+            }
+        }
+    }
+    __syncwarp();
+    return local;
+}
+
+// qrmsa.pyx:1545-1639, called after the service with schedule key (rel_bits, rel_id) has been released.  The services
+// still in the reference's heap are the accepted requests whose key sorts after it; they are visited in provisioning
+// (= request) order.  Returns the number of services moved; flags receives the near-threshold mark.
+template <class DM>
+__device__ __forceinline__ int defragment(const DM &dm, const KParams &p, const Tab &t, uint4 *tr, uint32_t *bm, uint32_t *lists,
+                                          uint8_t *pos, int cur, uint32_t rel_bits, int rel_id, int lane, uint32_t &flags) {
+    const int S = dm.S();
+    const int limit = p.n_defrag ? p.n_defrag : 1000000;
+    int moved = 0, err = 0;
+    for (int i0 = 0; i0 < cur && moved < limit; i0 += 32) {
+        const int id = i0 + lane;
+        uint4 rq = make_uint4(0u, 0u, 0u, 0u);
+        bool act = false;
+        if (id < cur) {
+            rq = tr[id];
+            if ((rq.w & (QRMSA_FLAG_ACCEPTED | QRMSA_FLAG_RELEASE_CANCELLED)) == QRMSA_FLAG_ACCEPTED) {
+                const uint32_t key = __float_as_uint(__fadd_rn(__uint_as_float(rq.x), __uint_as_float(rq.y)));
+                act = key > rel_bits || (key == rel_bits && id > rel_id);
+            }
+        }
+        unsigned todo = __ballot_sync(FULL, act);
+        while (todo && moved < limit) {
+            const int sl = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            uint4 rx;
+            rx.x = __shfl_sync(FULL, rq.x, sl); rx.y = __shfl_sync(FULL, rq.y, sl);
+            rx.z = __shfl_sync(FULL, rq.z, sl); rx.w = __shfl_sync(FULL, rq.w, sl);
+            const int xid = i0 + sl;
+            const SvcView v = decode_service(dm, p, t, rx, lane);
+            // valid starts for v.n slots on its path (the service itself still occupies its slots), below its own start
+            uint32_t r = path_available(dm, bm, v.hops, v.link, lane);
+            for (int a = 1, L = v.n + 1; a < L;) { const int b = min(a, L - a); r &= shr_multi(r, b); a += b; }
+            r &= range_mask(0, v.s, lane);
+            for (;;) {
+                const unsigned any = __ballot_sync(FULL, r != 0u);
+                if (!any) break;
+                const int fl = __ffs(any) - 1;
+                const uint32_t w = __shfl_sync(FULL, r, fl);
+                const int c = (fl << 5) + __ffs(w) - 1;
+                if (lane == fl) r &= r - 1u;
+                const double acc = acc_of_service(dm, p, t, bm, lists, v, c, lane);
+                if (acc > p.acct0_lo[v.m] && acc < p.acct0_hi[v.m]) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+                if (acc > p.acct0[v.m]) continue;   // osnr < minimum_osnr: next candidate (qrmsa.pyx:1600-1604)
+                // move: free the old slots and drop the record, then provision at c
+                err |= release_service(dm, p, t, bm, lists, pos, rx, lane, PathTab<false>());
+                const int cnt = lane < v.hops ? (int)bm[cnt_index(v.link, dm.RW())] : 0;
+                const uint32_t rec = (uint32_t)(2 * c + v.n) | ((uint32_t)v.n << 12) | ((uint32_t)v.m << 20) | ((uint32_t)v.ncls << 23);
+                err |= commit(dm, p, bm, lists, pos, v.hops, v.link, cnt, c, v.n, rec, lane);
+                if (lane == 0) tr[xid].w = rx.w - (uint32_t)v.s + (uint32_t)c;   // the slot is the action's last digit
+                __syncwarp();
+                moved += 1;
+                break;
+            }
+        }
+    }
+    return err ? -1 : moved;
+}
+
 // qrmsa.pyx:1067-1122 after a request has been decided: take the next request (clock := its arrival) and
 // release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
 // schedule exactly as they are absent from the reference heap.
-template <class DM, class BM, class PT = PathTab<false>, class ST = Streams<false>>
+struct DefragStats { uint32_t cycles, moved, flags; };
+template <class DM, class BM, class PT = PathTab<false>, class ST = Streams<false>, int FEAT = 0>
 __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
                                                    const unsigned long long *perm, const BM bm, uint32_t *lists, uint8_t *pos,
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel,
-                                                   const PT pt = PT(), const ST sm = ST()) {
+                                                   const PT pt = PT(), const ST sm = ST(), DefragStats *ds = nullptr) {
     cur += 1;
     if ((cur & 7) == 0) {   // (no-ops without the ring) the chunk entered was requested eight requests ago
         sm.wait();
@@ -609,6 +757,13 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
         if ((rq.w & (QRMSA_FLAG_ACCEPTED | QRMSA_FLAG_RELEASE_CANCELLED)) == QRMSA_FLAG_ACCEPTED) {
             err |= release_service(dm, p, t, bm, lists, pos, rq, lane, pt);
             n_rel += 1;
+            if constexpr ((FEAT & 2) != 0) {
+                if (p.n_defrag == 0 || (cur + 1) % p.n_defrag == 0) {   // qrmsa.pyx:1117-1119
+                    const int mv = defragment(dm, p, t, tr, bm, lists, pos, cur, __float_as_uint(head.rel), head.id, lane, ds->flags);
+                    ds->cycles += 1;
+                    if (mv < 0) err |= 1; else ds->moved += (uint32_t)mv;
+                }
+            }
         }
         rel_ptr += 1;
         if ((rel_ptr & 15) == 0) {
@@ -656,9 +811,11 @@ struct RowHandle<true> {
 // SM_: what the kernel keeps in shared memory beside the tables.  0 = nothing; 1 ("BMS") = per warp the env's link rows and
 // the request / schedule stream chunks, plus the compact path table; 2 = the stream chunks only (configurations whose
 // rows do not fit, e.g. 640 slots: the tables alone take 183 KB).
-template <int S_, int M_, int K_, int POLICY, int SM_ = 0>
+// FEAT: bit 0 measure_disruptions, bit 1 defragmentation (general-dimension, unstaged kernel only)
+template <int S_, int M_, int K_, int POLICY, int SM_ = 0, int FEAT = 0>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p, const int n_steps) {
     constexpr bool BMS = SM_ == 1, RING = SM_ != 0;
+    static_assert(FEAT == 0 || (SM_ == 0 && POLICY == POLICY_FIRST_FIT), "the feature hooks read rows and lists from global memory");
     __shared__ uint64_t mbar;
     stage_tables(p, &mbar);
     Tab t;
@@ -911,10 +1068,28 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 }
             }
             __syncwarp();
+            if (FEAT & 1) {   // qrmsa.pyx:937-952
+                int loc = 0;
+                if (found) {
+                    uint32_t f2 = 0u;
+                    loc = measure_disruptions(dm, p, t, tr, perm, bm_global, lists, cur, rel_ptr, lane, f2);
+                    if (f2 && lane == 0) tr[cur].w |= f2;
+                    QCNT(QRMSA_CNT_DISRUPTED, loc);
+                }
+                if (lane == 0 && p.step_disrupted) p.step_disrupted[env] = loc;
+                __syncwarp();
+            }
             uint32_t n_rel = 0;
-            if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, pt, sm))
+            DefragStats ds = {0u, 0u, 0u};
+            if (advance_and_release<Dim<S_, M_, K_>, typename RowHandle<BMS>::type, PathTab<BMS>, Streams<RING>, FEAT>(
+                    dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, pt, sm, &ds))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
+            if (FEAT & 2) {
+                QCNT(QRMSA_CNT_DEFRAG_CYCLES, ds.cycles);
+                QCNT(QRMSA_CNT_REALLOCATIONS, ds.moved);
+                if (ds.flags && lane == 0) tr[cur - 1].w |= ds.flags;   // a near-threshold check while moving services
+            }
         }
         if (BMS) {
             __syncwarp();
@@ -1043,11 +1218,32 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                     }
                 }
                 __syncwarp();
+                if (p.feat & 1) {   // qrmsa.pyx:937-952
+                    int loc = 0;
+                    if (status == QRMSA_STEP_ACCEPTED) {
+                        uint32_t f2 = 0u;
+                        loc = measure_disruptions(dm, p, t, tr, perm, bm, lists, cur, rel_ptr, lane, f2);
+                        if (f2 && lane == 0) tr[cur].w |= f2;
+                        if (f2 && !(flags & QRMSA_FLAG_NEAR_THRESHOLD)) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
+                        QCNT(QRMSA_CNT_DISRUPTED, loc);
+                    }
+                    if (lane == 0 && p.step_disrupted) p.step_disrupted[env] = loc;
+                    __syncwarp();
+                }
                 Head head = load_head(p, tr, perm, rel_ptr);
                 uint32_t n_rel = 0;
-                if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel))
-                    err = ENV_ERR_RELEASE_NOT_FOUND;
+                DefragStats ds = {0u, 0u, 0u};
+                int rerr;
+                if (p.feat & 2)
+                    rerr = advance_and_release<Dim<0, 0, 0>, uint32_t *, PathTab<false>, Streams<false>, 2>(
+                        dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, PathTab<false>(), Streams<false>(), &ds);
+                else
+                    rerr = advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel);
+                if (rerr) err = ENV_ERR_RELEASE_NOT_FOUND;
                 QCNT(QRMSA_CNT_RELEASES, n_rel);
+                QCNT(QRMSA_CNT_DEFRAG_CYCLES, ds.cycles);
+                QCNT(QRMSA_CNT_REALLOCATIONS, ds.moved);
+                if (ds.flags && lane == 0) tr[cur - 1].w |= ds.flags;
                 term = (cur + 1 == episode_length);  // episode_services_processed == episode_length (qrmsa.pyx:1056)
             }
             if (err) QCNT(QRMSA_CNT_ERRORS, 1);

@@ -93,6 +93,17 @@ class Engine:
         """0 / 1 / 2: how much per-env state the step kernel stages in shared memory (include/qrmsa_b200.h)."""
         check(self.lib.qrmsa_set_staging(self._h, int(level)), self._h)
 
+    def set_features(self, measure_disruptions: bool = False, defragmentation: bool = False, n_defrag_services: int = 0):
+        """The constructor switches of qrmsa.pyx:206-237 (see include/qrmsa_b200.h qrmsa_set_features)."""
+        check(self.lib.qrmsa_set_features(self._h, int(bool(measure_disruptions)), int(bool(defragmentation)),
+                                          int(n_defrag_services)), self._h)
+
+    def step_disrupted(self, stream=None) -> np.ndarray:
+        """Services found disrupted by the last decided request of every env (int32 [n_envs])."""
+        out = np.zeros(self.n_envs, np.int32)
+        check(self.lib.qrmsa_get_step_disrupted_host(self._h, _np_ptr(out), self._stream(stream)), self._h)
+        return out
+
     def enable_gsnr_log(self, enable: bool = True):
         check(self.lib.qrmsa_enable_gsnr_log(self._h, int(enable)), self._h)
 
@@ -234,6 +245,7 @@ class Engine:
         d = {n: int(row[i]) for i, n in enumerate(_lib.COUNTER_NAMES)}
         d["mod_hist"] = row[16:24].copy()
         d["gn_pruned"] = int(row[24])
+        d["disrupted_services"], d["defrag_cycles"], d["service_reallocations"] = int(row[25]), int(row[26]), int(row[27])
         return d
 
     def counters_tensor(self):

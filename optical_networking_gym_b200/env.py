@@ -24,7 +24,10 @@ the reference (qrmsa.pyx:584-587).
 draws `rng.randint(lower, higher)` like the reference (qrmsa.pyx:246-254); `reset(options={"only_episode_counters":
 True})` restarts the episode counters on the live network and drops the pending release events (qrmsa.pyx:433, :461-464).
 
-Not implemented (SURVEY §8f "next" rows): `measure_disruptions`, `defragmentation`, `bands`; they raise.
+`measure_disruptions=True` and `defragmentation=True` / `n_defrag_services` run on the device (qrmsa.pyx:937-952, :1113-1122,
+:1545-1639; `qrmsa_set_features`).
+
+Not implemented: `bands` (multiband: SURVEY §8f ranks it last and documents why its reference path is unusable); it raises.
 """
 from __future__ import annotations
 
@@ -98,10 +101,6 @@ def _unsupported(name):
 
 
 def _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, bit_rate_selection):
-    if measure_disruptions:
-        _unsupported("measure_disruptions=True")
-    if defragmentation:
-        _unsupported("defragmentation=True")
     if bands:
         _unsupported("bands (multiband)")
     if bit_rate_selection not in ("discrete", "continuous"):
@@ -199,6 +198,12 @@ class QRMSAEnv(_Common):
         self._horizon = int(min(16384, max(4 * self.episode_length, self.episode_length + 1, 2)))
         self._eng = Engine(tb, 1, self._horizon, device=device)
         self._eng.enable_gsnr_log(True)
+        self.measure_disruptions, self.defragmentation = bool(measure_disruptions), bool(defragmentation)
+        self.n_defrag_services = int(n_defrag_services)
+        if self.measure_disruptions or self.defragmentation:
+            self._eng.set_features(self.measure_disruptions, self.defragmentation, self.n_defrag_services)
+        self.disrupted_services = self.episode_disrupted_services = 0
+        self.episode_defrag_cicles = self.episode_service_realocations = 0
         self._running = []           # release keys of the running services (active_services column of the CSV)
         self.file_stats = None
         if file_name != "":          # qrmsa.pyx:387-406
@@ -270,7 +275,11 @@ class QRMSAEnv(_Common):
         self.episode_bit_rate_requested = self.episode_bit_rate_provisioned = 0.0
         self.bl_resource = self.bl_osnr = self.bl_reject = 0
         self.episode_modulation_histogram = {int(se): 0 for se in self.tables.mod_se}
+        self.episode_disrupted_services = 0
+        self.episode_defrag_cicles = self.episode_service_realocations = 0
         if options is not None and options.get("only_episode_counters"):
+            if self.measure_disruptions or self.defragmentation:
+                _unsupported("reset(options={'only_episode_counters': True}) together with measure_disruptions / defragmentation")
             # qrmsa.pyx:433, :461-464: counters restart, the network and the current request stay -- and because the
             # reference empties its release heap here, the services running now are never released
             if self._block is None:
@@ -292,6 +301,7 @@ class QRMSAEnv(_Common):
         self._cur = 0
         self._running = []
         self.bit_rate_requested = self.bit_rate_provisioned = 0.0            # :466-467 (full reset)
+        self.disrupted_services = 0                                          # :468
         self.current_service = self._service_from_block(0)
         self._account_new_service()
         obs, mask = self._observation()
@@ -304,6 +314,7 @@ class QRMSAEnv(_Common):
         tb = self.tables
         svc = self.current_service
         svc.blocked_due_to_resources = svc.blocked_due_to_osnr = False
+        disrupted_now = 0
         self._t_action[0] = int(action)
         self._eng.step_action(self._t_action, self._t_reward, self._t_status, self._t_gsnr, self._t_term)
         torch.cuda.current_stream().synchronize()
@@ -333,6 +344,10 @@ class QRMSAEnv(_Common):
             ase, nli = self._eng.ase_nli_host(self._cur, 1)                    # osnr.pyx:133-140, stored at :930-932
             svc.ASE, svc.NLI = float(ase[0, 0]), float(nli[0, 0])
             self._running.append(np.float32(np.float32(svc.arrival_time) + np.float32(svc.holding_time)))   # :1327-1330
+            if self.measure_disruptions:                                       # :937-952
+                disrupted_now = int(self._eng.step_disrupted()[0])
+                self.disrupted_services += disrupted_now
+                self.episode_disrupted_services += disrupted_now
             svc.initial_slot, svc.number_slots = initial_slot, n
             svc.center_frequency = (self.frequency_start + (self.frequency_slot_bandwidth * initial_slot)
                                     + (self.frequency_slot_bandwidth * (n / 2.0)))
@@ -359,7 +374,7 @@ class QRMSAEnv(_Common):
                     pk = route
                     plen = float(tb.path_length_km[tb.path_index(svc.source_id, int(svc.destination_id), route)])
                     se, mo = int(tb.mod_se[modulation_idx]), float(tb.mod_min_osnr[modulation_idx])
-                line += "{},{},{},{},{},{},{},{},{}".format(pk, plen, se, mo, svc.OSNR, svc.ASE, svc.NLI, 0, len(self._running))
+                line += "{},{},{},{},{},{},{},{},{}".format(pk, plen, se, mo, svc.OSNR, svc.ASE, svc.NLI, disrupted_now, len(self._running))
             else:
                 line += "-1,-1,-1,-1,-1,-1,-1,-1,-1"
             self.file_stats.write(line + "\n")
@@ -371,8 +386,19 @@ class QRMSAEnv(_Common):
             "disrupted_services": 0.0, "episode_disrupted_services": 0.0,
             "osnr": gsnr if status == _lib.STEP_ACCEPTED else 0.0, "osnr_req": osnr_req,
             "chosen_path_index": route, "chosen_slot": initial_slot,
-            "episode_defrag_cicles": 0, "episode_service_realocations": 0,
+            # assembled before the next request is drawn (qrmsa.pyx:996-1052): the release phase of THIS step shows up
+            # in the next step's info
+            "episode_defrag_cicles": self.episode_defrag_cicles,
+            "episode_service_realocations": self.episode_service_realocations,
         }
+        if self.disrupted_services > 0 and self.services_accepted > 0:            # :1035-1036
+            info["disrupted_services"] = float(self.disrupted_services) / self.services_accepted
+        if self.episode_disrupted_services > 0 and self.episode_services_accepted > 0:
+            # :1038-1041 -- int / int in C before the float(): the quotient is truncated
+            info["episode_disrupted_services"] = float(self.episode_disrupted_services // self.episode_services_accepted)
+        if self.defragmentation:
+            c = self._eng.counters()[0]
+            self.episode_defrag_cicles, self.episode_service_realocations = int(c[26]), int(c[27])
         if self.services_processed > 0:
             info["service_blocking_rate"] = float(self.services_processed - self.services_accepted) / self.services_processed
         if self.episode_services_processed > 0:
@@ -511,6 +537,7 @@ class BatchedQRMSAEnv(_Common):
                  frequency_slot_bandwidth: float = 12.5e9, margin: float = 0.0, measure_disruptions: bool = False,
                  seed: int = 50, allow_rejection: bool = True, reset: bool = True, channel_width: float = 12.5,
                  k_paths: int = 5, modulations_to_consider: int = 6, defragmentation: bool = False,
+                 n_defrag_services: int = 0,
                  gen_observation: bool = False, bands=None, device: int = 0, n_groups: int = 1, n_threads: int = 0,
                  request_source: str = "replay", env_offset: int = 0):
         _check_kwargs(measure_disruptions, defragmentation, bands, gen_observation, bit_rate_selection)
@@ -538,6 +565,8 @@ class BatchedQRMSAEnv(_Common):
         self._eng = Engine(tb, self.n_envs, max(self.episode_length, 2), device=device)
         if n_groups > 1:
             self._eng.set_groups(n_groups)
+        if measure_disruptions or defragmentation:
+            self._eng.set_features(measure_disruptions, defragmentation, n_defrag_services)
         self._dev = torch.device("cuda", device)
         shape = (self.episode_length, self.n_envs)
         self._pinned = [torch.empty(shape, dtype=dt, pin_memory=True) for dt in
@@ -644,6 +673,8 @@ class BatchedQRMSAEnv(_Common):
             "episode_service_blocking_rate": (c["decided"] - c["accepted"]) / dec,
             "episode_bit_rate_blocking_rate": (c["rate_requested_milli"] - c["rate_provisioned_milli"]) / req,
             "rejected": c["rejected"], "near_threshold_decisions": c["near_threshold"],
+            "disrupted_services": c["disrupted_services"] / max(c["accepted"], 1),
+            "episode_defrag_cicles": c["defrag_cycles"], "episode_service_realocations": c["service_reallocations"],
             **{f"modulation_{float(se)}": int(c["mod_hist"][i]) for i, se in enumerate(self.tables.mod_se)},
         }
 

@@ -56,6 +56,10 @@ def lib():
                                          C.POINTER(C.c_int), C.c_int]
         _lib.orc_get_slots.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_reset_episode_counters.argtypes = [C.c_void_p]
+        _lib.orc_set_features.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.orc_get_feature_counters.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_service_start.restype = C.c_int
+        _lib.orc_service_start.argtypes = [C.c_void_p, C.c_int]
         _lib.orc_observation.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         _lib.orc_get_link_list.restype = C.c_int
         _lib.orc_get_link_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -152,6 +156,19 @@ class OracleEnv:
         rw, g, term = C.c_double(0), C.c_double(0), C.c_int(0)
         st = lib().orc_step_action(self._h, int(action), C.byref(rw), C.byref(g), C.byref(term), int(episode_length))
         return st, rw.value, g.value, bool(term.value)
+
+    def set_features(self, measure_disruptions=False, defragmentation=False, n_defrag_services=0):
+        """measure_disruptions / defragmentation / n_defrag_services of the constructor (qrmsa.pyx:206-237)."""
+        lib().orc_set_features(self._h, int(bool(measure_disruptions)), int(bool(defragmentation)), int(n_defrag_services))
+
+    def feature_counters(self) -> dict:
+        out = np.zeros(5, np.int64)
+        lib().orc_get_feature_counters(self._h, _ptr(out))
+        return dict(disrupted_services=int(out[0]), episode_disrupted_services=int(out[1]), episode_defrag_cicles=int(out[2]),
+                    episode_service_realocations=int(out[3]), last_step_disrupted=int(out[4]))
+
+    def service_start(self, request_id: int) -> int:
+        return lib().orc_service_start(self._h, int(request_id))
 
     def reset_episode_counters(self):
         """reset(options={"only_episode_counters": True}): pending releases dropped, network and request kept."""

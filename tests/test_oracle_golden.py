@@ -192,3 +192,32 @@ def test_oracle_vs_reference_configuration_variants(tag):
     assert np.abs(r["gsnr"] - g["gsnr"]).max() < 1e-9
     assert np.array_equal(r["qot_step"], g["qot_step"]) and np.abs(r["qot_gsnr"] - g["qot_gsnr"]).max() < 1e-9
     assert np.array_equal(o.slots(), g["final_slots"])
+
+
+FEATS = ["feat_disrupt_nsfnet_320_l600_s7", "feat_defrag_nsfnet_320_l300_s9_n5", "feat_defrag_nsfnet_320_l150_s11_n0",
+         "feat_both_nobel-eu_320_l400_s13_n3"]
+
+
+@pytest.mark.parametrize("tag", FEATS)
+def test_oracle_disruptions_and_defragmentation_vs_reference(tag):
+    """measure_disruptions (qrmsa.pyx:937-952) and defragmentation (:1113-1122, :1545-1639) restated in the oracle:
+    decisions, per-step disrupted counts (the CSV column), reallocation / cycle counters and final slots against
+    recordings of the compiled reference."""
+    g = load_golden(tag)
+    tb = load_tables(tag.split("_")[2], 320)
+    n = len(g["action"])
+    o = orc.OracleEnv(tb, n + 1)
+    md, df, nd = (int(x) for x in g["feat"])
+    o.set_features(md, df, nd)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    for t in range(n):
+        # step()'s info is assembled before the next request is drawn (qrmsa.pyx:996-1052): the defragmentation counters
+        # it reports are those of the previous step's release phase
+        before = o.feature_counters()
+        assert before["episode_service_realocations"] == int(g["realocations"][t]), f"step {t}"
+        assert before["episode_defrag_cicles"] == int(g["defrag_cicles"][t]), f"step {t}"
+        r = o.run_first_fit(1, log_qot=False)
+        assert int(r["action"][0]) == int(g["action"][t]), f"step {t}"
+        assert o.feature_counters()["last_step_disrupted"] == int(g["disrupted_local"][t]), f"step {t}"
+    assert np.array_equal(o.slots(), g["final_slots"])
+    assert o.feature_counters()["disrupted_services"] == int(g["disrupted_local"].sum())

@@ -343,5 +343,59 @@ def main():
         print("csv_nsfnet_320_l300_s77:", len(text.splitlines()), "lines")
 
 
+    # measure_disruptions / defragmentation (qrmsa.pyx:937-952, :1113-1122, :1545-1639), first-fit heuristic
+    FEATS = [("feat_disrupt_nsfnet_320_l600_s7", "nsfnet", 600.0, 7, 400, dict(measure_disruptions=True)),
+             ("feat_defrag_nsfnet_320_l300_s9_n5", "nsfnet", 300.0, 9, 500, dict(defragmentation=True, n_defrag_services=5)),
+             ("feat_defrag_nsfnet_320_l150_s11_n0", "nsfnet", 150.0, 11, 250, dict(defragmentation=True, n_defrag_services=0)),
+             ("feat_both_nobel-eu_320_l400_s13_n3", "nobel-eu", 400.0, 13, 300,
+              dict(measure_disruptions=True, defragmentation=True, n_defrag_services=3))]
+    for tag, name, load, seed, steps, feats in FEATS:
+        if args.only and args.only not in tag:
+            continue
+        import glob, tempfile
+        t0 = time.time()
+        topo = topo_of(name)
+        tmp = tempfile.mkdtemp()
+        kw = rh.env_kwargs(topo, n_slots=320, load=load, episode_length=steps + 1)
+        kw.update(feats)
+        kw["file_name"] = os.path.join(tmp, "svc")      # the CSV carries the per-step disrupted count (qrmsa.pyx:983)
+        _, ref_qrmsa, _, _ = rh.import_reference()
+        with rh.seeded_random(seed):
+            env = ref_qrmsa.QRMSAEnv(**kw)
+        heur = rh.first_fit_heuristic()
+        node_index = {n: i for i, n in enumerate(topo.graph["node_indices"])}
+        rates = list(env.bit_rates)
+
+        def req(svc):
+            return (node_index[svc.source], node_index[svc.destination], rates.index(int(svc.bit_rate)),
+                    np.float32(svc.arrival_time), np.float32(svc.holding_time))
+
+        tr = [req(env.current_service)]
+        act, accd, dis_ratio, realloc, cycles, acc_total = [], [], [], [], [], []
+        for t in range(steps):
+            a, _, _ = heur(env)
+            svc = env.current_service
+            _, _, _, _, info = env.step(a)
+            act.append(a); accd.append(1 if svc.accepted else 0)
+            dis_ratio.append(info["disrupted_services"]); realloc.append(info["episode_service_realocations"])
+            cycles.append(info["episode_defrag_cicles"]); acc_total.append(info["episode_services_accepted"])
+            tr.append(req(env.current_service))
+        lines = open(glob.glob(os.path.join(tmp, "*.csv"))[0]).read().splitlines()[2:]
+        local = np.array([int(l.split(",")[11]) if l.split(",")[4] != "-1" else 0 for l in lines], np.int32)
+        arr = np.array(tr, dtype=[("src", "u1"), ("dst", "u1"), ("rate", "u1"), ("arrival", "f4"), ("holding", "f4")])
+        cum = np.rint(np.array(dis_ratio) * np.maximum(np.array(acc_total), 1)).astype(np.int64)
+        assert np.array_equal(np.cumsum(local), cum), "CSV column and info ratio disagree"
+        np.savez_compressed(os.path.join(GOLDEN, f"{tag}.npz"), action=np.array(act, np.int64), accepted=np.array(accd, np.uint8),
+                            disrupted_local=local, disrupted_ratio=np.array(dis_ratio), realocations=np.array(realloc, np.int64),
+                            defrag_cicles=np.array(cycles, np.int64),
+                            final_slots=np.array(env.topology.graph["available_slots"], dtype=np.uint8),
+                            meta_load=np.float64(load), meta_seed=np.int64(seed),
+                            feat=np.array([int(feats.get("measure_disruptions", False)), int(feats.get("defragmentation", False)),
+                                           int(feats.get("n_defrag_services", 0))], np.int64),
+                            **{k: arr[k].copy() for k in arr.dtype.names})
+        print(f"{tag}: {steps} steps, accepted {sum(accd)}, disrupted {int(cum[-1])}, realocations {realloc[-1]}, "
+              f"defrag cycles {cycles[-1]}, {time.time() - t0:.1f}s")
+
+
 if __name__ == "__main__":
     main()
