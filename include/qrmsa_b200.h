@@ -253,6 +253,15 @@ int qrmsa_step_action(qrmsa_ctx *ctx, const int64_t *d_action, float *d_reward, 
  * (wrappers/qrmsa_gym.py:74-75).
  */
 int qrmsa_observation(qrmsa_ctx *ctx, float *d_obs, uint8_t *d_mask, void *stream);
+/*
+ * modulations_to_consider < n_mods (examples/ONDM_2025/new_train_multi_ppo.py:101): the action space has
+ * k * modulations_to_consider * S + 1 entries and block j of a path stands for modulation max_modulation_idx - j, where
+ * max_modulation_idx is re-decided by every observation (QRMSAEnv.get_max_modulation_index, envs/qrmsa.pyx:543-581: the
+ * best modulation with an acceptable candidate on the first path that has one, never below modulations_to_consider - 1)
+ * and used by step() to decode the action (qrmsa.pyx:821-829).  uint8 [n_envs]: the value of every env's last observation
+ * (n_mods - 1 after a reset).  The decision log keeps the absolute modulation: its action words are composed with n_mods.
+ */
+int qrmsa_get_max_modulation_idx_host(qrmsa_ctx *ctx, uint8_t *h_out, void *stream);
 /* Sizes of one env's observation vector and action mask. */
 int qrmsa_observation_dims(const qrmsa_ctx *ctx, int *obs_dim, int *n_actions);
 

@@ -105,6 +105,7 @@ SIGNATURES = {
     "qrmsa_step_action": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "qrmsa_observation": (_I, [_P, _P, _P, _P]),
     "qrmsa_observation_dims": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
+    "qrmsa_get_max_modulation_idx_host": (_I, [_P, _P, _P]),
     "qrmsa_sample_masked_actions": (_I, [_P, _I, _P, _I, _I, C.c_int64, C.c_int64, _U64, _U64, _P, _I, _P]),
     "qrmsa_get_actions": (_I, [_P, _I, _I, _P, _P]),
     "qrmsa_get_actions_host": (_I, [_P, _I, _I, _P, _P]),

@@ -140,7 +140,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     if (S < 2 || S > 960) { ctx->err = "n_slots must be in 2..960 (one bitmap word per lane + the virtual slot)"; return QRMSA_ERR_UNSUPPORTED; }
     if (t->max_hops > 32 || t->max_hops < 1) { ctx->err = "paths longer than 32 hops"; return QRMSA_ERR_UNSUPPORTED; }
     if (M > 8 || R > 255 || N > 255 || E > 255 || K > 255) { ctx->err = "table dimension too large"; return QRMSA_ERR_UNSUPPORTED; }
-    if (kp.Mc != M) { ctx->err = "modulations_to_consider must equal the number of modulations"; return QRMSA_ERR_UNSUPPORTED; }
+    if (kp.Mc < 1 || kp.Mc > M) { ctx->err = "modulations_to_consider must be in 1..n_mods"; return QRMSA_ERR_UNSUPPORTED; }
     if ((long long)K * M * S >= (1 << 24)) { ctx->err = "action space exceeds 24 bits"; return QRMSA_ERR_UNSUPPORTED; }
     if (max_requests < 2 || max_requests > 16384) { ctx->err = "max_requests must be in 2..16384"; return QRMSA_ERR_UNSUPPORTED; }
     for (int l = 1; l < E; l++)
@@ -446,6 +446,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     if ((rc = dev_alloc(ctx, &kp.trace, (size_t)n_envs * kp.T))) return rc;
     if ((rc = dev_alloc(ctx, &kp.perm, (size_t)n_envs * kp.T))) return rc;
     if ((rc = dev_alloc(ctx, &kp.estate, (size_t)n_envs))) return rc;
+    if ((rc = dev_alloc(ctx, &kp.maxmod, (size_t)n_envs))) return rc;
     if ((rc = dev_alloc(ctx, &kp.counters, (size_t)QRMSA_N_COUNTERS * 1))) return rc;
     CK(cudaMemset(kp.counters, 0, sizeof(unsigned long long) * QRMSA_N_COUNTERS));
     CK(cudaMallocHost((void **)&ctx->h_counters, sizeof(int64_t) * QRMSA_N_COUNTERS));
@@ -502,6 +503,14 @@ extern "C" int qrmsa_set_features(qrmsa_ctx *ctx, int measure_disruptions, int d
         CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
         CK(cudaFuncSetAttribute(k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.blob_bytes));
     }
+    return QRMSA_OK;
+}
+
+extern "C" int qrmsa_get_max_modulation_idx_host(qrmsa_ctx *ctx, uint8_t *h_out, void *stream) {
+    if (!ctx || !h_out) return QRMSA_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(h_out, ctx->kp.maxmod, (size_t)ctx->kp.n_envs, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
     return QRMSA_OK;
 }
 
@@ -703,6 +712,10 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
     kp.smem_warp_stride = bsm ? ctx->warp_stride_bms : ctx->warp_stride_ring;
     // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
     const bool c320 = kp.S == 320 && kp.M == 6 && kp.K == 5, c640 = kp.S == 640 && kp.M == 6 && kp.K == 5;
+    if (kp.Mc < kp.M) {   // heuristics.py:36-54 composes the action from all modulations: with fewer digits it does not decode
+        ctx->err = "the fused heuristics address all modulations; with modulations_to_consider < n_mods use qrmsa_step_action";
+        return QRMSA_ERR_UNSUPPORTED;
+    }
     if (kp.feat && policy != QRMSA_POLICY_FIRST_FIT) {
         ctx->err = "measure_disruptions / defragmentation are built for the first-fit policy and for qrmsa_step_action";
         return QRMSA_ERR_UNSUPPORTED;
@@ -766,8 +779,8 @@ extern "C" int qrmsa_step_action(qrmsa_ctx *ctx, const int64_t *d_action, float 
 
 extern "C" int qrmsa_observation_dims(const qrmsa_ctx *ctx, int *obs_dim, int *n_actions) {
     if (!ctx) return QRMSA_ERR_ARG;
-    if (obs_dim) *obs_dim = 1 + 2 + ctx->kp.K + 12 * ctx->kp.K * ctx->kp.M;   // qrmsa.pyx:323-328
-    if (n_actions) *n_actions = ctx->kp.K * ctx->kp.M * ctx->kp.S + 1;        // qrmsa.pyx:319-321
+    if (obs_dim) *obs_dim = 1 + 2 + ctx->kp.K + 12 * ctx->kp.K * ctx->kp.Mc;   // qrmsa.pyx:323-328
+    if (n_actions) *n_actions = ctx->kp.K * ctx->kp.Mc * ctx->kp.S + 1;        // qrmsa.pyx:319-321
     return QRMSA_OK;
 }
 
@@ -776,6 +789,10 @@ extern "C" int qrmsa_observation(qrmsa_ctx *ctx, float *d_obs, uint8_t *d_mask, 
     if (ctx->kp.n_req < 1) { ctx->err = "no trace loaded"; return QRMSA_ERR_STATE; }
     if (!ctx->d_path_len_norm) { ctx->err = "path_length_km / link_length_km were not given to qrmsa_create"; return QRMSA_ERR_STATE; }
     if (!ctx->obs_grid && !ctx->obs2_grid) { ctx->err = "observation kernel needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
+    if (ctx->kp.Mc < ctx->kp.M && !ctx->obs2_grid) {
+        ctx->err = "modulations_to_consider < n_mods is built into the observation kernel for spectra up to 320 slots only";
+        return QRMSA_ERR_UNSUPPORTED;
+    }
     CK(cudaSetDevice(ctx->device));
     int obs_dim = 0, n_actions = 0;
     qrmsa_observation_dims(ctx, &obs_dim, &n_actions);

@@ -66,6 +66,8 @@ struct KParams {
     double acct0[8], acct0_lo[8], acct0_hi[8];   // 10^(-minimum_osnr/10) and its +-1e-3 dB band: disruption / defragmentation test
     int feat, n_defrag;          // bit 0 measure_disruptions, bit 1 defragmentation; n_defrag_services (qrmsa.pyx:206-237)
     int *step_disrupted;         // [n_envs] services found disrupted by the last decided request (nullable)
+    uint8_t *maxmod;             // [n_envs] max_modulation_idx: n_mods-1 after reset; with modulations_to_consider < n_mods the
+                                 // observation moves it with every request (qrmsa.pyx:437, :543-581) and step() decodes with it
     int need_monotone;  // slots_needed never decreases as the modulation index falls (true for SE-sorted tables)
     // static tables in global memory
     const uint8_t *path_hops;   // [N*N*K]
@@ -1129,7 +1131,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
     const int wpc = blockDim.x >> 5;
     const int gw = blockIdx.x * wpc + (threadIdx.x >> 5);
     const int gstride = gridDim.x * wpc;
-    const int reject = p.K * p.Mc * p.S;
+    const int reject = p.K * p.Mc * p.S;          // the caller's reject action (k * modulations_to_consider * S)
+    const int reject_log = p.K * p.M * p.S;       // the decision log addresses all n_mods modulations
 
     for (int env = gw; env < p.n_envs; env += gstride) {
         int4 st = p.estate[env];
@@ -1150,6 +1153,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
             const long long a64 = ext_action[env];
             uint32_t flags = QRMSA_FLAG_DECIDED;
             bool consume = true;
+            int a_log = reject_log;
             if (a64 == reject || a64 < 0 || a64 > reject) {
                 status = QRMSA_STEP_REJECT_ACTION;
                 reward = -6.0f;  // qrmsa.pyx:992-995
@@ -1158,7 +1162,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 const int s = a % p.S;
                 const int rel = (a / p.S) % p.Mc;
                 const int pi = (a / (p.S * p.Mc)) % p.K;
-                const int m = (p.M - 1 > 1) ? (p.M - 1) - rel : (p.Mc - 1) - rel;  // qrmsa.pyx:821-829
+                const int mmax = (int)p.maxmod[env];
+                const int m = (mmax > 1) ? mmax - rel : (p.Mc - 1) - rel;  // allowed_mods[rel], qrmsa.pyx:821-829
+                a_log = pi * p.M * p.S + ((p.M - 1) - m) * p.S + s;        // the same allocation in the log's encoding
                 const int n = t.need(rate * p.M + m);
                 const int path = (src * p.N + dst) * p.K + pi;
                 const int hops = __ldg(p.path_hops + path) & 0x7f;
@@ -1210,7 +1216,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 QCNT(QRMSA_CNT_RATE_REQUESTED, t.rate(rate));
                 if (flags & QRMSA_FLAG_NEAR_THRESHOLD) QCNT(QRMSA_CNT_NEAR_THRESHOLD, 1);
                 if (lane == 0) {
-                    tr[cur].w = (uint32_t)(status == QRMSA_STEP_ACCEPTED ? (int)a64 : reject) | flags;
+                    tr[cur].w = (uint32_t)(status == QRMSA_STEP_ACCEPTED ? a_log : reject_log) | flags;
                     if (p.gsnr_log) {
                         double *gl = p.gsnr_log + ((size_t)env * p.T + cur) * 3;
                         const bool acc_ = status == QRMSA_STEP_ACCEPTED;
@@ -1607,7 +1613,7 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
     Tab t;
     t.init();
     const Dim<0, 0, 0> dm(p);
-    const int S = p.S, W = p.W, M = p.M, K = p.K, D = p.D, CAP = p.CAP, E = p.E;
+    const int S = p.S, W = p.W, M = p.M, Mc = p.Mc, K = p.K, D = p.D, CAP = p.CAP, E = p.E;
     const int VW = W + 1, NW = (D + 31) >> 5;
     const int slot = threadIdx.x / OBS_ENV_THREADS;
     auto env_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(OBS_ENV_THREADS) : "memory"); };
@@ -1621,6 +1627,7 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
     int *phops = plink + K * 32;                                        // [K]
     uint32_t *lmask = reinterpret_cast<uint32_t *>(phops + K);          // [E]      paths crossing link l (0: none)
     int *tick = reinterpret_cast<int *>(lmask + E);                     // [1]      work ticket of the per-path phase
+    int *smax = tick + 1;                                               // [1]      max_modulation_idx of the open request
     const int tid = threadIdx.x - slot * OBS_ENV_THREADS, lane = tid & 31, warp = tid >> 5;
     constexpr int nw = OBS_ENV_THREADS >> 5;
     uint16_t *slist = reinterpret_cast<uint16_t *>(tick + 4) + warp * S;   // [nw][S]  valid starts of the open unit, compacted
@@ -1654,8 +1661,8 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
             if (lane == 0) { phops[pi] = hops; obs[3 + pi] = hops ? (float)path_len_norm[path] : 0.f; }
             for (int w = lane; w < NW; w += 32) need[pi * NW + w] = 0u;
             if (hops == 0) {   // fewer than k paths for this pair: features stay -1, no valid action (qrmsa.pyx:697)
-                for (int i = lane; i < M * 12; i += 32) obs[3 + K + pi * M * 12 + i] = -1.f;
-                for (int i = lane; i < M * S; i += 32) mask[(size_t)pi * M * S + i] = 0;
+                for (int i = lane; i < Mc * 12; i += 32) obs[3 + K + pi * Mc * 12 + i] = -1.f;
+                for (int i = lane; i < Mc * S; i += 32) mask[(size_t)pi * Mc * S + i] = 0;
                 continue;
             }
             const int l = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
@@ -1796,6 +1803,39 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
         }
         env_sync();   // X complete
         for (int i = tid; i < E; i += OBS_ENV_THREADS) lmask[i] = 0u;   // (read above, set again after the closing barrier)
+        // ---- modulations_to_consider < n_mods: get_max_modulation_index (qrmsa.pyx:543-581) -- paths in order, modulations
+        // from the most efficient one, any valid start whose GSNR meets minimum_osnr + margin; never below Mc - 1.  The Mc
+        // blocks of a path then stand for modulations max_idx, max_idx - 1, ... (qrmsa.pyx:716-719)
+        int maxidx = M - 1;
+        if (Mc < M) {
+            if (warp == 0) {
+                int found = -1;
+                for (int pi = 0; pi < K && found < 0; ++pi) {
+                    if (phops[pi] == 0) continue;
+                    const double2 pg = __ldg(p.path_gn + pbase + pi);
+                    for (int mi = 0; mi < M && found < 0; ++mi) {
+                        const int m = (M - 1) - mi;
+                        const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
+                        const uint32_t *vrow = validM + (pi * 8 + mi) * VW;
+                        bool ok = false;
+                        for (int it = 0; it * 32 < S; ++it) {
+                            const int s = lane + it * 32;
+                            if (s < S && ((vrow[it] >> lane) & 1u))
+                                ok |= gn_base(p, t, pg, s, n, ncls).with(X[pi * D + 2 * s + n]) <= t.ACCT(m);
+                        }
+                        if (__any_sync(FULL, ok)) found = m;
+                    }
+                }
+                if (lane == 0) {
+                    *smax = max(found, Mc - 1);
+                    p.maxmod[env] = (uint8_t)max(found, Mc - 1);
+                }
+            }
+            env_sync();
+            maxidx = *smax;
+        }
+        // block j of a path is modulation mod_of(j) (allowed_mods[j], qrmsa.pyx:821-829)
+        auto mod_of = [&](int j) { return maxidx > 1 ? maxidx - j : (Mc - 1) - j; };
         // ---- phase 2: units = (path, run of modulations that need the same number of slots), handed to the warps by a
         // ticket.  The unit's valid starts are compacted so that every lane holds one; GSNR once per start, then mask
         // bytes and the 12 features per modulation of the unit (qrmsa.pyx:583-781).
@@ -1803,17 +1843,17 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
             int u = 0;
             if (lane == 0) u = atomicAdd(tick, 1);
             u = __shfl_sync(FULL, u, 0);
-            if (u >= K * M) break;
-            const int pi = u / M, mi0 = u - pi * M;
+            if (u >= K * Mc) break;
+            const int pi = u / Mc, mi0 = u - pi * Mc;
             if (phops[pi] == 0) continue;
-            const int n = t.need(rate * M + (M - 1) - mi0);
-            if (mi0 > 0 && t.need(rate * M + (M - 1) - (mi0 - 1)) == n) continue;   // not the head of its run
+            const int n = t.need(rate * M + mod_of(mi0));
+            if (mi0 > 0 && t.need(rate * M + mod_of(mi0 - 1)) == n) continue;   // not the head of its run
             int mi1 = mi0 + 1;
-            while (mi1 < M && t.need(rate * M + (M - 1) - mi1) == n) ++mi1;
-            const int ncls = t.cls(rate * M + (M - 1) - mi0);
+            while (mi1 < Mc && t.need(rate * M + mod_of(mi1)) == n) ++mi1;
+            const int ncls = t.cls(rate * M + mod_of(mi0));
             const int path = pbase + pi;
             const double2 pg = __ldg(p.path_gn + path);
-            const uint32_t *vrow = validM + (pi * 8 + mi0) * VW;
+            const uint32_t *vrow = validM + (pi * 8 + (M - 1) - mod_of(mi0)) * VW;   // bitmaps are kept per modulation, best first
             const double *Xp = X + pi * D + n;
             // compaction (a word of the bitmap is its own ballot) and the all-zero mask rows of the unit
             int cnt = 0;
@@ -1823,7 +1863,7 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
                 cnt += __popc(w);
             }
             for (int mi = mi0; mi < mi1; ++mi) {
-                uint8_t *mrow = mask + (size_t)pi * M * S + (size_t)mi * S;
+                uint8_t *mrow = mask + (size_t)pi * Mc * S + (size_t)mi * S;
                 for (int s = lane; s < S; s += 32) mrow[s] = 0;
             }
             __syncwarp();
@@ -1848,8 +1888,8 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
             long long k_s2 = 0;
             double k_sum = 0.0, k_vmax = -1e300, k_sq = 0.0;
             for (int mi = mi0; mi < mi1; ++mi) {
-                const double th = p.mod_thr_nomargin[(M - 1) - mi], ath = fabs(th);
-                uint8_t *mrow = mask + (size_t)pi * M * S + (size_t)mi * S;
+                const double th = p.mod_thr_nomargin[mod_of(mi)], ath = fabs(th);
+                uint8_t *mrow = mask + (size_t)pi * Mc * S + (size_t)mi * S;
                 // count, sum s, sum s^2, max s in integers; sum norm, max norm, sum norm^2 in FP64
                 int c_n = 0, c_s = 0, c_max = -1;
                 long long c_s2 = 0;
@@ -1884,7 +1924,7 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
                     f_std = sqrt(fmax((double)k_s2 / cntv - f_avg * f_avg, 0.0));
                     ovar = fmax(k_sq / cntv - omean * omean, 0.0);
                 }
-                float *o = obs + 3 + K + (pi * M + mi0 + lane) * 12;
+                float *o = obs + 3 + K + (pi * Mc + mi0 + lane) * 12;
                 o[0] = (float)(cntv * inv_S);
                 o[1] = (float)(f_avg * inv_S1);
                 o[2] = (float)(f_std * inv_S1);
@@ -2146,7 +2186,11 @@ __global__ void k_reset(const KParams p) {
     }
     const size_t nrec = (size_t)p.n_envs * p.E * p.CAP;
     for (size_t i = tid; i < nrec; i += nthreads) p.lists[i] = p.sentinel;
-    for (size_t i = tid; i < (size_t)p.n_envs; i += nthreads) { p.estate[i] = make_int4(0, 0, 0, 0); p.counted[i] = 0u; }
+    for (size_t i = tid; i < (size_t)p.n_envs; i += nthreads) {
+        p.estate[i] = make_int4(0, 0, 0, 0);
+        p.counted[i] = 0u;
+        p.maxmod[i] = (uint8_t)(p.M - 1);
+    }
 }
 
 // Request-major SoA [n_req][n_envs] -> per-env AoS records, through a shared-memory tile so that both the

@@ -195,6 +195,12 @@ class Engine:
         check(self.lib.qrmsa_observation_dims(self._h, C.byref(a), C.byref(b)), self._h)
         return a.value, b.value
 
+    def max_modulation_idx(self, stream=None) -> np.ndarray:
+        """Every env's max_modulation_idx as of its last observation (uint8 [n_envs]; qrmsa.pyx:543-581)."""
+        out = np.zeros(self.n_envs, np.uint8)
+        check(self.lib.qrmsa_get_max_modulation_idx_host(self._h, _np_ptr(out), self._stream(stream)), self._h)
+        return out
+
     def observation(self, obs, mask, stream=None):
         """obs: float32 CUDA [n_envs, obs_dim]; mask: uint8 CUDA [n_envs, n_actions] (both preallocated)."""
         check(self.lib.qrmsa_observation(self._h, obs.data_ptr(), mask.data_ptr(), self._stream(stream)), self._h)

@@ -249,6 +249,8 @@ class QRMSAEnv(_Common):
 
         self._eng.observation(self._t_obs, self._t_mask)
         torch.cuda.current_stream().synchronize()
+        if self.tables.mods_to_consider < self.tables.n_mods:     # get_max_modulation_index, qrmsa.pyx:543-581, :680
+            self.max_modulation_idx = int(self._eng.max_modulation_idx()[0])
         return self._t_obs[0].cpu().numpy(), {"mask": self._t_mask[0].cpu().numpy()}
 
     def _service_from_block(self, i: int) -> Service:
@@ -299,6 +301,7 @@ class QRMSAEnv(_Common):
         self._eng.reset()
         self._eng.load_trace_host(*[np.ascontiguousarray(a[:, None]) for a in self._block])
         self._cur = 0
+        self.max_modulation_idx = self.tables.n_mods - 1                      # :437
         self._running = []
         self.bit_rate_requested = self.bit_rate_provisioned = 0.0            # :466-467 (full reset)
         self.disrupted_services = 0                                          # :468

@@ -56,6 +56,8 @@ def lib():
                                          C.POINTER(C.c_int), C.c_int]
         _lib.orc_get_slots.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_reset_episode_counters.argtypes = [C.c_void_p]
+        _lib.orc_max_mod_idx.restype = C.c_int
+        _lib.orc_max_mod_idx.argtypes = [C.c_void_p]
         _lib.orc_set_features.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib.orc_get_feature_counters.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_service_start.restype = C.c_int
@@ -170,6 +172,10 @@ class OracleEnv:
     def service_start(self, request_id: int) -> int:
         return lib().orc_service_start(self._h, int(request_id))
 
+    @property
+    def max_modulation_idx(self) -> int:
+        return lib().orc_max_mod_idx(self._h)
+
     def reset_episode_counters(self):
         """reset(options={"only_episode_counters": True}): pending releases dropped, network and request kept."""
         lib().orc_reset_episode_counters(self._h)
@@ -177,8 +183,9 @@ class OracleEnv:
     def observation(self):
         """(obs float32[1+2+k+12kM], mask uint8[kMS+1]) for the current request (gen_observation=True mode)."""
         tb = self.tables
-        obs = np.zeros(1 + 2 + tb.k_paths + 12 * tb.k_paths * tb.n_mods, np.float32)
-        mask = np.zeros(tb.k_paths * tb.n_mods * tb.n_slots + 1, np.uint8)
+        mc = int(tb.mods_to_consider)
+        obs = np.zeros(1 + 2 + tb.k_paths + 12 * tb.k_paths * mc, np.float32)
+        mask = np.zeros(tb.k_paths * mc * tb.n_slots + 1, np.uint8)
         pl = np.ascontiguousarray(tb.path_length_km, np.float64)
         lo, hi = link_length_range(tb)
         lib().orc_observation(self._h, _ptr(pl), lo, hi, _ptr(obs), _ptr(mask))

@@ -103,3 +103,46 @@ def test_batched_observation_vs_oracle():
             _mask_diff_allowed(tb, o, hm[e], rm)
             assert hm[e, -1] == 1
     eng.close()
+
+
+def test_fewer_modulations_to_consider_vs_reference_recording():
+    """modulations_to_consider = 2 of 6 (examples/ONDM_2025/new_train_multi_ppo.py:101): the observation kernel re-decides
+    max_modulation_idx per request (qrmsa.pyx:543-581), the two blocks of a path are modulations max_idx and max_idx - 1
+    (:716-719), step() decodes the action with it (:821-829).  Observation, mask, max_modulation_idx, rewards and final
+    slots against a recording of the compiled reference."""
+    import torch
+    from optical_networking_gym_b200 import _lib
+    from optical_networking_gym_b200.engine import Engine, unpack_bitmaps
+
+    g = load_golden("obs_mc2_nsfnet_320_l260_s5")
+    tb = load_tables("nsfnet", 320).replace(mods_to_consider=2)
+    n_req, n_act = len(g["src"]), int(g["n_actions"])
+    mask_ref = np.unpackbits(g["mask"], axis=1)[:, :n_act]
+    eng = Engine(tb, 1, n_req)
+    assert eng.observation_dims() == (g["obs"].shape[1], n_act) == (3 + 5 + 12 * 5 * 2, 5 * 2 * 320 + 1)
+    eng.reset(); eng.load_trace_host(*[np.ascontiguousarray(g[k][:, None]) for k in TRACE_KEYS])
+    dev = torch.device("cuda")
+    obs = torch.zeros((1, g["obs"].shape[1]), dtype=torch.float32, device=dev)
+    mask = torch.zeros((1, n_act), dtype=torch.uint8, device=dev)
+    a = torch.zeros(1, dtype=torch.int64, device=dev)
+    st = torch.zeros(1, dtype=torch.uint8, device=dev)
+    rw = torch.zeros(1, dtype=torch.float32, device=dev)
+    seen = set()
+    for t in range(len(g["action"]) + 1):
+        mask.fill_(7)
+        eng.observation(obs, mask)
+        torch.cuda.synchronize()
+        assert int(eng.max_modulation_idx()[0]) == int(g["max_mod"][t]), f"max_modulation_idx at step {t}"
+        seen.add(int(g["max_mod"][t]))
+        assert np.abs(obs.cpu().numpy()[0] - g["obs"][t]).max() < OBS_TOL, f"obs at step {t}"
+        assert np.array_equal(mask.cpu().numpy()[0], mask_ref[t]), f"mask at step {t}"
+        if t < len(g["action"]):
+            a[0] = int(g["action"][t])
+            eng.step_action(a, rw, st, None, None)
+            torch.cuda.synchronize()
+            assert int(st[0]) in (0, 1) and float(rw[0]) == pytest.approx(float(g["reward"][t]), abs=1e-6)
+    assert len(seen) >= 3
+    assert np.array_equal(unpack_bitmaps(eng.export_bitmaps(0, 1), 320)[0], g["final_slots"])
+    with pytest.raises(_lib.QRMSAError, match="address all modulations"):
+        eng.step_first_fit(1)
+    eng.close()

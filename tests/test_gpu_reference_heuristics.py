@@ -187,3 +187,27 @@ def test_file_name_writes_the_reference_csv(tmp_path):
         assert fa[:8] == fb[:8] and fa[11:] == fb[11:], (a, b)       # ids, endpoints, rate, path, modulation, counts: exact text
         for i in (8, 9, 10):
             assert float(fa[i]) == pytest.approx(float(fb[i]), abs=1e-6)
+
+
+def test_two_modulations_to_consider_env_vs_live_reference():
+    """QRMSAEnv(modulations_to_consider=2, gen_observation=True) next to the reference env (the ONDM PPO setting,
+    examples/ONDM_2025/new_train_multi_ppo.py:101): action space, masks, max_modulation_idx and the decode of the mask-chosen
+    action follow the reference request by request."""
+    _, _, H, _ = rh.import_reference()
+    ref, env, _ = _pair(2025, 10, load=260.0, gen_observation=True, modulations_to_consider=2)
+    assert env.action_space.n == ref.action_space.n == 5 * 2 * 320 + 1
+    obs_r, info_r = ref.reset()
+    obs_b, info_b = env.reset()
+    for t in range(7):
+        _same_request(env.current_service, ref.current_service)
+        assert env.max_modulation_idx == ref.max_modulation_idx, t
+        assert np.array_equal(info_b["mask"], info_r["mask"]), f"mask differs at step {t}"
+        assert np.abs(obs_b - obs_r).max() < 2e-6
+        a = H.shortest_available_path_first_fit_best_modulation(info_r["mask"])
+        assert env.encoded_decimal_to_array(a) == list(ref.encoded_decimal_to_array(a))
+        obs_r, rw_r, term_r, _, info_r = ref.step(a)
+        obs_b, rw_b, term_b, _, info_b = env.step(a)
+        assert rw_b == rw_r and term_b == term_r
+        assert info_b["chosen_slot"] == info_r["chosen_slot"] and info_b["osnr"] == pytest.approx(info_r["osnr"], abs=1e-3)
+    assert np.array_equal(env.available_slots_matrix(), np.asarray(ref.topology.graph["available_slots"]))
+    env.close()

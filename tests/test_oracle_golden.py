@@ -221,3 +221,25 @@ def test_oracle_disruptions_and_defragmentation_vs_reference(tag):
         assert o.feature_counters()["last_step_disrupted"] == int(g["disrupted_local"][t]), f"step {t}"
     assert np.array_equal(o.slots(), g["final_slots"])
     assert o.feature_counters()["disrupted_services"] == int(g["disrupted_local"].sum())
+
+
+def test_oracle_observation_with_fewer_modulations_vs_reference():
+    """modulations_to_consider = 2 of 6 (examples/ONDM_2025/new_train_multi_ppo.py:101): observation() moves
+    max_modulation_idx with every request (qrmsa.pyx:543-581, :680), the two blocks of a path stand for modulations
+    max_idx and max_idx - 1 (:716-719) and step() decodes the action with it (:821-829)."""
+    g = load_golden("obs_mc2_nsfnet_320_l260_s5")
+    tb = load_tables("nsfnet", 320).replace(mods_to_consider=2)
+    n_req, n_act = len(g["src"]), int(g["n_actions"])
+    assert n_act == tb.n_actions == 5 * 2 * 320 + 1
+    mask_ref = np.unpackbits(g["mask"], axis=1)[:, :n_act]
+    o = orc.OracleEnv(tb, n_req)
+    o.reset(*[g[k] for k in TRACE_KEYS])
+    for t in range(len(g["action"]) + 1):
+        obs, mask = o.observation()
+        assert o.max_modulation_idx == int(g["max_mod"][t]), f"step {t}"
+        assert np.abs(obs - g["obs"][t]).max() < 2e-6, f"obs at step {t}"
+        assert np.array_equal(mask, mask_ref[t]), f"mask at step {t}"
+        if t < len(g["action"]):
+            st, rw, _, _ = o.step_action(int(g["action"][t]), n_req)
+            assert st in (0, 1) and rw == pytest.approx(float(g["reward"][t]), abs=1e-9), f"step {t}"
+    assert np.array_equal(o.slots(), g["final_slots"])

@@ -143,18 +143,26 @@ def gen_rl(topo, tb, S, load, seed, n_steps):
     return out
 
 
-def gen_obs(topo, S, load, seed, n_steps):
+def gen_obs(topo, S, load, seed, n_steps, modulations_to_consider=6):
     """gen_observation=True (qrmsa.pyx:583-781): observation vector + GSNR-validated action mask per step,
     driven by a seeded mix of mask-sampled and first-fit actions."""
     heur = rh.first_fit_heuristic()
     # a few hundred first-fit steps without observations would be faster, but the env cannot switch modes;
     # a higher load fills the network within the recorded steps instead
-    env = rh.make_env(topo, seed, n_slots=S, load=load, episode_length=n_steps + 1, gen_observation=True)
+    if modulations_to_consider == 6:
+        env = rh.make_env(topo, seed, n_slots=S, load=load, episode_length=n_steps + 1, gen_observation=True)
+    else:   # modulations_to_consider < len(modulations): max_modulation_idx moves with the request (qrmsa.pyx:543-581)
+        _, ref_qrmsa, _, _ = rh.import_reference()
+        kw = rh.env_kwargs(topo, n_slots=S, load=load, episode_length=n_steps + 1, gen_observation=True)
+        kw["modulations_to_consider"] = modulations_to_consider
+        with rh.seeded_random(seed):
+            env = ref_qrmsa.QRMSAEnv(**kw)
     node_index = {n: i for i, n in enumerate(topo.graph["node_indices"])}
     rates = list(env.bit_rates)
     rng = np.random.default_rng(seed)
     obs0, info0 = env.reset()
-    rec = dict(src=[], dst=[], rate=[], arrival=[], holding=[], action=[], reward=[], obs=[obs0], mask=[info0["mask"]])
+    rec = dict(src=[], dst=[], rate=[], arrival=[], holding=[], action=[], reward=[], obs=[obs0], mask=[info0["mask"]],
+               max_mod=[int(env.max_modulation_idx)])
 
     def log_req(svc):
         rec["src"].append(node_index[svc.source]); rec["dst"].append(node_index[svc.destination])
@@ -174,12 +182,13 @@ def gen_obs(topo, S, load, seed, n_steps):
         obs, reward, term, _, info = env.step(a)
         mask = info["mask"]
         rec["action"].append(a); rec["reward"].append(reward); rec["obs"].append(obs); rec["mask"].append(mask)
+        rec["max_mod"].append(int(env.max_modulation_idx))
         log_req(env.current_service)
     out = dict(src=np.array(rec["src"], np.uint8), dst=np.array(rec["dst"], np.uint8), rate=np.array(rec["rate"], np.uint8),
                arrival=np.array(rec["arrival"], np.float32), holding=np.array(rec["holding"], np.float32),
                action=np.array(rec["action"], np.int64), reward=np.array(rec["reward"], np.float64),
                obs=np.array(rec["obs"], np.float32), mask=np.packbits(np.array(rec["mask"], np.uint8), axis=1),
-               n_actions=np.int64(len(mask)),
+               n_actions=np.int64(len(mask)), max_mod=np.array(rec["max_mod"], np.int32),
                final_slots=np.array(env.topology.graph["available_slots"], np.uint8))
     return out
 
@@ -342,6 +351,13 @@ def main():
                             **{k: arr[k].copy() for k in arr.dtype.names})
         print("csv_nsfnet_320_l300_s77:", len(text.splitlines()), "lines")
 
+
+    if not args.only or args.only in "obs_mc2_nsfnet_320_l260_s5":
+        t0 = time.time()
+        out = gen_obs(topo_of("nsfnet"), 320, 260.0, 5, 40, modulations_to_consider=2)
+        out["meta_load"] = np.float64(260.0); out["meta_seed"] = np.int64(5)
+        np.savez_compressed(os.path.join(GOLDEN, "obs_mc2_nsfnet_320_l260_s5.npz"), **out)
+        print(f"obs_mc2_nsfnet_320_l260_s5: 40 steps, max_modulation_idx values {sorted(set(out['max_mod'].tolist()))}, {time.time() - t0:.1f}s")
 
     # measure_disruptions / defragmentation (qrmsa.pyx:937-952, :1113-1122, :1545-1639), first-fit heuristic
     FEATS = [("feat_disrupt_nsfnet_320_l600_s7", "nsfnet", 600.0, 7, 400, dict(measure_disruptions=True)),
