@@ -31,10 +31,12 @@ __device__ __forceinline__ float sampler_logit(const __nv_bfloat16 *p, size_t i)
 
 constexpr int SAMPLER_THREADS = 256;
 
-// uniform in (0, 1): 24 random bits, centred ((r >> 8) + 0.5) / 2^24 -- never 0 or 1, so both logs are finite
+// uniform in (0, 1): 24 random bits, centred ((r >> 8) + 0.5) / 2^24 -- never 0 or 1, so both logs are finite.
+// __logf (MUFU.LG2 + one multiply; absolute error < 2^-21 away from 1) is plenty for sampling noise; the numpy
+// restatement of the tests uses the exact log and accepts a swapped near tie.
 __device__ __forceinline__ float sampler_gumbel(uint32_t r) {
     const float u = ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    return -logf(-logf(u));
+    return -__logf(-__logf(u));
 }
 
 template <class T>
@@ -51,18 +53,19 @@ __global__ void __launch_bounds__(SAMPLER_THREADS)
         const uint8_t *mk = mask + (size_t)env * mask_stride;
         float best = -INFINITY;
         int best_i = 0x7fffffff;
-        // one valid action: its Gumbel noise is word (a & 3) of the Philox block of group a >> 2
-        auto take = [&](int a) {
-            const uint4 r = sampler_philox(make_uint4((uint32_t)(a >> 2), 0u, (uint32_t)env, 0u), key);
-            const uint32_t w = (a & 3) == 0 ? r.x : (a & 3) == 1 ? r.y : (a & 3) == 2 ? r.z : r.w;
+        auto consider = [&](int a, uint32_t w) {
             const float k = sampler_logit(lg, (size_t)a) + sampler_gumbel(w);
             if (k > best || (k == best && a < best_i)) { best = k; best_i = a; }
         };
+        // one valid action on its own (row head / tail): its Gumbel noise is word (a & 3) of the Philox block of group a >> 2
+        auto take = [&](int a) {
+            const uint4 r = sampler_philox(make_uint4((uint32_t)(a >> 2), 0u, (uint32_t)env, 0u), key);
+            consider(a, (a & 3) == 0 ? r.x : (a & 3) == 1 ? r.y : (a & 3) == 2 ? r.z : r.w);
+        };
         // The mask row is scanned 16 bytes per lane and load (two loads in flight); rows start at any byte (n_actions is
         // odd), so up to 15 leading and 15 trailing bytes are read one by one.  Valid actions come in runs of consecutive
-        // start slots: the chunks that hold any are spread over the warp, two chunks per pass with one action per lane,
-        // so a run costs one Philox block per lane instead of sixteen in a row on one lane.  Logits are only touched
-        // where the mask is set.
+        // start slots: the 16-byte chunks that hold any are spread over the warp eight at a time, a lane taking one aligned
+        // group of four actions -- one Philox block per group, drawn once.  Logits are only touched where the mask is set.
         const int head = min((int)((16u - (unsigned)(reinterpret_cast<uintptr_t>(mk) & 15u)) & 15u), n_actions);
         const int n16 = (n_actions - head) >> 4;
         const int tail0 = head + (n16 << 4);
@@ -83,14 +86,35 @@ __global__ void __launch_bounds__(SAMPLER_THREADS)
             }
             unsigned nz = __ballot_sync(0xffffffffu, m16 != 0u);
             while (nz) {
-                const int la = __ffs(nz) - 1;
-                nz &= nz - 1u;
-                int lb = la;
-                bool two = false;
-                if (nz) { lb = __ffs(nz) - 1; nz &= nz - 1u; two = true; }
-                const int srcl = lane < 16 ? la : lb;
-                const uint32_t mm = __shfl_sync(0xffffffffu, m16, srcl);
-                if ((lane < 16 || two) && ((mm >> (lane & 15)) & 1u)) take(head + ((c0 + srcl) << 4) + (lane & 15));
+                // the (lane >> 2)-th chunk of the next eight that hold a valid action
+                unsigned rest = nz;
+                int src = -1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int l = rest ? __ffs(rest) - 1 : -1;
+                    if (j == (lane >> 2)) src = l;
+                    rest &= rest - 1u;
+                }
+                nz = rest;
+                const uint32_t mm = __shfl_sync(0xffffffffu, m16, src < 0 ? 0 : src);
+                // actions are counted from the row start, chunks from `head`: a chunk's four-action pieces straddle the
+                // Philox groups unless head is a multiple of 4, so the noise word is picked per action from its own group
+                const int a0 = head + ((c0 + src) << 4) + ((lane & 3) << 2);
+                const uint32_t m4 = src < 0 ? 0u : (mm >> ((lane & 3) << 2)) & 0xfu;
+                if (m4) {
+                    const int g0 = a0 >> 2;
+                    const uint4 r0 = sampler_philox(make_uint4((uint32_t)g0, 0u, (uint32_t)env, 0u), key);
+                    uint4 r1 = r0;
+                    if ((a0 & 3) && (m4 >> (4 - (a0 & 3))))      // some valid action of this piece lies in the next group
+                        r1 = sampler_philox(make_uint4((uint32_t)(g0 + 1), 0u, (uint32_t)env, 0u), key);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        if (!((m4 >> b) & 1u)) continue;
+                        const int a = a0 + b;
+                        const uint4 &r = (a >> 2) == g0 ? r0 : r1;
+                        consider(a, (a & 3) == 0 ? r.x : (a & 3) == 1 ? r.y : (a & 3) == 2 ? r.z : r.w);
+                    }
+                }
             }
         }
         if (lane < n_actions - tail0 && mk[tail0 + lane]) take(tail0 + lane);

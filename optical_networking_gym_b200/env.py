@@ -607,6 +607,8 @@ class BatchedQRMSAEnv(_Common):
             self._trace_valid = True
         self._episodes += 1
         self.steps_done = 0
+        self._rl_path = False
+        self._term.zero_()
         self._observe()
         return self._obs, {"mask": self._mask}
 
@@ -623,9 +625,13 @@ class BatchedQRMSAEnv(_Common):
         return self._trace
 
     def step(self, actions):
-        """actions: int64 CUDA tensor [n_envs] -> (obs, reward, terminated, truncated, info) of device tensors."""
+        """actions: int64 CUDA tensor [n_envs] -> (obs, reward, terminated, truncated, info) of device tensors.
+        An env whose action is refused (status NOT_FREE / LOW_GSNR) keeps its request, as in the reference
+        (qrmsa.pyx:886-897), so after such calls the envs are at different requests: `steps_done` counts CALLS, the
+        per-env progress is `engine.env_state()[:, 0]` and the per-env end of episode is the returned `terminated`."""
         self._eng.step_action(actions, self._reward, self._status, self._gsnr, self._term)
         self.steps_done += 1
+        self._rl_path = True
         self._observe()
         info = {"status": self._status, "osnr": self._gsnr, "mask": self._mask}
         return self._obs, self._reward, self._term.bool(), self._term.bool() & False, info
@@ -650,6 +656,10 @@ class BatchedQRMSAEnv(_Common):
 
     @property
     def terminated(self) -> bool:
+        """Every env has decided its last request.  After step(actions) calls the envs may have progressed unevenly
+        (refused actions do not consume a request): the device's per-env flags decide then."""
+        if getattr(self, "_rl_path", False):
+            return bool(self._term.all())
         return self.steps_done >= self.episode_length - 1
 
     def action_masks(self):
