@@ -90,6 +90,7 @@ def main():
     iI, iT, iP = sh.index("Instructions Executed"), sh.index("Thread Instructions Executed"), sh.index("Predicated-On Thread Instructions Executed")
     iS = sh.index("# Samples")
     ops, per_addr, tot, thr, pon = collections.Counter(), {}, 0, 0, 0
+    freq = collections.OrderedDict()   # runs of consecutive SASS instructions executed equally often = one loop level
     for r in sass:
         if len(r) <= iP or not r[0].startswith("0x"):
             continue
@@ -98,6 +99,10 @@ def main():
         op = (p[1] if p[0].startswith("@") else p[0]).split(".")[0]
         ops[op] += n
         per_addr[r[0]] = (n, int(r[iT]), int(r[iP]), int(r[iS] or 0))
+        if env_steps and n:
+            k = round(n / env_steps, 2)
+            f = freq.setdefault(k, [0, 0])
+            f[0] += 1; f[1] += n
     # ---- attribution to source lines from the CUDA+SASS page.  Inlined code is listed under its own line AND under
     # the lines of its callers, so every SASS address is counted ONCE, for the first line it appears under (the page
     # lists a file's lines in order, which puts a callee's own line before its call sites further down the file).
@@ -163,6 +168,12 @@ def main():
                 f"{100.0 * attributed / max(tot, 1):.1f} % attributed to source lines below\n\n")
         f.write("## SASS opcode mix (per env-step)\n\n" if env_steps else "## SASS opcode mix\n\n")
         f.write(", ".join(f"{o} {n / per:.1f}" for o, n in ops.most_common(30)) + "\n\n")
+        if env_steps:
+            f.write("## by execution frequency (SASS instructions that run equally often per env-step belong to one loop level)\n\n"
+                    "| executions per env-step | SASS instructions | warp-instructions per env-step |\n|---|---|---|\n")
+            for k, (cnt, n) in sorted(freq.items(), key=lambda kv: -kv[1][1])[:28]:
+                f.write(f"| {k:.2f} | {cnt} | {n / per:.1f} |\n")
+            f.write("\n")
         f.write("## stages (device function owning the line; warp-instructions per env-step, active lanes per instruction)\n\n"
                 "| function | instr | lanes | % of stall samples |\n|---|---|---|---|\n")
         for st, n in stages.most_common(40):
