@@ -217,6 +217,18 @@ __device__ __forceinline__ uint32_t row_ld(const RowsS &r, unsigned i) {
 __device__ __forceinline__ void row_st(const RowsS &r, unsigned i, uint32_t v) {
     asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(r.wb + 4u * i), "n"(WARP_STREAM_BYTES), "r"(v) : "memory");
 }
+// Set / clear bits of a row word.  Rows in global memory: a reduction (SASS REDG.E.OR / .AND) -- nothing comes back, so
+// the warp does not wait an L2 round trip for the old word (germany50/640: 6.26e8 -> 6.49e8 env-steps/s); the L1 line is
+// invalidated by the reduction, later row loads of the warp see the new word.  Rows in shared memory: load + store.
+template <bool SET>
+__device__ __forceinline__ void row_rmw(uint32_t *bm, unsigned i, uint32_t mask) {
+    if (SET) atomicOr(bm + i, mask); else atomicAnd(bm + i, ~mask);
+}
+template <bool SET>
+__device__ __forceinline__ void row_rmw(const RowsS &r, unsigned i, uint32_t mask) {
+    const uint32_t w = row_ld(r, i);
+    row_st(r, i, SET ? (w | mask) : (w & ~mask));
+}
 __device__ __forceinline__ unsigned cnt_index(int l, int RW) { return (unsigned)(l * RW + RW - 1); }
 __device__ __forceinline__ uint32_t *cnt_word(uint32_t *bm, int l, int RW) { return bm + (unsigned)(l * RW + RW - 1); }
 __device__ __forceinline__ const uint32_t *cnt_word(const uint32_t *bm, int l, int RW) { return bm + (unsigned)(l * RW + RW - 1); }
@@ -229,9 +241,7 @@ __device__ __forceinline__ unsigned pos_index(const KParams &p, int l, int pair)
     return (unsigned)(pair * p.E + l);
 }
 __device__ __forceinline__ void pos_store(const KParams &p, uint8_t *pos, int l, int pair, int v) {
-    const unsigned i = pos_index(p, l, pair);
-    if (p.pos_bytes == 1) pos[i] = (uint8_t)v;
-    else reinterpret_cast<uint16_t *>(pos)[i] = (uint16_t)v;
+    if (p.pos_bytes) pos[pos_index(p, l, pair)] = (uint8_t)v;   // (no table above 511 slots: release_by_search)
 }
 __device__ __forceinline__ int rec_pair(uint32_t rec) { return (int)(((rec & 0xfffu) - ((rec >> 12) & 0xffu)) >> 2); }
 
@@ -436,11 +446,7 @@ __device__ __forceinline__ void update_bitmaps(const DM &dm, const BM bm, int ho
     for (int i0 = 0; i0 < hops; i0 += 8) {
         const int i = i0 + (lane >> 2);
         const int l = __shfl_sync(FULL, mylink, i & 31);
-        if (i < hops && mask) {
-            const unsigned wi = (unsigned)(l * RW + j);
-            const uint32_t w = row_ld(bm, wi);
-            row_st(bm, wi, SET ? (w | mask) : (w & ~mask));
-        }
+        if (i < hops && mask) row_rmw<SET>(bm, (unsigned)(l * RW + j), mask);
     }
 }
 
@@ -464,6 +470,67 @@ __device__ __forceinline__ int commit(const DM &dm, const KParams &p, const BM b
     return __any_sync(FULL, err);
 }
 
+// LPH[hops] = (32 / hops) | ceil(65536 / (32 / hops)) << 8: lanes per hop when the 32 lanes are split evenly between the
+// hops of a path, and the multiplier that turns lane / lph into a multiply-shift (exact for lane < 32).
+__constant__ uint32_t LPH[33] = {
+    0x80020u, 0x80020u, 0x100010u, 0x199a0au, 0x200008u, 0x2aab06u, 0x333405u, 0x400004u, 0x400004u, 0x555603u, 0x555603u,
+    0x800002u, 0x800002u, 0x800002u, 0x800002u, 0x800002u, 0x800002u, 0x1000001u, 0x1000001u, 0x1000001u, 0x1000001u,
+    0x1000001u, 0x1000001u, 0x1000001u, 0x1000001u, 0x1000001u, 0x1000001u, 0x1000001u, 0x1000001u, 0x1000001u, 0x1000001u,
+    0x1000001u, 0x1000001u};
+
+// Release without a position table (spectra above 511 slots, where a list index no longer fits a byte and a two-byte
+// table would be 56 KB per env on germany50/640 -- more than rows and hot list lines together, never resident in L2 and a
+// DRAM round trip in the middle of every release).  The record is FOUND instead: the lanes are split evenly between the
+// hops, the lanes of a hop read its list four records per 16-byte load -- lines the GN sums keep warm -- and compare
+// centre | width; the lane that finds the record swap-removes it (the list's last record is fetched beside the search).
+// Returns 1 unless every hop found its record.
+template <class DM, class BM>
+__device__ __forceinline__ int release_by_search(const DM &dm, const KParams &p, const BM bm, uint32_t *lists, int hops,
+                                                 int mylink, int s, int n, int lane) {
+    const int CAP = dm.CAP(), RW = dm.RW();
+    const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12);   // centre and width identify the record
+    const int cown = lane < hops ? (int)row_ld(bm, cnt_index(mylink, RW)) : 0;
+    const uint32_t lut = LPH[hops];
+    const int lph = (int)(lut & 0xffu);
+    const int hop = (int)(((uint32_t)lane * (lut >> 8)) >> 16);   // lane / lph
+    const int sub = lane - hop * lph;
+    const int l = __shfl_sync(FULL, mylink, hop & 31);
+    const int ch = __shfl_sync(FULL, cown, hop & 31);
+    const int c = hop < hops ? ch : 0;                             // lanes left over when 32 % hops != 0 have no hop
+    const int groups = (c + 3) >> 2;
+    const int gmax = __reduce_max_sync(FULL, groups);
+    uint32_t *lst = lists + (unsigned)(l * CAP);
+    const uint32_t last = c > 0 ? lst[c - 1] : 0u;
+    update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, dm.S()), lane);
+    int fpos = -1;
+    auto look = [&](const uint4 v, int g) {
+        if ((v.x & 0xfffffu) == target) fpos = 4 * g;
+        if ((v.y & 0xfffffu) == target) fpos = 4 * g + 1;
+        if ((v.z & 0xfffffu) == target) fpos = 4 * g + 2;
+        if ((v.w & 0xfffffu) == target) fpos = 4 * g + 3;
+    };
+    // two groups per lane and pass, both loads issued before either is looked at (a link of up to 8 * lph records is one
+    // round trip: 64 records on a 4-hop path)
+#pragma unroll 1
+    for (int b = 0; b < gmax; b += 2 * lph) {
+        const int g0 = b + sub, g1 = g0 + lph;
+        uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+        if (g0 < groups) v0 = *reinterpret_cast<const uint4 *>(lst + 4 * g0);
+        if (g1 < groups) v1 = *reinterpret_cast<const uint4 *>(lst + 4 * g1);
+        look(v0, g0);
+        look(v1, g1);
+    }
+    const bool found = fpos >= 0 && fpos < c;   // (fillers past the count have width 0: they never match)
+    if (found) {
+        lst[fpos] = last;
+        lst[c - 1] = p.sentinel;   // entries past the count are always the zero-contribution filler
+        row_st(bm, cnt_index(l, RW), (uint32_t)(c - 1));
+    }
+    const int n_found = __popc(__ballot_sync(FULL, found));
+    __syncwarp();
+    return n_found != hops;
+}
+
 // qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record.
 // Lane i handles hop i: the record's place in the link's list comes from the position table, so there is no search.
 template <class DM, class BM, class PT = PathTab<false>>
@@ -481,6 +548,7 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int path = (src * p.N + dst) * dm.K() + pi;
     const int hops = pt.hops_flags(p, path) & 0x7f;
     const int mylink = pt.link(p, path, lane, hops);
+    if (p.pos_bytes == 0) return release_by_search(dm, p, bm, lists, hops, mylink, s, n, lane);
 #ifdef QRMSA_VALIDATE_RELEASE
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12);   // centre and width identify the record
 #endif
@@ -495,7 +563,7 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     if (lane < hops) {
         c = (int)row_ld(bm, cw);
         const unsigned pidx = pos_index(p, mylink, s >> 1);
-        fpos = p.pos_bytes == 1 ? (int)pos[pidx] : (int)reinterpret_cast<const uint16_t *>(pos)[pidx];
+        fpos = (int)pos[pidx];
         last = lst[max(c - 1, 0)];
     }
     update_bitmaps<true>(dm, bm, hops, mylink, s, min(s + n + 1, S), lane);

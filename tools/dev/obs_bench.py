@@ -1,6 +1,10 @@
 import sys, time, numpy as np, torch
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from helpers import load_tables
+from optical_networking_gym_b200 import _lib
+if len(sys.argv) > 2:   # kernel experiments: a prebuilt library (tools/dev/build_variant.sh)
+    import os
+    _lib.LIB_PATH = os.path.abspath(sys.argv[2]); _lib.needs_build = lambda: False
 from optical_networking_gym_b200.env import BatchedQRMSAEnv
 tb = load_tables("nsfnet", 320)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
@@ -13,4 +17,6 @@ for _ in range(2): env.engine.observation(obs, mask)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(5): env.engine.observation(obs, mask)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
-print(f"k_observation: {n} envs in {dt*1e3:.2f} ms = {n/dt:,.0f} env/s; valid actions per env {float(mask.sum())/n:.0f}")
+import hashlib
+dig = hashlib.sha256(obs.cpu().numpy().tobytes() + mask.cpu().numpy().tobytes()).hexdigest()[:16]
+print(f"{sys.argv[2] if len(sys.argv) > 2 else 'in-tree'} sha {dig} k_observation: {n} envs in {dt*1e3:.2f} ms = {n/dt:,.0f} env/s; valid actions per env {float(mask.sum())/n:.0f}")
