@@ -22,6 +22,7 @@ struct qrmsa_ctx {
     size_t ring_smem = 0;            // dynamic shared memory of the step kernel with the stream chunks only (0 = does not fit)
     size_t bm_smem = 0;              // dynamic shared memory of the step kernel with the bitmap rows staged (0 = does not fit)
     int staging = 2;                 // qrmsa_set_staging: 2 = rows + streams + paths when they fit, 1 = streams only, 0 = none
+    int ring_hops_off = 0, bms_hops_off = 0;      // KParams.smem_pt_hops of the two staged variants
     int warp_off_bms = 0, warp_stride_bms = 0;   // KParams.smem_warp_* of the two staged variants
     int warp_off_ring = 0, warp_stride_ring = 0;
     size_t cta_smem = 0;   // k_step_highest_snr (and k_observation): one CTA per env
@@ -350,7 +351,7 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
             if (fit) {
                 ctx->bm_smem = need;
                 kp.smem_pt_off = pt_off;
-                kp.smem_pt_hops = pt_off + kp.pt_hops_off;
+                kp.smem_pt_hops = ctx->bms_hops_off = pt_off + kp.pt_hops_off;
                 kp.smem_pt_links = pt_off + kp.pt_links_off;
             } else {
                 (void)cudaGetLastError();   // the attribute call refused: fall back to the smaller variants below
@@ -360,9 +361,12 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
     // the stream chunks alone, 512 bytes per warp after the tables (configurations whose rows do not fit)
     ctx->ring_smem = 0;
     {
-        const size_t need = (size_t)kp.blob_bytes + (size_t)wpc * WARP_STREAM_BYTES;
+        size_t need = (size_t)kp.blob_bytes + (size_t)wpc * WARP_STREAM_BYTES;
         ctx->warp_off_ring = kp.blob_bytes;
         ctx->warp_stride_ring = WARP_STREAM_BYTES;
+        // + the hop-count bytes of the path table (PathTab<2>)
+        ctx->ring_hops_off = (int)need;
+        need += round_up(n_paths, 16);
         if (need <= smem_budget) {
             bool fit = opt_in((const void *)k_step_policy<640, 6, 5, POLICY_FIRST_FIT, 2>, need);
             fit &= opt_in((const void *)k_step_policy<0, 0, 0, POLICY_FIRST_FIT, 2>, need);
@@ -712,6 +716,7 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
     KParams kp = ctx->kp;
     kp.smem_warp_off = bsm ? ctx->warp_off_bms : ctx->warp_off_ring;
     kp.smem_warp_stride = bsm ? ctx->warp_stride_bms : ctx->warp_stride_ring;
+    kp.smem_pt_hops = bsm ? ctx->bms_hops_off : (rsm ? ctx->ring_hops_off : 0);
     // compile-time specialisations for the BASELINE configurations; anything else takes the generic kernel
     const bool c320 = kp.S == 320 && kp.M == 6 && kp.K == 5, c640 = kp.S == 640 && kp.M == 6 && kp.K == 5;
     if (kp.Mc < kp.M) {   // heuristics.py:36-54 composes the action from all modulations: with fewer digits it does not decode

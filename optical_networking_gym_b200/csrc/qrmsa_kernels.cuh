@@ -286,15 +286,18 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Path lookups (hop count + flag, link ids).  PathTab<false>: the global tables, read through L1.  PathTab<true>: the
+// Path lookups (hop count + flag, link ids).  PathTab<0>: the global tables, read through L1.  PathTab<1>: the
 // compact copy the step kernel keeps in shared memory (offset u16 | hops u8 | link ids u8, variable length): the two
 // dependent table loads of every path visit and of every release become LDS, and ~19 KB of hot lines leave L1.
-template <bool SMEM>
+// PathTab<2>: only the hop-count bytes in shared memory (configurations whose rows and link ids do not fit, e.g.
+// germany50/640: 12 KB of the 28 KB the 228 KB carve-out leaves unused beside tables + stream chunks) -- the first of
+// the two dependent loads is an LDS, the link ids stay one load through L1/L2 (6.56e8 -> 6.64e8 env-steps/s).
+template <int MODE>
 struct PathTab {
-    uint32_t base;   // shared-window address of the dynamic shared block (SMEM only); the table's parts sit at the
+    uint32_t base;   // shared-window address of the dynamic shared block (MODE != 0); the table's parts sit at the
                      // KParams offsets smem_pt_off / smem_pt_hops / smem_pt_links
     __device__ __forceinline__ int hops_flags(const KParams &p, int path) const {
-        if (SMEM) {
+        if (MODE != 0) {
             uint32_t v;
             asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p.smem_pt_hops + (uint32_t)path));
             return (int)v;
@@ -303,7 +306,7 @@ struct PathTab {
     }
     // link id of hop `lane` (0 for lanes past the path)
     __device__ __forceinline__ int link(const KParams &p, int path, int lane, int hops) const {
-        if (SMEM) {
+        if (MODE == 1) {
             uint32_t off, v = 0;
             asm("ld.shared.u16 %0, [%1];" : "=r"(off) : "r"(base + (uint32_t)p.smem_pt_off + 2u * (uint32_t)path));
             if (lane < hops) asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)p.smem_pt_links + off + (uint32_t)lane));
@@ -533,7 +536,7 @@ __device__ __forceinline__ int release_by_search(const DM &dm, const KParams &p,
 
 // qrmsa.pyx:1332-1350: free [s, s+n+1) (clamped at S) on every link of the path, drop the channel record.
 // Lane i handles hop i: the record's place in the link's list comes from the position table, so there is no search.
-template <class DM, class BM, class PT = PathTab<false>>
+template <class DM, class BM, class PT = PathTab<0>>
 __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, const Tab &t, const BM bm,
                                                uint32_t *lists, uint8_t *pos, const uint4 rq, int lane,
                                                const PT pt = PT()) {
@@ -792,7 +795,7 @@ __device__ __forceinline__ int defragment(const DM &dm, const KParams &p, const 
                 if (acc > p.acct0_lo[v.m] && acc < p.acct0_hi[v.m]) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
                 if (acc > p.acct0[v.m]) continue;   // osnr < minimum_osnr: next candidate (qrmsa.pyx:1600-1604)
                 // move: free the old slots and drop the record, then provision at c
-                err |= release_service(dm, p, t, bm, lists, pos, rx, lane, PathTab<false>());
+                err |= release_service(dm, p, t, bm, lists, pos, rx, lane, PathTab<0>());
                 const int cnt = lane < v.hops ? (int)bm[cnt_index(v.link, dm.RW())] : 0;
                 const uint32_t rec = (uint32_t)(2 * c + v.n) | ((uint32_t)v.n << 12) | ((uint32_t)v.m << 20) | ((uint32_t)v.ncls << 23);
                 err |= commit(dm, p, bm, lists, pos, v.hops, v.link, cnt, c, v.n, rec, lane);
@@ -810,7 +813,7 @@ __device__ __forceinline__ int defragment(const DM &dm, const KParams &p, const 
 // release every accepted service whose key is <= now.  Entries of not-yet-decided requests block the
 // schedule exactly as they are absent from the reference heap.
 struct DefragStats { uint32_t cycles, moved, flags; };
-template <class DM, class BM, class PT = PathTab<false>, class ST = Streams<false>, int FEAT = 0>
+template <class DM, class BM, class PT = PathTab<0>, class ST = Streams<false>, int FEAT = 0>
 __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &p, const Tab &t, uint4 *tr,
                                                    const unsigned long long *perm, const BM bm, uint32_t *lists, uint8_t *pos,
                                                    int &cur, int &rel_ptr, Head &head, int lane, uint32_t &n_rel,
@@ -898,13 +901,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
     // BMS: shared memory = tables | per-warp areas (stream chunks, then the env's link rows) | compact path table.
     // Everything is addressed from two pinned 32-bit registers (t.sb, wb) plus KParams offsets, which reach the
     // instructions as constant-bank operands -- no per-access re-derivation of warp index times stride.
-    PathTab<BMS> pt;
+    PathTab<SM_> pt;
     pt.base = t.sb;
     uint32_t wb = 0;
     if (BMS) {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.ptab);
         uint4 *dst = reinterpret_cast<uint4 *>(qsmem + p.smem_pt_off);
         for (int i = threadIdx.x; i < (p.ptab_bytes >> 4); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    if (SM_ == 2) {   // the hop-count bytes of the path table (PathTab<2>)
+        const int n_paths = p.N * p.N * p.K;
+        for (int i = threadIdx.x; i < n_paths; i += blockDim.x) qsmem[p.smem_pt_hops + i] = p.path_hops[i];
         __syncthreads();
     }
     if (RING) {
@@ -1151,7 +1159,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
             }
             uint32_t n_rel = 0;
             DefragStats ds = {0u, 0u, 0u};
-            if (advance_and_release<Dim<S_, M_, K_>, typename RowHandle<BMS>::type, PathTab<BMS>, Streams<RING>, FEAT>(
+            if (advance_and_release<Dim<S_, M_, K_>, typename RowHandle<BMS>::type, PathTab<SM_>, Streams<RING>, FEAT>(
                     dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, pt, sm, &ds))
                 err = ENV_ERR_RELEASE_NOT_FOUND;
             QCNT(QRMSA_CNT_RELEASES, n_rel);
@@ -1309,8 +1317,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 DefragStats ds = {0u, 0u, 0u};
                 int rerr;
                 if (p.feat & 2)
-                    rerr = advance_and_release<Dim<0, 0, 0>, uint32_t *, PathTab<false>, Streams<false>, 2>(
-                        dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, PathTab<false>(), Streams<false>(), &ds);
+                    rerr = advance_and_release<Dim<0, 0, 0>, uint32_t *, PathTab<0>, Streams<false>, 2>(
+                        dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel, PathTab<0>(), Streams<false>(), &ds);
                 else
                     rerr = advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel);
                 if (rerr) err = ENV_ERR_RELEASE_NOT_FOUND;
