@@ -240,8 +240,9 @@ __device__ __forceinline__ const uint32_t *cnt_word(const uint32_t *bm, int l, i
 __device__ __forceinline__ unsigned pos_index(const KParams &p, int l, int pair) {
     return (unsigned)(pair * p.E + l);
 }
-__device__ __forceinline__ void pos_store(const KParams &p, uint8_t *pos, int l, int pair, int v) {
-    if (p.pos_bytes) pos[pos_index(p, l, pair)] = (uint8_t)v;   // (no table above 511 slots: release_by_search)
+template <class DM>
+__device__ __forceinline__ void pos_store(const DM &dm, const KParams &p, uint8_t *pos, int l, int pair, int v) {
+    if (dm.has_pos()) pos[pos_index(p, l, pair)] = (uint8_t)v;   // (no table above 511 slots: release_by_search)
 }
 __device__ __forceinline__ int rec_pair(uint32_t rec) { return (int)(((rec & 0xfffu) - ((rec >> 12) & 0xffu)) >> 2); }
 
@@ -258,6 +259,9 @@ struct Dim {
     __device__ __forceinline__ int CAP() const { return S_ ? ((S_ + 1) / 2 + 31) / 32 * 32 : p.CAP; }
     __device__ __forceinline__ int M() const { return M_ ? M_ : p.M; }
     __device__ __forceinline__ int K() const { return K_ ? K_ : p.K; }
+    // is there a position table (qrmsa_create: list indices fit a byte)?  Known at compile time in the specialised kernels,
+    // which then carry only one of the two release paths
+    __device__ __forceinline__ bool has_pos() const { return S_ ? (((S_ + 1) / 2 + 31) / 32 * 32 <= 256) : p.pos_bytes != 0; }
 };
 
 // word `lane` of (x >> b), x a multi-word bitmap spread over the lanes.  Lanes past the data hold 0 and
@@ -466,7 +470,7 @@ __device__ __forceinline__ int commit(const DM &dm, const KParams &p, const BM b
             err = 1;
         } else {
             lists[(unsigned)(mylink * dm.CAP() + mycnt)] = rec;
-            pos_store(p, pos, mylink, s >> 1, mycnt);
+            pos_store(dm, p, pos, mylink, s >> 1, mycnt);
             row_st(bm, cnt_index(mylink, dm.RW()), (uint32_t)(mycnt + 1));
         }
     }
@@ -543,15 +547,17 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
     const int S = dm.S(), M = dm.M(), CAP = dm.CAP();
     const uint32_t a = rq.w & QRMSA_ACTION_MASK;
     const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
-    const int s = a % S;
-    const int rel = (a / S) % M;
-    const int pi = a / (S * M);
+    // action = (pi * M + rel) * S + s: two divisions (by constants in the specialised kernels), remainders by multiply-subtract
+    const uint32_t q = a / (uint32_t)S;
+    const int s = (int)(a - q * (uint32_t)S);
+    const int pi = (int)(q / (uint32_t)M);
+    const int rel = (int)q - pi * M;
     const int m = (M - 1) - rel;
     const int n = t.need(rate * M + m);
     const int path = (src * p.N + dst) * dm.K() + pi;
     const int hops = pt.hops_flags(p, path) & 0x7f;
     const int mylink = pt.link(p, path, lane, hops);
-    if (p.pos_bytes == 0) return release_by_search(dm, p, bm, lists, hops, mylink, s, n, lane);
+    if (!dm.has_pos()) return release_by_search(dm, p, bm, lists, hops, mylink, s, n, lane);
 #ifdef QRMSA_VALIDATE_RELEASE
     const uint32_t target = (uint32_t)(2 * s + n) | ((uint32_t)n << 12);   // centre and width identify the record
 #endif
@@ -580,7 +586,7 @@ __device__ __forceinline__ int release_service(const DM &dm, const KParams &p, c
         } else {
             lst[fpos] = last;
             lst[c - 1] = p.sentinel;   // entries past the count are always the zero-contribution filler
-            pos_store(p, pos, mylink, rec_pair(last), fpos);
+            pos_store(dm, p, pos, mylink, rec_pair(last), fpos);
             row_st(bm, cw, (uint32_t)(c - 1));
         }
     }
@@ -826,7 +832,9 @@ __device__ __forceinline__ int advance_and_release(const DM &dm, const KParams &
     const float now = __uint_as_float(sm.arrival_bits(tr, cur));
     int err = 0;
     while (head.id >= 0 && head.id < cur && head.rel <= now) {
-        const uint4 rq = tr[head.id];
+        // (endpoints and action word in one 8-byte load: taken apart, the compiler fetches .z only after the test on .w)
+        const uint2 zw = *reinterpret_cast<const uint2 *>(&tr[head.id].z);
+        const uint4 rq = make_uint4(0u, 0u, zw.x, zw.y);
         if ((rq.w & (QRMSA_FLAG_ACCEPTED | QRMSA_FLAG_RELEASE_CANCELLED)) == QRMSA_FLAG_ACCEPTED) {
             err |= release_service(dm, p, t, bm, lists, pos, rq, lane, pt);
             n_rel += 1;
@@ -1729,6 +1737,16 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
             *tick = 0;
         }
         for (int i = tid; i < K * D; i += OBS_ENV_THREADS) X[i] = 0.0;   // (its readers passed the barrier that ends the loop)
+        {   // every mask entry is rewritten: zeros here, 16 bytes per store (n_actions is odd, so the env's row starts at any
+            // byte: the unaligned head and tail go byte by byte); the valid candidates are set to 1 in phase 2, two barriers on
+            const int total = K * Mc * S;
+            const int head = min((int)((16u - ((uint32_t)(uintptr_t)mask & 15u)) & 15u), total);
+            const int nvec = (total - head) >> 4;
+            if (tid < head) mask[tid] = 0;
+            uint4 *mv = reinterpret_cast<uint4 *>(mask + head);
+            for (int i = tid; i < nvec; i += OBS_ENV_THREADS) mv[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = head + (nvec << 4) + tid; i < total; i += OBS_ENV_THREADS) mask[i] = 0;
+        }
 
         // ---- phase 0, warp per path: links, availability, free blocks, valid starts of every modulation, usable centres
         for (int pi = warp; pi < K; pi += nw) {
@@ -1738,7 +1756,6 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
             for (int w = lane; w < NW; w += 32) need[pi * NW + w] = 0u;
             if (hops == 0) {   // fewer than k paths for this pair: features stay -1, no valid action (qrmsa.pyx:697)
                 for (int i = lane; i < Mc * 12; i += 32) obs[3 + K + pi * Mc * 12 + i] = -1.f;
-                for (int i = lane; i < Mc * S; i += 32) mask[(size_t)pi * Mc * S + i] = 0;
                 continue;
             }
             const int l = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
@@ -1846,23 +1863,28 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
                 double s1[OBS2_NJ], s2[OBS2_NJ];
 #pragma unroll
                 for (int j = 0; j < OBS2_NJ; ++j) s1[j] = s2[j] = 0.0;
+                // (the common case -- every group of centres has a taker in this warp -- runs without the per-term test)
+                auto sum_link = [&](auto all_c) {
+                    constexpr bool ALL = decltype(all_c)::value != 0;
 #pragma unroll 2
-                for (int q = 0; q < cnt; ++q) {
-                    const uint32_t rec = lst[q];                              // same address on every lane: one broadcast
-                    const int c2r = (int)(rec & 0xfffu);
-                    const uint32_t goff = ((rec >> 23) + 1u) * (8u * (uint32_t)D);
-                    const double phin = t.PHIN(rec >> 20);
+                    for (int q = 0; q < cnt; ++q) {
+                        const uint32_t rec = lst[q];                              // same address on every lane: one broadcast
+                        const int c2r = (int)(rec & 0xfffu);
+                        const uint32_t goff = ((rec >> 23) + 1u) * (8u * (uint32_t)D);
+                        const double phin = t.PHIN(rec >> 20);
 #pragma unroll
-                    for (int j = 0; j < OBS2_NJ; ++j) {
-                        if (!wany[j]) continue;                                 // warp-uniform
-                        const uint32_t a_inv = t.sb + 8u * (uint32_t)abs(c2r - c2j[j]);
-                        double g, inv;
-                        asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(a_inv + goff), "n"(lay::INV));
-                        asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(a_inv), "n"(lay::INV));
-                        s1[j] += g;
-                        s2[j] = fma(phin, inv, s2[j]);
+                        for (int j = 0; j < OBS2_NJ; ++j) {
+                            if (!ALL && !wany[j]) continue;                         // warp-uniform
+                            const uint32_t a_inv = t.sb + 8u * (uint32_t)abs(c2r - c2j[j]);
+                            double g, inv;
+                            asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(a_inv + goff), "n"(lay::INV));
+                            asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(a_inv), "n"(lay::INV));
+                            s1[j] += g;
+                            s2[j] = fma(phin, inv, s2[j]);
+                        }
                     }
-                }
+                };
+                if (wany[0] && wany[1] && wany[2] && wany[3]) sum_link(IntC<1>()); else sum_link(IntC<0>());
                 const double w1 = t.W1(l), w2 = t.W2(l);   // W2 is stored negated
 #pragma unroll
                 for (int j = 0; j < OBS2_NJ; ++j) {
@@ -1931,73 +1953,58 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
             const double2 pg = __ldg(p.path_gn + path);
             const uint32_t *vrow = validM + (pi * 8 + (M - 1) - mod_of(mi0)) * VW;   // bitmaps are kept per modulation, best first
             const double *Xp = X + pi * D + n;
-            // compaction (a word of the bitmap is its own ballot) and the all-zero mask rows of the unit
+            // compaction: a word of the bitmap is its own ballot
             int cnt = 0;
             for (int it = 0; it * 32 < S; ++it) {
                 const uint32_t w = vrow[it];
                 if ((w >> lane) & 1u) slist[cnt + __popc(w & ((1u << lane) - 1u))] = (uint16_t)(lane + it * 32);
                 cnt += __popc(w);
             }
-            for (int mi = mi0; mi < mi1; ++mi) {
-                uint8_t *mrow = mask + (size_t)pi * Mc * S + (size_t)mi * S;
-                for (int s = lane; s < S; s += 32) mrow[s] = 0;
-            }
             __syncwarp();
-            double g_cached[OBS2_NIT];
-            int s_cached[OBS2_NIT];
-#pragma unroll
-            for (int c = 0; c < OBS2_NIT; ++c) {
-                g_cached[c] = 0.0;
-                s_cached[c] = -1;
-                if (c * 32 < cnt) {   // warp-uniform
-                    const int idx = c * 32 + lane;
-                    if (idx < cnt) {
-                        const int s = slist[idx];
-                        const double acc = gn_base(p, t, pg, s, n, ncls).with(Xp[2 * s]);
-                        g_cached[c] = 10.0 * log10(1.0 / acc);
-                        s_cached[c] = s;
+            // The modulations of a run see the same valid starts with the same GSNR g and differ only in their threshold:
+            // the integer statistics (count, sum s, sum s^2, max s) and the moments of y = g - th0 (th0: the run's first
+            // threshold) are taken ONCE per unit; a modulation's normalised margin (g - th) / |th| = (y + (th0 - th)) / |th|
+            // follows from them in closed form.  What stays per (start, modulation) is the mask bit.  np.round(x, 10) >= 0
+            // (osnr.pyx:366; rint(x * 1e10) >= 0, -0.0 included) <=> x * 1e10 >= -0.5 <=> g >= th - 0.5e-10 |th|; the
+            // rounding itself (<= 5e-11) is far below the float32 features and is not applied to the moments.
+            const double th0 = p.mod_thr_nomargin[mod_of(mi0)];
+            uint8_t *mrow0 = mask + (size_t)(pi * Mc + mi0) * S;
+            int c_s = 0, c_max = -1;
+            uint32_t c_s2 = 0u;   // sum of s^2 over <= 960 slots < 2^32
+            double v_sum = 0.0, v_max = -1e300, v_sq = 0.0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < cnt; c0 += 32) {
+                const int idx = c0 + lane;
+                if (idx < cnt) {
+                    const int s = slist[idx];
+                    const double acc = gn_base(p, t, pg, s, n, ncls).with(Xp[2 * s]);
+                    const double g = -10.0 * log10(acc);
+                    const double y = g - th0;
+                    c_s += s; c_s2 += (uint32_t)(s * s); c_max = s;   // starts are held in ascending order
+                    v_sum += y; v_max = fmax(v_max, y); v_sq = fma(y, y, v_sq);
+                    for (int mi = mi0; mi < mi1; ++mi) {
+                        const double th = p.mod_thr_nomargin[mod_of(mi)];
+                        if (g >= fma(-0.5e-10, fabs(th), th)) mrow0[(mi - mi0) * S + s] = 1;
                     }
                 }
             }
-            // lane j keeps the reduced statistics of the unit's j-th modulation; the features are finished side by side
-            int k_n = 0, k_s = 0, k_max = -1;
-            long long k_s2 = 0;
-            double k_sum = 0.0, k_vmax = -1e300, k_sq = 0.0;
-            for (int mi = mi0; mi < mi1; ++mi) {
-                const double th = p.mod_thr_nomargin[mod_of(mi)], ath = fabs(th);
-                uint8_t *mrow = mask + (size_t)pi * Mc * S + (size_t)mi * S;
-                // count, sum s, sum s^2, max s in integers; sum norm, max norm, sum norm^2 in FP64
-                int c_n = 0, c_s = 0, c_max = -1;
-                long long c_s2 = 0;
-                double v_sum = 0.0, v_max = -1e300, v_sq = 0.0;
+            c_s = __reduce_add_sync(FULL, c_s); c_s2 = __reduce_add_sync(FULL, c_s2); c_max = __reduce_max_sync(FULL, c_max);
 #pragma unroll
-                for (int c = 0; c < OBS2_NIT; ++c) {
-                    const int s = s_cached[c];
-                    if (s >= 0) {
-                        // np.round(x, 10) (osnr.pyx:366): rint(x * 1e10) / 1e10; its sign decides the mask bit
-                        const double r10 = rint(((g_cached[c] - th) / ath) * 1e10);
-                        const double nrm = r10 / 1e10;
-                        if (r10 >= 0.0) mrow[s] = 1;
-                        c_n += 1; c_s += s; c_s2 += (long long)s * s; c_max = max(c_max, s);
-                        v_sum += nrm; v_max = fmax(v_max, nrm); v_sq = fma(nrm, nrm, v_sq);
-                    }
-                }
-                c_n = __reduce_add_sync(FULL, c_n); c_s = __reduce_add_sync(FULL, c_s); c_max = __reduce_max_sync(FULL, c_max);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    c_s2 += __shfl_xor_sync(FULL, c_s2, o);
-                    v_sum += __shfl_xor_sync(FULL, v_sum, o);
-                    v_sq += __shfl_xor_sync(FULL, v_sq, o);
-                    v_max = fmax(v_max, __shfl_xor_sync(FULL, v_max, o));
-                }
-                if (lane == mi - mi0) { k_n = c_n; k_s = c_s; k_max = c_max; k_s2 = c_s2; k_sum = v_sum; k_vmax = v_max; k_sq = v_sq; }
+            for (int o = 16; o > 0; o >>= 1) {
+                v_sum += __shfl_xor_sync(FULL, v_sum, o);
+                v_sq += __shfl_xor_sync(FULL, v_sq, o);
+                v_max = fmax(v_max, __shfl_xor_sync(FULL, v_max, o));
             }
+            // lane j finishes the features of the unit's j-th modulation
             if (lane < mi1 - mi0) {
-                const double cntv = (double)k_n, total_av = pstat[pi * 3 + 0];
+                const double cntv = (double)cnt, total_av = pstat[pi * 3 + 0];
                 double f_avg = 0, f_std = 0, f_max = 0, best = 0, omean = 0, ovar = 0;
-                if (k_n > 0) {
-                    f_avg = (double)k_s / cntv; omean = k_sum / cntv; f_max = (double)k_max; best = fmax(k_vmax, 0.0);
-                    f_std = sqrt(fmax((double)k_s2 / cntv - f_avg * f_avg, 0.0));
+                if (cnt > 0) {
+                    const double th = p.mod_thr_nomargin[mod_of(mi0 + lane)], ia = 1.0 / fabs(th), dl = th0 - th;
+                    const double k_sum = fma(cntv, dl, v_sum) * ia;
+                    const double k_sq = fma(dl, fma(cntv, dl, 2.0 * v_sum), v_sq) * (ia * ia);
+                    f_avg = (double)c_s / cntv; omean = k_sum / cntv; f_max = (double)c_max; best = fmax((v_max + dl) * ia, 0.0);
+                    f_std = sqrt(fmax((double)c_s2 / cntv - f_avg * f_avg, 0.0));
                     ovar = fmax(k_sq / cntv - omean * omean, 0.0);
                 }
                 float *o = obs + 3 + K + (pi * Mc + mi0 + lane) * 12;

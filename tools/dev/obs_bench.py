@@ -19,4 +19,6 @@ for _ in range(5): env.engine.observation(obs, mask)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
 import hashlib
 dig = hashlib.sha256(obs.cpu().numpy().tobytes() + mask.cpu().numpy().tobytes()).hexdigest()[:16]
+if len(sys.argv) > 3:   # keep a sample of the outputs: variants are compared here afterwards (features to 2e-6, mask bit for bit)
+    np.savez_compressed(sys.argv[3], obs=obs[:1024].cpu().numpy(), mask=np.packbits(mask[:1024].cpu().numpy(), axis=1))
 print(f"{sys.argv[2] if len(sys.argv) > 2 else 'in-tree'} sha {dig} k_observation: {n} envs in {dt*1e3:.2f} ms = {n/dt:,.0f} env/s; valid actions per env {float(mask.sum())/n:.0f}")
