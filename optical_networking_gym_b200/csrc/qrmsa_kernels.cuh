@@ -1672,11 +1672,15 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
 template <int V> struct IntC { static constexpr int value = V; };
 constexpr int OBS2_NJ = 4;                          // centres per thread
 constexpr int OBS2_MAX_D = OBS2_NJ * OBS_ENV_THREADS;
-constexpr int OBS2_NIT = (OBS2_MAX_D / 2 + 31) / 32;   // starts per lane in the per-path phase (320 slots / 32 lanes)
+constexpr int OBS2_STAGE = 16;                      // channel records decoded and staged per warp and pass of a link's list
 
 __host__ __device__ inline int obs2_env_smem(int K, int D, int W, int E) {
     const int VW = W + 1, NW = (D + 31) >> 5, S = D / 2, NWARP = OBS_ENV_THREADS / 32;
-    const int words = K * 8 * VW + K * NW + K * VW + K * 32 + K + E + 4 + (NWARP * S + 1) / 2;
+    // scratch after the fixed arrays: phase 2 keeps the compacted valid starts of each warp's unit there (u16 [NWARP][S]);
+    // phase 1 the compacted needed centres (u16 [D]) and, 16-byte aligned, each warp's 16 staged records of 16 bytes
+    const int scratch2 = 2 * NWARP * S, scratch1 = 2 * D + 16 + NWARP * OBS2_STAGE * 16;
+    const int scratch = (scratch1 > scratch2 ? scratch1 : scratch2);
+    const int words = K * 8 * VW + K * NW + K * VW + K * 32 + K + E + 4 + (scratch + 3) / 4;
     return ((8 * K * D + 8 * 3 * K + 4 * words) + 15) / 16 * 16;
 }
 
@@ -1833,68 +1837,107 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
             }
         }
         env_sync();
-        // ---- phase 1, thread per four centres: neighbour sums link by link (core/osnr.pyx:64-94, table form)
+        // ---- phase 1: neighbour sums link by link (core/osnr.pyx:64-94, table form).  Only centres that some path can use
+        // are summed: their union over the paths is compacted (every warp builds the same list -- identical stores, no
+        // barrier) and thread t owns compacted centres t, t + 160, ... for the whole request, so the sums of a link stay in
+        // registers and X[p][c2] has one writer.  nj = ceil(needed / 160) centre groups are live (a template parameter of
+        // the inner loop: no per-term test).  A link's records are decoded once -- centre, G-row address, phi * bandwidth --
+        // 16 per pass, lane per record, into the warp's staging area, and the loop over them is one 16-byte broadcast
+        // LDS per record and, per centre, |d|, two addresses, two LDS.64, DADD, DFMA.
         {
-            int c2j[OBS2_NJ];
-            uint32_t myneed[OBS2_NJ];   // bit pi: path pi uses this centre
+            unsigned char *scr = reinterpret_cast<unsigned char *>(tick + 4);
+            uint16_t *clist = reinterpret_cast<uint16_t *>(scr);
+            const uint32_t stage = (smem_u32(scr + 2 * D) + 15u) / 16u * 16u + (uint32_t)(warp * OBS2_STAGE * 16);
+            uint32_t uw = 0u;
+            if (lane < NW)
+                for (int pi = 0; pi < K; ++pi) uw |= need[pi * NW + lane];
+            int incl = __popc(uw);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int P = __shfl_sync(FULL, incl, 31);
+            const int excl = incl - __popc(uw);
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t word = __shfl_sync(FULL, uw, w);
+                const int base = __shfl_sync(FULL, excl, w);
+                if ((word >> lane) & 1u) clist[base + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(w * 32 + lane);
+            }
+            __syncwarp();
+            const int nj = (P + OBS_ENV_THREADS - 1) / OBS_ENV_THREADS;
+            int c2j8[OBS2_NJ];            // 8 * centre (byte offset into a table row)
+            uint32_t myneed[OBS2_NJ];     // bit pi: path pi uses this centre
 #pragma unroll
             for (int j = 0; j < OBS2_NJ; ++j) {
-                c2j[j] = tid + j * OBS_ENV_THREADS;
+                const int idx = tid + j * OBS_ENV_THREADS;
+                int c2 = 0;
                 uint32_t mset = 0u;
-                if (c2j[j] < D)
-                    for (int pi = 0; pi < K; ++pi) mset |= ((need[pi * NW + (c2j[j] >> 5)] >> (c2j[j] & 31)) & 1u) << pi;
+                if (idx < P) {
+                    c2 = clist[idx];
+                    for (int pi = 0; pi < K; ++pi) mset |= ((need[pi * NW + (c2 >> 5)] >> (c2 & 31)) & 1u) << pi;
+                }
+                c2j8[j] = 8 * c2;
                 myneed[j] = mset;
             }
+            const uint32_t d8 = 8u * (uint32_t)D;
 #pragma unroll 1
-            for (int l = 0; l < E; ++l) {
+            for (int l = 0; l < E && nj > 0; ++l) {
                 const uint32_t pm = lmask[l];
                 if (!pm) continue;      // no path of this request crosses the link
-                bool want[OBS2_NJ], wany[OBS2_NJ];
                 bool some = false;
 #pragma unroll
-                for (int j = 0; j < OBS2_NJ; ++j) {
-                    want[j] = (myneed[j] & pm) != 0u;
-                    wany[j] = __any_sync(FULL, want[j]);
-                    some |= wany[j];
-                }
-                if (!some) continue;
+                for (int j = 0; j < OBS2_NJ; ++j) some |= (myneed[j] & pm) != 0u;
+                if (!__any_sync(FULL, some)) continue;
                 const int cnt = (int)bm[(unsigned)(l * p.RW + p.RW - 1)];
                 const uint32_t *lst = lists + (unsigned)(l * CAP);
                 double s1[OBS2_NJ], s2[OBS2_NJ];
 #pragma unroll
                 for (int j = 0; j < OBS2_NJ; ++j) s1[j] = s2[j] = 0.0;
-                // (the common case -- every group of centres has a taker in this warp -- runs without the per-term test)
-                auto sum_link = [&](auto all_c) {
-                    constexpr bool ALL = decltype(all_c)::value != 0;
-#pragma unroll 2
-                    for (int q = 0; q < cnt; ++q) {
-                        const uint32_t rec = lst[q];                              // same address on every lane: one broadcast
-                        const int c2r = (int)(rec & 0xfffu);
-                        const uint32_t goff = ((rec >> 23) + 1u) * (8u * (uint32_t)D);
+#pragma unroll 1
+                for (int q0 = 0; q0 < cnt; q0 += OBS2_STAGE) {
+                    __syncwarp();   // the previous pass has been read
+                    if (lane < OBS2_STAGE) {   // (entries past the count hold the zero-contribution filler record; CAP is a multiple of 32)
+                        const uint32_t rec = lst[q0 + lane];
                         const double phin = t.PHIN(rec >> 20);
-#pragma unroll
-                        for (int j = 0; j < OBS2_NJ; ++j) {
-                            if (!ALL && !wany[j]) continue;                         // warp-uniform
-                            const uint32_t a_inv = t.sb + 8u * (uint32_t)abs(c2r - c2j[j]);
-                            double g, inv;
-                            asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(a_inv + goff), "n"(lay::INV));
-                            asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(a_inv), "n"(lay::INV));
-                            s1[j] += g;
-                            s2[j] = fma(phin, inv, s2[j]);
-                        }
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stage + 16u * (uint32_t)lane),
+                                     "r"(8u * (rec & 0xfffu)), "r"(t.sb + ((rec >> 23) + 1u) * d8),
+                                     "r"((uint32_t)__double2loint(phin)), "r"((uint32_t)__double2hiint(phin)) : "memory");
                     }
-                };
-                if (wany[0] && wany[1] && wany[2] && wany[3]) sum_link(IntC<1>()); else sum_link(IntC<0>());
+                    __syncwarp();
+                    const int nq = min(OBS2_STAGE, cnt - q0);
+                    auto sum_pass = [&](auto njc) {
+                        constexpr int NJ = decltype(njc)::value;
+#pragma unroll 2
+                        for (int q = 0; q < nq; ++q) {
+                            uint32_t c2r8, gb, plo, phi;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c2r8), "=r"(gb), "=r"(plo), "=r"(phi)
+                                         : "r"(stage + 16u * (uint32_t)q));
+                            const double phin = __hiloint2double((int)phi, (int)plo);
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j) {
+                                const uint32_t dd = (uint32_t)abs((int)c2r8 - c2j8[j]);
+                                double g, inv;
+                                asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(gb + dd), "n"(lay::INV));
+                                asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(t.sb + dd), "n"(lay::INV));
+                                s1[j] += g;
+                                s2[j] = fma(phin, inv, s2[j]);
+                            }
+                        }
+                    };
+                    if (nj >= 4) sum_pass(IntC<4>()); else if (nj == 3) sum_pass(IntC<3>());
+                    else if (nj == 2) sum_pass(IntC<2>()); else sum_pass(IntC<1>());
+                }
                 const double w1 = t.W1(l), w2 = t.W2(l);   // W2 is stored negated
 #pragma unroll
                 for (int j = 0; j < OBS2_NJ; ++j) {
-                    if (!want[j]) continue;
-                    const double y = fma(w2, s2[j], w1 * s1[j]);
                     uint32_t ps = myneed[j] & pm;
+                    if (!ps) continue;
+                    const double y = fma(w2, s2[j], w1 * s1[j]);
                     while (ps) {
                         const int pi = __ffs(ps) - 1;
                         ps &= ps - 1u;
-                        X[pi * D + c2j[j]] += y;                                // this thread owns the centre: no race
+                        X[pi * D + (c2j8[j] >> 3)] += y;                         // this thread owns the centre: no race
                     }
                 }
             }
@@ -1937,17 +1980,26 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
         // ---- phase 2: units = (path, run of modulations that need the same number of slots), handed to the warps by a
         // ticket.  The unit's valid starts are compacted so that every lane holds one; GSNR once per start, then mask
         // bytes and the 12 features per modulation of the unit (qrmsa.pyx:583-781).
+        // the runs are the same on every path (slots needed depend on bit rate and modulation only): lane j < Mc holds the
+        // slot count of block j, a ballot marks the heads of the runs
+        const int my_n = lane < Mc ? t.need(rate * M + mod_of(lane)) : -1;
+        const int prev_n = __shfl_up_sync(FULL, my_n, 1);
+        const uint32_t heads = __ballot_sync(FULL, lane < Mc && (lane == 0 || prev_n != my_n));
+        const int R = __popc(heads);
+        const uint32_t rcpR = (65536u + (uint32_t)R - 1u) / (uint32_t)R;   // u / R for the few tickets of a request
         for (;;) {
             int u = 0;
             if (lane == 0) u = atomicAdd(tick, 1);
             u = __shfl_sync(FULL, u, 0);
-            if (u >= K * Mc) break;
-            const int pi = u / Mc, mi0 = u - pi * Mc;
+            if (u >= K * R) break;
+            const int pi = (int)(((uint32_t)u * rcpR) >> 16);
             if (phops[pi] == 0) continue;
-            const int n = t.need(rate * M + mod_of(mi0));
-            if (mi0 > 0 && t.need(rate * M + mod_of(mi0 - 1)) == n) continue;   // not the head of its run
-            int mi1 = mi0 + 1;
-            while (mi1 < Mc && t.need(rate * M + mod_of(mi1)) == n) ++mi1;
+            uint32_t h = heads;
+            for (int i = u - pi * R; i > 0; --i) h &= h - 1u;
+            const int mi0 = __ffs(h) - 1;
+            h &= h - 1u;
+            const int mi1 = h ? __ffs(h) - 1 : Mc;
+            const int n = __shfl_sync(FULL, my_n, mi0);
             const int ncls = t.cls(rate * M + mod_of(mi0));
             const int path = pbase + pi;
             const double2 pg = __ldg(p.path_gn + path);
