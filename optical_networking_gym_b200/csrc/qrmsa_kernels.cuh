@@ -1795,32 +1795,30 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
                 need[pi * NW + w] = bits;
             }
             // free blocks of the path availability (qrmsa.pyx:631-646): lane j looks at word j; a block is counted in the
-            // word that holds its last slot, its first slot is the nearest block start at or below it
+            // word that holds its last slot.  A block that reaches bit 0 of its word continues the free run that ends at the
+            // top of the word below (`carry`, handed up through all-free words)
             int b_free = 0, b_n = 0, b_len = 0, b_len2 = 0;
-            if (lane < W) {
-                const uint32_t *av = avs + pi * VW;
-                auto real = [&](int j) -> uint32_t {   // word j of the availability without the virtual slot at S
-                    if (j < 0 || j >= W) return 0u;
-                    uint32_t v = av[j];
-                    if (j == (S >> 5)) v &= (1u << (S & 31)) - 1u;
-                    return v;
-                };
-                const uint32_t wv = real(lane), up = real(lane + 1);
+            {
+                uint32_t wv = 0u;   // word `lane` of the availability without the virtual slot at S
+                if (lane < W) {
+                    wv = avs[pi * VW + lane];
+                    if (lane == (S >> 5)) wv &= (1u << (S & 31)) - 1u;
+                }
                 b_free = __popc(wv);
+                const int top = __clz((int)~wv);   // free slots at the top of the word (32: the whole word)
+                int carry = 0, run = 0;
+                for (int w = 0; w < W; ++w) {
+                    if (lane == w) carry = run;
+                    const int tl = __shfl_sync(FULL, top, w);
+                    run = tl == 32 ? run + 32 : tl;
+                }
+                const uint32_t up = __shfl_down_sync(FULL, wv, 1);   // (lanes at and past W hold 0)
                 uint32_t ends = wv & ~((wv >> 1) | (up << 31));
                 while (ends) {
                     const int eb = __ffs(ends) - 1;
                     ends &= ends - 1u;
-                    int j = lane, start;
-                    uint32_t cand = wv & ((eb == 31) ? 0xffffffffu : ((2u << eb) - 1u));
-                    for (;;) {   // block start: highest free slot at or below the end whose lower neighbour is occupied
-                        const uint32_t word = j == lane ? wv : real(j);
-                        const uint32_t starts = cand & ~((word << 1) | (real(j - 1) >> 31));
-                        if (starts) { start = (j << 5) + 31 - __clz(starts); break; }
-                        j -= 1;
-                        cand = real(j);
-                    }
-                    const int len = (lane << 5) + eb - start + 1;
+                    const uint32_t occ = ~wv & ((eb == 31) ? 0xffffffffu : ((2u << eb) - 1u));   // occupied slots below the end
+                    const int len = occ ? eb - 31 + __clz((int)occ) : eb + 1 + carry;
                     b_n += 1; b_len += len; b_len2 += len * len;
                 }
             }
@@ -2053,17 +2051,18 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
                 double f_avg = 0, f_std = 0, f_max = 0, best = 0, omean = 0, ovar = 0;
                 if (cnt > 0) {
                     const double th = p.mod_thr_nomargin[mod_of(mi0 + lane)], ia = 1.0 / fabs(th), dl = th0 - th;
+                    const double icnt = 1.0 / cntv;   // (the features are float32: one reciprocal serves the four means)
                     const double k_sum = fma(cntv, dl, v_sum) * ia;
                     const double k_sq = fma(dl, fma(cntv, dl, 2.0 * v_sum), v_sq) * (ia * ia);
-                    f_avg = (double)c_s / cntv; omean = k_sum / cntv; f_max = (double)c_max; best = fmax((v_max + dl) * ia, 0.0);
-                    f_std = sqrt(fmax((double)c_s2 / cntv - f_avg * f_avg, 0.0));
-                    ovar = fmax(k_sq / cntv - omean * omean, 0.0);
+                    f_avg = (double)c_s * icnt; omean = k_sum * icnt; f_max = (double)c_max; best = fmax((v_max + dl) * ia, 0.0);
+                    f_std = sqrt(fmax((double)c_s2 * icnt - f_avg * f_avg, 0.0));
+                    ovar = fmax(k_sq * icnt - omean * omean, 0.0);
                 }
                 float *o = obs + 3 + K + (pi * Mc + mi0 + lane) * 12;
                 o[0] = (float)(cntv * inv_S);
                 o[1] = (float)(f_avg * inv_S1);
                 o[2] = (float)(f_std * inv_S1);
-                o[3] = (float)fmax(((double)n - 5.5) / 3.5, 0.0);
+                o[3] = (float)fmax(((double)n - 5.5) * (1.0 / 3.5), 0.0);
                 o[4] = (float)(2.0 * (total_av - 0.5 * (double)S) * inv_S);
                 o[5] = (float)pstat[pi * 3 + 1];
                 o[6] = (float)pstat[pi * 3 + 2];
