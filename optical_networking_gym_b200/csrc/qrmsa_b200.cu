@@ -46,6 +46,8 @@ struct qrmsa_ctx {
     int obs_grid = 0, obs_epc = 0, obs_env_smem = 0;   // k_observation: envs per CTA, shared memory per env
     size_t obs_smem = 0;
     int obs2_grid = 0, obs2_epc = 0, obs2_env_smem = 0;   // k_observation_links (spectra up to 320 slots)
+    int hs2_grid = 0, hs2_epc = 0;                        // k_step_highest_snr_links (same per-env shared-memory area)
+    size_t hs2_smem = 0;
     size_t obs2_smem = 0;
     std::string err;
 };
@@ -390,6 +392,26 @@ static int create_impl(qrmsa_ctx *ctx, const qrmsa_static_tables *t, int n_envs,
             CK(cudaFuncSetAttribute(k_step_highest_snr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->cta_smem));
             const int per_sm = std::max(1, std::min((int)((size_t)smem_sm / (ctx->cta_smem + 1024)), 2048 / (epc * OBS_ENV_THREADS)));
             ctx->cta_grid = std::min((n_envs + epc - 1) / epc, ctx->sm_count * per_sm);
+        }
+    }
+    // link-major highest-SNR kernel: spectra up to 320 slots and at most 8 paths per pair (one bit per path in the link
+    // sets); its static shared memory (the per-warp picks) comes off the budget
+    if (D <= OBS2_MAX_D && K <= 8) {
+        cudaFuncAttributes fh{};
+        CK(cudaFuncGetAttributes(&fh, k_step_highest_snr_links));
+        const size_t budget_h = (size_t)ctx->smem_optin - fh.sharedSizeBytes;
+        ctx->obs2_env_smem = obs2_env_smem(K, D, kp.W, E);
+        int e2 = OBS_MAX_EPC;
+        while (e2 > 1 && (size_t)kp.blob_bytes + (size_t)e2 * ctx->obs2_env_smem > budget_h) e2 >>= 1;
+        const size_t need2 = (size_t)kp.blob_bytes + (size_t)e2 * ctx->obs2_env_smem;
+        if (need2 <= budget_h &&
+            cudaFuncSetAttribute(k_step_highest_snr_links, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need2) == cudaSuccess) {
+            ctx->hs2_epc = e2;
+            ctx->hs2_smem = need2;
+            const int per_sm = std::max(1, std::min((int)((size_t)smem_sm / (need2 + 1024)), 2048 / (e2 * OBS_ENV_THREADS)));
+            ctx->hs2_grid = std::min((n_envs + e2 - 1) / e2, ctx->sm_count * per_sm);
+        } else {
+            (void)cudaGetLastError();
         }
     }
     // ---- observation kernel: route-length normalisation (qrmsa.pyx:676-690) and launch shape
@@ -748,8 +770,10 @@ extern "C" int qrmsa_step_heuristic(qrmsa_ctx *ctx, int policy, int n_steps, voi
         else if (bsm) k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT, 1><<<g, th, bsm, st>>>(kp, n_steps);
         else k_step_policy<0, 0, 0, POLICY_LB_FIRST_FIT><<<g, th, sm, st>>>(kp, n_steps);
     } else if (policy == QRMSA_POLICY_HIGHEST_SNR) {
-        if (!ctx->cta_grid) { ctx->err = "highest-SNR policy needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
-        k_step_highest_snr<<<ctx->cta_grid, ctx->cta_epc * OBS_ENV_THREADS, ctx->cta_smem, st>>>(kp, n_steps, ctx->cta_epc, ctx->cta_env_smem);
+        if (ctx->hs2_grid)
+            k_step_highest_snr_links<<<ctx->hs2_grid, ctx->hs2_epc * OBS_ENV_THREADS, ctx->hs2_smem, st>>>(kp, n_steps, ctx->hs2_epc, ctx->obs2_env_smem);
+        else if (!ctx->cta_grid) { ctx->err = "highest-SNR policy needs more shared memory than the device offers"; return QRMSA_ERR_UNSUPPORTED; }
+        else k_step_highest_snr<<<ctx->cta_grid, ctx->cta_epc * OBS_ENV_THREADS, ctx->cta_smem, st>>>(kp, n_steps, ctx->cta_epc, ctx->cta_env_smem);
     } else {
         CK(cudaMemsetAsync(kp.work, 0, 4, st));
         if (c320 && bsm) k_step_policy<320, 6, 5, POLICY_LOAD_BALANCING, 1><<<g, th, bsm, st>>>(kp, n_steps);

@@ -1692,108 +1692,88 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {   // bit i -> bit 2i
     return x;
 }
 
-__global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
-    k_observation_links(const KParams p, const double *__restrict__ path_len_norm, const double inv_max_rate,
-                        float *__restrict__ obs_out, uint8_t *__restrict__ mask_out, const int obs_dim, const int n_actions,
-                        const int epc, const int env_smem) {
-    __shared__ uint64_t mbar;
-    stage_tables(p, &mbar);
-    Tab t;
-    t.init();
+// One env's shared-memory area of the link-major kernels (k_observation_links, k_step_highest_snr_links), after the table blob
+struct LinkArea {
+    double *X, *pstat;                   // [K][D] neighbour sum per path and centre; [K][3] free slots, mean / std of the free blocks
+    uint32_t *validM, *need, *avs;       // [K][8][VW] valid starts per modulation; [K][NW] usable centres; [K][VW] availability
+    int *plink, *phops;                  // [K][32] link ids; [K] hop counts
+    uint32_t *lmask;                     // [E] paths crossing link l (0: none)
+    int *tick, *smax;                    // work ticket of the per-path phase; max_modulation_idx of the open request
+    unsigned char *scr;                  // scratch (obs2_env_smem): compacted centres + staged records, later compacted starts
+    __device__ __forceinline__ void carve(unsigned char *base, int K, int D, int VW, int NW, int E) {
+        X = reinterpret_cast<double *>(base);
+        pstat = X + (size_t)K * D;
+        validM = reinterpret_cast<uint32_t *>(pstat + 3 * K);
+        need = validM + K * 8 * VW;
+        avs = need + K * NW;
+        plink = reinterpret_cast<int *>(avs + K * VW);
+        phops = plink + K * 32;
+        lmask = reinterpret_cast<uint32_t *>(phops + K);
+        tick = reinterpret_cast<int *>(lmask + E);
+        smax = tick + 1;
+        scr = reinterpret_cast<unsigned char *>(tick + 4);
+    }
+};
+
+// Phase 0 of a request, warp per path: links, availability, valid starts of every modulation, usable centres; with STATS
+// (observation) the path-length feature, the free-block statistics and the -1 features of a missing path.
+template <bool STATS>
+__device__ __forceinline__ void links_open_paths(const KParams &p, const Tab &t, const LinkArea &ar, const uint32_t *bm, const int pbase,
+                                                 const int rate, const int warp, const int lane, float *obs,
+                                                 const double *__restrict__ path_len_norm) {
     const Dim<0, 0, 0> dm(p);
-    const int S = p.S, W = p.W, M = p.M, Mc = p.Mc, K = p.K, D = p.D, CAP = p.CAP, E = p.E;
+    const int S = p.S, W = p.W, M = p.M, K = p.K, D = p.D;
     const int VW = W + 1, NW = (D + 31) >> 5;
-    const int slot = threadIdx.x / OBS_ENV_THREADS;
-    auto env_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(OBS_ENV_THREADS) : "memory"); };
-    unsigned char *base = qsmem + p.blob_bytes + (size_t)slot * env_smem;
-    double *X = reinterpret_cast<double *>(base);                       // [K][D]   neighbour sum per path and centre
-    double *pstat = X + (size_t)K * D;                                  // [K][3]   free slots, mean / std of the free blocks
-    uint32_t *validM = reinterpret_cast<uint32_t *>(pstat + 3 * K);     // [K][8][VW] valid-start bitmaps per modulation
-    uint32_t *need = validM + K * 8 * VW;                               // [K][NW]  centres some modulation can use
-    uint32_t *avs = need + K * NW;                                      // [K][VW]  path availability (+ the virtual slot)
-    int *plink = reinterpret_cast<int *>(avs + K * VW);                 // [K][32]  link ids
-    int *phops = plink + K * 32;                                        // [K]
-    uint32_t *lmask = reinterpret_cast<uint32_t *>(phops + K);          // [E]      paths crossing link l (0: none)
-    int *tick = reinterpret_cast<int *>(lmask + E);                     // [1]      work ticket of the per-path phase
-    int *smax = tick + 1;                                               // [1]      max_modulation_idx of the open request
-    const int tid = threadIdx.x - slot * OBS_ENV_THREADS, lane = tid & 31, warp = tid >> 5;
     constexpr int nw = OBS_ENV_THREADS >> 5;
-    uint16_t *slist = reinterpret_cast<uint16_t *>(tick + 4) + warp * S;   // [nw][S]  valid starts of the open unit, compacted
-    const double inv_S = 1.0 / (double)S, inv_S1 = 1.0 / (double)(S - 1);
-
-    for (int i = tid; i < E; i += OBS_ENV_THREADS) lmask[i] = 0u;
-    env_sync();
-    for (int env = blockIdx.x * epc + slot; env < p.n_envs; env += gridDim.x * epc) {
-        const int4 st = p.estate[env];
-        float *obs = obs_out + (size_t)env * obs_dim;
-        uint8_t *mask = mask_out + (size_t)env * n_actions;
-        const int cur = st.x < p.n_req ? st.x : p.n_req - 1;
-        const uint4 rq = p.trace[(size_t)env * p.T + cur];
-        const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
-        const uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
-        const uint32_t *lists = p.lists + (size_t)env * E * CAP;
-        const int pbase = (src * p.N + dst) * K;
-        if (tid == 0) {
-            obs[0] = (float)((double)t.rate(rate) * inv_max_rate);                       // qrmsa.pyx:654-665
-            obs[1] = (float)(p.N > 1 ? (double)src / (double)(p.N - 1) : 0.0);
-            obs[2] = (float)(p.N > 1 ? (double)dst / (double)(p.N - 1) : 0.0);
-            mask[n_actions - 1] = 1;                                                        // qrmsa.pyx:766
-            *tick = 0;
+    double *pstat = ar.pstat;
+    uint32_t *validM = ar.validM, *need = ar.need, *avs = ar.avs, *lmask = ar.lmask;
+    int *plink = ar.plink, *phops = ar.phops;
+    for (int pi = warp; pi < K; pi += nw) {
+        const int path = pbase + pi;
+        const int hops = __ldg(p.path_hops + path) & 0x7f;
+        if (lane == 0) {
+            phops[pi] = hops;
+            if (STATS) obs[3 + pi] = hops ? (float)path_len_norm[path] : 0.f;
         }
-        for (int i = tid; i < K * D; i += OBS_ENV_THREADS) X[i] = 0.0;   // (its readers passed the barrier that ends the loop)
-        {   // every mask entry is rewritten: zeros here, 16 bytes per store (n_actions is odd, so the env's row starts at any
-            // byte: the unaligned head and tail go byte by byte); the valid candidates are set to 1 in phase 2, two barriers on
-            const int total = K * Mc * S;
-            const int head = min((int)((16u - ((uint32_t)(uintptr_t)mask & 15u)) & 15u), total);
-            const int nvec = (total - head) >> 4;
-            if (tid < head) mask[tid] = 0;
-            uint4 *mv = reinterpret_cast<uint4 *>(mask + head);
-            for (int i = tid; i < nvec; i += OBS_ENV_THREADS) mv[i] = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = head + (nvec << 4) + tid; i < total; i += OBS_ENV_THREADS) mask[i] = 0;
+        for (int w = lane; w < NW; w += 32) need[pi * NW + w] = 0u;
+        if (hops == 0) {   // fewer than k paths for this pair: features stay -1, no valid action (qrmsa.pyx:697)
+            if (STATS)
+                for (int i = lane; i < p.Mc * 12; i += 32) obs[3 + K + pi * p.Mc * 12 + i] = -1.f;
+            continue;
         }
-
-        // ---- phase 0, warp per path: links, availability, free blocks, valid starts of every modulation, usable centres
-        for (int pi = warp; pi < K; pi += nw) {
-            const int path = pbase + pi;
-            const int hops = __ldg(p.path_hops + path) & 0x7f;
-            if (lane == 0) { phops[pi] = hops; obs[3 + pi] = hops ? (float)path_len_norm[path] : 0.f; }
-            for (int w = lane; w < NW; w += 32) need[pi * NW + w] = 0u;
-            if (hops == 0) {   // fewer than k paths for this pair: features stay -1, no valid action (qrmsa.pyx:697)
-                for (int i = lane; i < Mc * 12; i += 32) obs[3 + K + pi * Mc * 12 + i] = -1.f;
-                continue;
-            }
-            const int l = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
-            plink[pi * 32 + lane] = l;
-            if (lane < hops) atomicOr(&lmask[l], 1u << pi);
-            const uint32_t a = path_available(dm, bm, hops, l, lane);
-            if (lane < VW) avs[pi * VW + lane] = a;
-            uint32_t r = a;
-            int aa = 1;
+        const int l = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+        plink[pi * 32 + lane] = l;
+        if (lane < hops) atomicOr(&lmask[l], 1u << pi);
+        const uint32_t a = path_available(dm, bm, hops, l, lane);
+        if (lane < VW) avs[pi * VW + lane] = a;
+        uint32_t r = a;
+        int aa = 1;
+        for (int mi = 0; mi < M; ++mi) {
+            const int L = t.need(rate * M + (M - 1) - mi) + 1;
+            if (L < aa) { r = a; aa = 1; }
+            while (aa < L) { const int b = min(aa, L - aa); r &= shr_multi(r, b); aa += b; }
+            if (lane < VW) validM[(pi * 8 + mi) * VW + lane] = r;
+        }
+        __syncwarp();
+        // need[c2] = some modulation has a valid start s with 2 s + n == c2: for the 32 centres of word w and a
+        // modulation of n slots these are the 16 starts from 16 w - (n >> 1), spread to every other bit
+        for (int w = lane; w < NW; w += 32) {
+            uint32_t bits = 0u;
             for (int mi = 0; mi < M; ++mi) {
-                const int L = t.need(rate * M + (M - 1) - mi) + 1;
-                if (L < aa) { r = a; aa = 1; }
-                while (aa < L) { const int b = min(aa, L - aa); r &= shr_multi(r, b); aa += b; }
-                if (lane < VW) validM[(pi * 8 + mi) * VW + lane] = r;
+                const int n = t.need(rate * M + (M - 1) - mi);
+                int s0 = 16 * w - (n >> 1), sh = 0;
+                if (s0 < 0) { sh = -s0; s0 = 0; }
+                if (sh >= 16) continue;
+                const uint32_t *row = validM + (pi * 8 + mi) * VW;
+                const int q = s0 >> 5;
+                const uint32_t lo = q < VW ? row[q] : 0u, hi = q + 1 < VW ? row[q + 1] : 0u;
+                const uint32_t v16 = ((__funnelshift_r(lo, hi, s0 & 31) & 0xffffu) << sh) & 0xffffu;
+                bits |= spread16(v16) << (n & 1);
             }
-            __syncwarp();
-            // need[c2] = some modulation has a valid start s with 2 s + n == c2: for the 32 centres of word w and a
-            // modulation of n slots these are the 16 starts from 16 w - (n >> 1), spread to every other bit
-            for (int w = lane; w < NW; w += 32) {
-                uint32_t bits = 0u;
-                for (int mi = 0; mi < M; ++mi) {
-                    const int n = t.need(rate * M + (M - 1) - mi);
-                    int s0 = 16 * w - (n >> 1), sh = 0;
-                    if (s0 < 0) { sh = -s0; s0 = 0; }
-                    if (sh >= 16) continue;
-                    const uint32_t *row = validM + (pi * 8 + mi) * VW;
-                    const int q = s0 >> 5;
-                    const uint32_t lo = q < VW ? row[q] : 0u, hi = q + 1 < VW ? row[q + 1] : 0u;
-                    const uint32_t v16 = ((__funnelshift_r(lo, hi, s0 & 31) & 0xffffu) << sh) & 0xffffu;
-                    bits |= spread16(v16) << (n & 1);
-                }
-                if (w == NW - 1 && (D & 31)) bits &= (1u << (D & 31)) - 1u;
-                need[pi * NW + w] = bits;
-            }
+            if (w == NW - 1 && (D & 31)) bits &= (1u << (D & 31)) - 1u;
+            need[pi * NW + w] = bits;
+        }
+        if (STATS) {
             // free blocks of the path availability (qrmsa.pyx:631-646): lane j looks at word j; a block is counted in the
             // word that holds its last slot.  A block that reaches bit 0 of its word continues the free run that ends at the
             // top of the word below (`carry`, handed up through all-free words)
@@ -1834,112 +1814,186 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
                 pstat[pi * 3 + 0] = (double)b_free; pstat[pi * 3 + 1] = mean_block; pstat[pi * 3 + 2] = std_block;
             }
         }
-        env_sync();
-        // ---- phase 1: neighbour sums link by link (core/osnr.pyx:64-94, table form).  Only centres that some path can use
-        // are summed: their union over the paths is compacted (every warp builds the same list -- identical stores, no
-        // barrier) and thread t owns compacted centres t, t + 160, ... for the whole request, so the sums of a link stay in
-        // registers and X[p][c2] has one writer.  nj = ceil(needed / 160) centre groups are live (a template parameter of
-        // the inner loop: no per-term test).  A link's records are decoded once -- centre, G-row address, phi * bandwidth --
-        // 16 per pass, lane per record, into the warp's staging area, and the loop over them is one 16-byte broadcast
-        // LDS per record and, per centre, |d|, two addresses, two LDS.64, DADD, DFMA.
-        {
-            unsigned char *scr = reinterpret_cast<unsigned char *>(tick + 4);
-            uint16_t *clist = reinterpret_cast<uint16_t *>(scr);
-            const uint32_t stage = (smem_u32(scr + 2 * D) + 15u) / 16u * 16u + (uint32_t)(warp * OBS2_STAGE * 16);
-            uint32_t uw = 0u;
-            if (lane < NW)
-                for (int pi = 0; pi < K; ++pi) uw |= need[pi * NW + lane];
-            int incl = __popc(uw);
+    }
+}
+
+// Phase 1 of a request: neighbour sums link by link (core/osnr.pyx:64-94, table form) into X[p][c2].  Returns the number
+// of (record, centre) terms this thread summed.
+__device__ __forceinline__ uint32_t links_neighbour_sums(const KParams &p, const Tab &t, const LinkArea &ar, const uint32_t *bm,
+                                                         const uint32_t *lists, const int tid) {
+    const int K = p.K, D = p.D, CAP = p.CAP, E = p.E, NW = (D + 31) >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
+    double *X = ar.X;
+    const uint32_t *need = ar.need, *lmask = ar.lmask;
+    uint32_t n_terms = 0u;
+    // ---- phase 1: neighbour sums link by link (core/osnr.pyx:64-94, table form).  Only centres that some path can use
+    // are summed: their union over the paths is compacted (every warp builds the same list -- identical stores, no
+    // barrier) and thread t owns compacted centres t, t + 160, ... for the whole request, so the sums of a link stay in
+    // registers and X[p][c2] has one writer.  nj = ceil(needed / 160) centre groups are live (a template parameter of
+    // the inner loop: no per-term test).  A link's records are decoded once -- centre, G-row address, phi * bandwidth --
+    // 16 per pass, lane per record, into the warp's staging area, and the loop over them is one 16-byte broadcast
+    // LDS per record and, per centre, |d|, two addresses, two LDS.64, DADD, DFMA.
+    {
+        unsigned char *scr = ar.scr;
+        uint16_t *clist = reinterpret_cast<uint16_t *>(scr);
+        const uint32_t stage = (smem_u32(scr + 2 * D) + 15u) / 16u * 16u + (uint32_t)(warp * OBS2_STAGE * 16);
+        uint32_t uw = 0u;
+        if (lane < NW)
+            for (int pi = 0; pi < K; ++pi) uw |= need[pi * NW + lane];
+        int incl = __popc(uw);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int P = __shfl_sync(FULL, incl, 31);
+        const int excl = incl - __popc(uw);
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t word = __shfl_sync(FULL, uw, w);
+            const int base = __shfl_sync(FULL, excl, w);
+            if ((word >> lane) & 1u) clist[base + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(w * 32 + lane);
+        }
+        __syncwarp();
+        const int nj = (P + OBS_ENV_THREADS - 1) / OBS_ENV_THREADS;
+        int c2j8[OBS2_NJ];            // 8 * centre (byte offset into a table row)
+        uint32_t myneed[OBS2_NJ];     // bit pi: path pi uses this centre
+#pragma unroll
+        for (int j = 0; j < OBS2_NJ; ++j) {
+            const int idx = tid + j * OBS_ENV_THREADS;
+            int c2 = 0;
+            uint32_t mset = 0u;
+            if (idx < P) {
+                c2 = clist[idx];
+                for (int pi = 0; pi < K; ++pi) mset |= ((need[pi * NW + (c2 >> 5)] >> (c2 & 31)) & 1u) << pi;
             }
-            const int P = __shfl_sync(FULL, incl, 31);
-            const int excl = incl - __popc(uw);
-            for (int w = 0; w < NW; ++w) {
-                const uint32_t word = __shfl_sync(FULL, uw, w);
-                const int base = __shfl_sync(FULL, excl, w);
-                if ((word >> lane) & 1u) clist[base + __popc(word & ((1u << lane) - 1u))] = (uint16_t)(w * 32 + lane);
+            c2j8[j] = 8 * c2;
+            myneed[j] = mset;
+        }
+        const uint32_t d8 = 8u * (uint32_t)D;
+#pragma unroll 1
+        for (int l = 0; l < E && nj > 0; ++l) {
+            const uint32_t pm = lmask[l];
+            if (!pm) continue;      // no path of this request crosses the link
+            bool some = false;
+#pragma unroll
+            for (int j = 0; j < OBS2_NJ; ++j) some |= (myneed[j] & pm) != 0u;
+            if (!__any_sync(FULL, some)) continue;
+            const int cnt = (int)bm[(unsigned)(l * p.RW + p.RW - 1)];
+            const uint32_t *lst = lists + (unsigned)(l * CAP);
+            double s1[OBS2_NJ], s2[OBS2_NJ];
+#pragma unroll
+            for (int j = 0; j < OBS2_NJ; ++j) s1[j] = s2[j] = 0.0;
+#pragma unroll 1
+            for (int q0 = 0; q0 < cnt; q0 += OBS2_STAGE) {
+                __syncwarp();   // the previous pass has been read
+                if (lane < OBS2_STAGE) {   // (entries past the count hold the zero-contribution filler record; CAP is a multiple of 32)
+                    const uint32_t rec = lst[q0 + lane];
+                    const double phin = t.PHIN(rec >> 20);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stage + 16u * (uint32_t)lane),
+                                 "r"(8u * (rec & 0xfffu)), "r"(t.sb + ((rec >> 23) + 1u) * d8),
+                                 "r"((uint32_t)__double2loint(phin)), "r"((uint32_t)__double2hiint(phin)) : "memory");
+                }
+                __syncwarp();
+                const int nq = min(OBS2_STAGE, cnt - q0);
+                n_terms += (uint32_t)(nq * nj);
+                auto sum_pass = [&](auto njc) {
+                    constexpr int NJ = decltype(njc)::value;
+#pragma unroll 2
+                    for (int q = 0; q < nq; ++q) {
+                        uint32_t c2r8, gb, plo, phi;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c2r8), "=r"(gb), "=r"(plo), "=r"(phi)
+                                     : "r"(stage + 16u * (uint32_t)q));
+                        const double phin = __hiloint2double((int)phi, (int)plo);
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            const uint32_t dd = (uint32_t)abs((int)c2r8 - c2j8[j]);
+                            double g, inv;
+                            asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(gb + dd), "n"(lay::INV));
+                            asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(t.sb + dd), "n"(lay::INV));
+                            s1[j] += g;
+                            s2[j] = fma(phin, inv, s2[j]);
+                        }
+                    }
+                };
+                if (nj >= 4) sum_pass(IntC<4>()); else if (nj == 3) sum_pass(IntC<3>());
+                else if (nj == 2) sum_pass(IntC<2>()); else sum_pass(IntC<1>());
             }
-            __syncwarp();
-            const int nj = (P + OBS_ENV_THREADS - 1) / OBS_ENV_THREADS;
-            int c2j8[OBS2_NJ];            // 8 * centre (byte offset into a table row)
-            uint32_t myneed[OBS2_NJ];     // bit pi: path pi uses this centre
+            const double w1 = t.W1(l), w2 = t.W2(l);   // W2 is stored negated
 #pragma unroll
             for (int j = 0; j < OBS2_NJ; ++j) {
-                const int idx = tid + j * OBS_ENV_THREADS;
-                int c2 = 0;
-                uint32_t mset = 0u;
-                if (idx < P) {
-                    c2 = clist[idx];
-                    for (int pi = 0; pi < K; ++pi) mset |= ((need[pi * NW + (c2 >> 5)] >> (c2 & 31)) & 1u) << pi;
-                }
-                c2j8[j] = 8 * c2;
-                myneed[j] = mset;
-            }
-            const uint32_t d8 = 8u * (uint32_t)D;
-#pragma unroll 1
-            for (int l = 0; l < E && nj > 0; ++l) {
-                const uint32_t pm = lmask[l];
-                if (!pm) continue;      // no path of this request crosses the link
-                bool some = false;
-#pragma unroll
-                for (int j = 0; j < OBS2_NJ; ++j) some |= (myneed[j] & pm) != 0u;
-                if (!__any_sync(FULL, some)) continue;
-                const int cnt = (int)bm[(unsigned)(l * p.RW + p.RW - 1)];
-                const uint32_t *lst = lists + (unsigned)(l * CAP);
-                double s1[OBS2_NJ], s2[OBS2_NJ];
-#pragma unroll
-                for (int j = 0; j < OBS2_NJ; ++j) s1[j] = s2[j] = 0.0;
-#pragma unroll 1
-                for (int q0 = 0; q0 < cnt; q0 += OBS2_STAGE) {
-                    __syncwarp();   // the previous pass has been read
-                    if (lane < OBS2_STAGE) {   // (entries past the count hold the zero-contribution filler record; CAP is a multiple of 32)
-                        const uint32_t rec = lst[q0 + lane];
-                        const double phin = t.PHIN(rec >> 20);
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stage + 16u * (uint32_t)lane),
-                                     "r"(8u * (rec & 0xfffu)), "r"(t.sb + ((rec >> 23) + 1u) * d8),
-                                     "r"((uint32_t)__double2loint(phin)), "r"((uint32_t)__double2hiint(phin)) : "memory");
-                    }
-                    __syncwarp();
-                    const int nq = min(OBS2_STAGE, cnt - q0);
-                    auto sum_pass = [&](auto njc) {
-                        constexpr int NJ = decltype(njc)::value;
-#pragma unroll 2
-                        for (int q = 0; q < nq; ++q) {
-                            uint32_t c2r8, gb, plo, phi;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c2r8), "=r"(gb), "=r"(plo), "=r"(phi)
-                                         : "r"(stage + 16u * (uint32_t)q));
-                            const double phin = __hiloint2double((int)phi, (int)plo);
-#pragma unroll
-                            for (int j = 0; j < NJ; ++j) {
-                                const uint32_t dd = (uint32_t)abs((int)c2r8 - c2j8[j]);
-                                double g, inv;
-                                asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(gb + dd), "n"(lay::INV));
-                                asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(t.sb + dd), "n"(lay::INV));
-                                s1[j] += g;
-                                s2[j] = fma(phin, inv, s2[j]);
-                            }
-                        }
-                    };
-                    if (nj >= 4) sum_pass(IntC<4>()); else if (nj == 3) sum_pass(IntC<3>());
-                    else if (nj == 2) sum_pass(IntC<2>()); else sum_pass(IntC<1>());
-                }
-                const double w1 = t.W1(l), w2 = t.W2(l);   // W2 is stored negated
-#pragma unroll
-                for (int j = 0; j < OBS2_NJ; ++j) {
-                    uint32_t ps = myneed[j] & pm;
-                    if (!ps) continue;
-                    const double y = fma(w2, s2[j], w1 * s1[j]);
-                    while (ps) {
-                        const int pi = __ffs(ps) - 1;
-                        ps &= ps - 1u;
-                        X[pi * D + (c2j8[j] >> 3)] += y;                         // this thread owns the centre: no race
-                    }
+                uint32_t ps = myneed[j] & pm;
+                if (!ps) continue;
+                const double y = fma(w2, s2[j], w1 * s1[j]);
+                while (ps) {
+                    const int pi = __ffs(ps) - 1;
+                    ps &= ps - 1u;
+                    X[pi * D + (c2j8[j] >> 3)] += y;                         // this thread owns the centre: no race
                 }
             }
         }
+    }
+    return n_terms;
+}
+
+__global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
+    k_observation_links(const KParams p, const double *__restrict__ path_len_norm, const double inv_max_rate,
+                        float *__restrict__ obs_out, uint8_t *__restrict__ mask_out, const int obs_dim, const int n_actions,
+                        const int epc, const int env_smem) {
+    __shared__ uint64_t mbar;
+    stage_tables(p, &mbar);
+    Tab t;
+    t.init();
+    const Dim<0, 0, 0> dm(p);
+    const int S = p.S, W = p.W, M = p.M, Mc = p.Mc, K = p.K, D = p.D, CAP = p.CAP, E = p.E;
+    const int VW = W + 1, NW = (D + 31) >> 5;
+    const int slot = threadIdx.x / OBS_ENV_THREADS;
+    auto env_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(OBS_ENV_THREADS) : "memory"); };
+    unsigned char *base = qsmem + p.blob_bytes + (size_t)slot * env_smem;
+    LinkArea ar;
+    ar.carve(base, K, D, VW, NW, E);
+    double *X = ar.X, *pstat = ar.pstat;
+    uint32_t *validM = ar.validM, *lmask = ar.lmask;
+    int *phops = ar.phops, *tick = ar.tick, *smax = ar.smax;
+    const int tid = threadIdx.x - slot * OBS_ENV_THREADS, lane = tid & 31, warp = tid >> 5;
+    uint16_t *slist = reinterpret_cast<uint16_t *>(ar.scr) + warp * S;   // [nw][S]  valid starts of the open unit, compacted
+    const double inv_S = 1.0 / (double)S, inv_S1 = 1.0 / (double)(S - 1);
+
+    for (int i = tid; i < E; i += OBS_ENV_THREADS) lmask[i] = 0u;
+    env_sync();
+    for (int env = blockIdx.x * epc + slot; env < p.n_envs; env += gridDim.x * epc) {
+        const int4 st = p.estate[env];
+        float *obs = obs_out + (size_t)env * obs_dim;
+        uint8_t *mask = mask_out + (size_t)env * n_actions;
+        const int cur = st.x < p.n_req ? st.x : p.n_req - 1;
+        const uint4 rq = p.trace[(size_t)env * p.T + cur];
+        const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+        const uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
+        const uint32_t *lists = p.lists + (size_t)env * E * CAP;
+        const int pbase = (src * p.N + dst) * K;
+        if (tid == 0) {
+            obs[0] = (float)((double)t.rate(rate) * inv_max_rate);                       // qrmsa.pyx:654-665
+            obs[1] = (float)(p.N > 1 ? (double)src / (double)(p.N - 1) : 0.0);
+            obs[2] = (float)(p.N > 1 ? (double)dst / (double)(p.N - 1) : 0.0);
+            mask[n_actions - 1] = 1;                                                        // qrmsa.pyx:766
+            *tick = 0;
+        }
+        for (int i = tid; i < K * D; i += OBS_ENV_THREADS) X[i] = 0.0;   // (its readers passed the barrier that ends the loop)
+        {   // every mask entry is rewritten: zeros here, 16 bytes per store (n_actions is odd, so the env's row starts at any
+            // byte: the unaligned head and tail go byte by byte); the valid candidates are set to 1 in phase 2, two barriers on
+            const int total = K * Mc * S;
+            const int head = min((int)((16u - ((uint32_t)(uintptr_t)mask & 15u)) & 15u), total);
+            const int nvec = (total - head) >> 4;
+            if (tid < head) mask[tid] = 0;
+            uint4 *mv = reinterpret_cast<uint4 *>(mask + head);
+            for (int i = tid; i < nvec; i += OBS_ENV_THREADS) mv[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = head + (nvec << 4) + tid; i < total; i += OBS_ENV_THREADS) mask[i] = 0;
+        }
+
+        // ---- phase 0, warp per path: links, availability, free blocks, valid starts of every modulation, usable centres
+        links_open_paths<true>(p, t, ar, bm, pbase, rate, warp, lane, obs, path_len_norm);
+        env_sync();
+        // ---- phase 1: neighbour sums of every usable centre, link by link
+        links_neighbour_sums(p, t, ar, bm, lists, tid);
         env_sync();   // X complete
         for (int i = tid; i < E; i += OBS_ENV_THREADS) lmask[i] = 0u;   // (read above, set again after the closing barrier)
         // ---- modulations_to_consider < n_mods: get_max_modulation_index (qrmsa.pyx:543-581) -- paths in order, modulations
@@ -2299,6 +2353,242 @@ __global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
         }
         if (tid == 0) p.estate[env] = make_int4(cur, rel_ptr, st.z, err);
         env_bar(bar);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// heuristic_highest_snr + env.step, link-major (spectra up to 320 slots, at most 8 paths per pair): the first two phases
+// are the observation kernel's -- warp per path (availability, valid starts of every modulation, usable centres), then the
+// neighbour sums once per DISTINCT link of the request into X[p][c2] -- and the candidate scan runs as ticketed units
+// (path, run of modulations with the same slot count) on compacted valid starts: one GN base + one lookup per start, one
+// threshold test per modulation of the run.  Per request: four env-wide barriers (the round-1 kernel: five per path plus a
+// dozen for its four block reductions) and the neighbour sums of shared links are made once instead of once per path.
+// Winner = smallest 1/GSNR, the smallest action index among equals; runner-up and near-threshold rules as in
+// k_step_highest_snr (heuristics.py:272-328).
+// --------------------------------------------------------------------------------------------------------
+struct HsnrPick {   // per-lane, per-warp and per-env summary of the candidates seen
+    unsigned long long best, second, near;
+    int idx, any;   // any: bit 0 some modulation had no valid start, bit 1 some check failed
+};
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(FULL, v, o);
+        v = y < v ? y : v;
+    }
+    return v;
+}
+// min over the lanes: the winner (smallest acc, then smallest action index) and the best of everything else
+__device__ __forceinline__ HsnrPick warp_pick(const HsnrPick a) {
+    HsnrPick r;
+    r.best = warp_min_u64(a.best);
+    r.idx = (int)__reduce_min_sync(FULL, a.best == r.best ? (unsigned)a.idx : 0xffffffffu);
+    r.second = warp_min_u64((a.best == r.best && a.idx == r.idx) ? a.second : a.best);
+    r.near = warp_min_u64(a.near);
+    r.any = (int)__reduce_or_sync(FULL, (unsigned)a.any);
+    return r;
+}
+
+__global__ void __launch_bounds__(OBS_ENV_THREADS * OBS_MAX_EPC, 1)
+    k_step_highest_snr_links(const KParams p, const int n_steps, const int epc, const int env_smem) {
+    constexpr int nw = OBS_ENV_THREADS >> 5;
+    __shared__ uint64_t mbar;
+    __shared__ unsigned long long s_red_[OBS_MAX_EPC][nw][3];
+    __shared__ int s_redi_[OBS_MAX_EPC][nw][4];
+    __shared__ int s_cur_[OBS_MAX_EPC], s_err_[OBS_MAX_EPC];
+    stage_tables(p, &mbar);
+    Tab t;
+    t.init();
+    const Dim<0, 0, 0> dm(p);
+    const int S = p.S, W = p.W, M = p.M, K = p.K, D = p.D, CAP = p.CAP, E = p.E;
+    const int VW = W + 1, NW = (D + 31) >> 5;
+    const int slot = threadIdx.x / OBS_ENV_THREADS;
+    auto env_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(OBS_ENV_THREADS) : "memory"); };
+    LinkArea ar;
+    ar.carve(qsmem + p.blob_bytes + (size_t)slot * env_smem, K, D, VW, NW, E);
+    const int tid = threadIdx.x - slot * OBS_ENV_THREADS, lane = tid & 31, warp = tid >> 5;
+    uint16_t *slist = reinterpret_cast<uint16_t *>(ar.scr) + warp * S;
+    unsigned long long (*s_red)[3] = s_red_[slot];
+    int (*s_redi)[4] = s_redi_[slot];
+    int &s_cur = s_cur_[slot], &s_err = s_err_[slot];
+    const int reject = K * M * S;
+    const double TIE = 1.0000002302585359;   // 10^(1e-6 / 10): 1e-6 dB on the linear value
+
+    for (int i = tid; i < E; i += OBS_ENV_THREADS) ar.lmask[i] = 0u;
+    env_sync();
+    for (int env = blockIdx.x * epc + slot; env < p.n_envs; env += gridDim.x * epc) {
+        const int4 st = p.estate[env];
+        if (st.w != ENV_OK) continue;   // (uniform over the env's threads)
+        int cur = st.x, rel_ptr = st.y, err = 0;
+        uint4 *tr = p.trace + (size_t)env * p.T;
+        const unsigned long long *perm = p.perm + (size_t)env * p.T;
+        uint32_t *bm = p.bm + (size_t)env * p.bm_stride;
+        uint32_t *lists = p.lists + (size_t)env * E * CAP;
+        uint8_t *pos = p.pos + (size_t)env * p.pos_stride;
+        Head head;
+        head.id = -1; head.rel = 0.f;
+        if (warp == 0) head = load_head(p, tr, perm, rel_ptr);
+        unsigned long long tot_checks = 0ull, tot_terms = 0ull;   // (warp 0)
+        uint32_t tot_rel = 0u, tot_steps = 0u;
+
+#pragma unroll 1
+        for (int step = 0; step < n_steps && cur + 1 < p.n_req && !err; ++step) {
+            const uint4 rq = tr[cur];
+            const int src = rq.z & 0xff, dst = (rq.z >> 8) & 0xff, rate = (rq.z >> 16) & 0xff;
+            const int pbase = (src * p.N + dst) * K;
+            if (tid == 0) *ar.tick = 0;
+            for (int i = tid; i < K * D; i += OBS_ENV_THREADS) ar.X[i] = 0.0;
+            links_open_paths<false>(p, t, ar, bm, pbase, rate, warp, lane, nullptr, nullptr);
+            env_sync();
+            uint32_t n_terms = links_neighbour_sums(p, t, ar, bm, lists, tid);
+            env_sync();   // X complete
+            for (int i = tid; i < E; i += OBS_ENV_THREADS) ar.lmask[i] = 0u;   // (set again after the barrier that closes the step)
+            // ---- candidates: lane j < M holds the slot count of modulation M-1-j, a ballot marks the heads of the runs
+            const int my_n = lane < M ? t.need(rate * M + (M - 1) - lane) : -1;
+            const int prev_n = __shfl_up_sync(FULL, my_n, 1);
+            const uint32_t heads = __ballot_sync(FULL, lane < M && (lane == 0 || prev_n != my_n));
+            const int R = __popc(heads);
+            const uint32_t rcpR = (65536u + (uint32_t)R - 1u) / (uint32_t)R;
+            HsnrPick pk;
+            pk.best = pk.second = pk.near = ~0ull;
+            pk.idx = 0x7fffffff; pk.any = 0;
+            int best_phys = -1;   // (path, start, slots): the same channel under another modulation
+            uint32_t n_checks = 0u;
+            for (;;) {
+                int u = 0;
+                if (lane == 0) u = atomicAdd(ar.tick, 1);
+                u = __shfl_sync(FULL, u, 0);
+                if (u >= K * R) break;
+                const int pi = (int)(((uint32_t)u * rcpR) >> 16);
+                if (ar.phops[pi] == 0) continue;
+                uint32_t h = heads;
+                for (int i = u - pi * R; i > 0; --i) h &= h - 1u;
+                const int mi0 = __ffs(h) - 1;
+                h &= h - 1u;
+                const int mi1 = h ? __ffs(h) - 1 : M;
+                const int n = __shfl_sync(FULL, my_n, mi0);
+                const int ncls = t.cls(rate * M + (M - 1) - mi0);
+                const double2 pg = __ldg(p.path_gn + pbase + pi);
+                const uint32_t *vrow = ar.validM + (pi * 8 + mi0) * VW;
+                const double *Xp = ar.X + pi * D + n;
+                int cnt = 0;
+                for (int it = 0; it * 32 < S; ++it) {
+                    const uint32_t w = vrow[it];
+                    if ((w >> lane) & 1u) slist[cnt + __popc(w & ((1u << lane) - 1u))] = (uint16_t)(lane + it * 32);
+                    cnt += __popc(w);
+                }
+                __syncwarp();
+                if (cnt == 0) pk.any |= 1;   // no valid start: blocked_resources (heuristics.py:295-297)
+#pragma unroll 1
+                for (int c0 = 0; c0 < cnt; c0 += 32) {
+                    const int idx = c0 + lane;
+                    if (idx < cnt) {
+                        const int s = slist[idx];
+                        const double acc = gn_base(p, t, pg, s, n, ncls).with(Xp[2 * s]);
+                        const unsigned long long k = (unsigned long long)__double_as_longlong(acc);   // acc > 0: its bits order it
+                        const int phys = (pi << 20) | (s << 8) | n;
+                        for (int mi = mi0; mi < mi1; ++mi) {
+                            const int m = (M - 1) - mi;
+                            n_checks += 1u;
+                            if (acc > t.ACCLO(m) && acc < t.ACCHI(m) && k < pk.near) pk.near = k;
+                            if (acc <= t.ACCT(m)) {                       // gsnr >= threshold (heuristics.py:312-313)
+                                const int a = (pi * M + mi) * S + s;       // = the action index
+                                if (k == pk.best && phys == best_phys) {
+                                    // the identical channel under a lower modulation: same GSNR by construction, the first
+                                    // one keeps the tie (heuristics.py:314) and it is no runner-up
+                                    if (a < pk.idx) pk.idx = a;
+                                } else if (k < pk.best || (k == pk.best && a < pk.idx)) {
+                                    pk.second = pk.best; pk.best = k; pk.idx = a; best_phys = phys;
+                                } else if (k < pk.second) {
+                                    pk.second = k;
+                                }
+                            } else {
+                                pk.any |= 2;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();   // slist is rewritten by the next unit
+            }
+            // ---- winner: per warp by shuffles, then warp 0 over the env's warps
+            {
+                const HsnrPick wp = warp_pick(pk);
+                n_checks = __reduce_add_sync(FULL, n_checks);
+                n_terms = __reduce_add_sync(FULL, n_terms);
+                if (lane == 0) {
+                    s_red[warp][0] = wp.best; s_red[warp][1] = wp.second; s_red[warp][2] = wp.near;
+                    s_redi[warp][0] = wp.idx; s_redi[warp][1] = wp.any; s_redi[warp][2] = (int)n_checks; s_redi[warp][3] = (int)n_terms;
+                }
+            }
+            env_sync();
+            if (warp == 0) {
+                HsnrPick e;
+                e.best = e.second = e.near = ~0ull;
+                e.idx = 0x7fffffff; e.any = 0;
+                uint32_t c_checks = 0u, c_terms = 0u;
+                if (lane < nw) {
+                    e.best = s_red[lane][0]; e.second = s_red[lane][1]; e.near = s_red[lane][2];
+                    e.idx = s_redi[lane][0]; e.any = s_redi[lane][1];
+                    c_checks = (uint32_t)s_redi[lane][2]; c_terms = (uint32_t)s_redi[lane][3];
+                }
+                const HsnrPick g = warp_pick(e);
+                tot_checks += __reduce_add_sync(FULL, c_checks);
+                tot_terms += __reduce_add_sync(FULL, c_terms);
+                const bool found = g.best != ~0ull;
+                uint32_t flags = QRMSA_FLAG_DECIDED;
+                // a check within 1e-3 dB of its threshold matters when flipping it could change the outcome: no acceptable
+                // candidate at all, or its GSNR is at least the winner's
+                if (g.near != ~0ull && (!found || __longlong_as_double((long long)g.near) <= __longlong_as_double((long long)g.best) * TIE))
+                    flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+                int action = reject;
+                if (found) {
+                    flags |= QRMSA_FLAG_ACCEPTED;
+                    action = g.idx;
+                    if (g.second != ~0ull && __longlong_as_double((long long)g.second) <= __longlong_as_double((long long)g.best) * TIE)
+                        flags |= QRMSA_FLAG_NEAR_TIE;
+                    const int s = g.idx % S, mi = (g.idx / S) % M, pi = g.idx / (S * M), m = (M - 1) - mi;
+                    const int path = pbase + pi;
+                    const int hops = __ldg(p.path_hops + path) & 0x7f;
+                    const int mylink = lane < hops ? __ldg(p.path_links + path * p.Hmax + lane) : 0;
+                    const int mycnt = lane < hops ? (int)*cnt_word(bm, mylink, p.RW) : 0;
+                    const int n = t.need(rate * M + m), ncls = t.cls(rate * M + m);
+                    const uint32_t rec_w = (uint32_t)(2 * s + n) | ((uint32_t)n << 12) | ((uint32_t)m << 20) | ((uint32_t)ncls << 23);
+                    if (commit(dm, p, bm, lists, pos, hops, mylink, mycnt, s, n, rec_w, lane)) err = ENV_ERR_LIST_OVERFLOW;
+                    if (lane == 0 && p.gsnr_log) {
+                        const double acc = __longlong_as_double((long long)g.best), ase = gn_base(p, t, path, s, n, ncls).ase;
+                        double *gl = p.gsnr_log + ((size_t)env * p.T + cur) * 3;
+                        gl[0] = -10.0 * log10(acc); gl[1] = -10.0 * log10(ase); gl[2] = -10.0 * log10(acc - ase);
+                    }
+                } else {
+                    if ((g.any & 1) && !(g.any & 2)) flags |= QRMSA_FLAG_BLOCKED_RESOURCES;   // heuristics.py:324-326
+                    if (g.any & 2) flags |= QRMSA_FLAG_BLOCKED_OSNR;
+                    if (lane == 0 && p.gsnr_log) {
+                        double *gl = p.gsnr_log + ((size_t)env * p.T + cur) * 3;
+                        gl[0] = gl[1] = gl[2] = 0.0;
+                    }
+                }
+                if (lane == 0) tr[cur].w = (uint32_t)action | flags;
+                __syncwarp();
+                uint32_t n_rel = 0;
+                if (advance_and_release(dm, p, t, tr, perm, bm, lists, pos, cur, rel_ptr, head, lane, n_rel))
+                    err = ENV_ERR_RELEASE_NOT_FOUND;
+                tot_rel += n_rel;
+                tot_steps += 1u;
+                if (lane == 0) { s_cur = cur; s_err = err; }
+            }
+            env_sync();   // the step's commit and releases are visible to every warp of the env
+            cur = s_cur;
+            err = s_err;
+        }
+        if (tid == 0) {
+            p.estate[env] = make_int4(cur, rel_ptr, st.z, err);
+            unsigned long long *cglob = p.counters + (size_t)(env / p.group_size) * QRMSA_N_COUNTERS;
+            atomicAdd(cglob + QRMSA_CNT_GN_EVALS, tot_checks);
+            atomicAdd(cglob + QRMSA_CNT_GN_TERMS, tot_terms);
+            atomicAdd(cglob + QRMSA_CNT_PATHS_TRIED, (unsigned long long)tot_steps * (unsigned long long)K);
+            if (tot_rel) atomicAdd(cglob + QRMSA_CNT_RELEASES, (unsigned long long)tot_rel);
+        }
+        env_sync();
     }
 }
 
