@@ -1053,57 +1053,69 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_step_policy(const KParams p,
                 bool counted = false;
                 // Modulations that need the same number of slots share the candidate (same first-fit start, same
                 // centre frequency, same bandwidth), hence the same GSNR: the search and the GN sum are done once per
-                // slot count and the following modulations only compare against their own threshold.
-                int n_seen = -1, s = 0;
-                bool have_x = false;
-                double x = 0.0;
-                GnBase gb;
-                gb.ase = gb.cn = gb.selfpb = 0.0;
+                // RUN of such modulations, and the run's threshold tests are made side by side -- lane m compares against
+                // the thresholds of modulation m, ballots say which modulations are hopeless in an empty network, which
+                // pass, and which sit within 1e-3 dB.  The reference's loop order (best modulation first, stop at the
+                // first that passes: heuristics.py:938-958) is read off the masks.
+                uint32_t todo = (1u << M) - 1u;   // modulations not looked at yet (bit m)
+                const int my_need = mynd & 0xff;
 #pragma unroll 1
-                for (int m = M - 1; m >= 0; --m) {
-                    const int nd = __shfl_sync(FULL, mynd, m);
+                while (todo) {
+                    const int m_hi = 31 - __clz((int)todo);
+                    const int nd = __shfl_sync(FULL, mynd, m_hi);
                     const int n = nd & 0xff, ncls = nd >> 8;
-                    if (n != n_seen) {
-                        n_seen = -1;
-                        const int L = n + 1;
-                        if (L < a) { r = av; a = 1; }
-                        while (a < L) {
-                            const int b = min(a, L - a);
-                            r &= shr_multi(r, b);
-                            a += b;
-                        }
-                        const unsigned any = __ballot_sync(FULL, r != 0u);
-                        if (!any) {
-                            // no block of n+1 slots: the reference sets blocked_due_to_resources and tries the next
-                            // modulation (heuristics.py:938-940); when the remaining ones all need >= n slots none of
-                            // them can fit either, so the loop ends here with the same flags
-                            blk_res = 1;
-                            if (p.need_monotone) break;
-                            continue;
-                        }
-                        const int fl = __ffs(any) - 1;
-                        const uint32_t w = __shfl_sync(FULL, r, fl);
-                        s = (fl << 5) + __ffs(w) - 1;
-                        gb = gn_base(p, t, path, s, n, ncls);
-                        have_x = false;
-                        n_seen = n;
+                    // the run: m_hi and the modulations right below it that need n slots too
+                    const uint32_t same = __ballot_sync(FULL, lane < M && my_need == n);
+                    const uint32_t gap = ~same & ((1u << m_hi) - 1u);
+                    const uint32_t run = gap ? (same & todo & ~((2u << (31 - __clz((int)gap))) - 1u)) : (same & todo);
+                    todo &= ~run;
+                    const int L = n + 1;
+                    if (L < a) { r = av; a = 1; }
+                    while (a < L) {
+                        const int b = min(a, L - a);
+                        r &= shr_multi(r, b);
+                        a += b;
                     }
-                    if (prunable && gb.empty() >= t.ACCHI(m)) {  // hopeless even in an empty network
-                        QCNT(QRMSA_CNT_GN_PRUNED, 1);
+                    const unsigned any = __ballot_sync(FULL, r != 0u);
+                    if (!any) {
+                        // no block of n+1 slots: the reference sets blocked_due_to_resources and tries the next
+                        // modulation (heuristics.py:938-940); when the remaining ones all need >= n slots none of
+                        // them can fit either, so the loop ends here with the same flags
+                        blk_res = 1;
+                        if (p.need_monotone) break;
+                        continue;
+                    }
+                    const int fl = __ffs(any) - 1;
+                    const uint32_t w = __shfl_sync(FULL, r, fl);
+                    const int s = (fl << 5) + __ffs(w) - 1;
+                    const GnBase gb = gn_base(p, t, path, s, n, ncls);
+                    const bool mine = (run >> lane) & 1u;
+                    // hopeless even in an empty network (only on paths where every neighbour term is >= 0)
+                    const uint32_t dead = prunable ? __ballot_sync(FULL, mine && gb.empty() >= t.ACCHI(lane & 7)) : 0u;
+                    const uint32_t live = run & ~dead;
+                    if (!live) {
+                        QCNT(QRMSA_CNT_GN_PRUNED, __popc(dead));
                         blk_osnr = 1;
                         if (POLICY == POLICY_FIRST_FIT) blk_res = 0;
                         continue;
                     }
-                    if (!have_x) {
-                        uint32_t terms = 0;
-                        x = gn_neighbours(dm, t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms);
-                        have_x = true;
-                        QCNT(QRMSA_CNT_GN_TERMS, terms);
-                        if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
-                    }
+                    uint32_t terms = 0;
+                    const double x = gn_neighbours(dm, t, lists, hops, mylink, mycnt, 2 * s + n, lane, terms);
+                    QCNT(QRMSA_CNT_GN_TERMS, terms);
+                    if (!counted) { QCNT(QRMSA_CNT_RECORDS_READ, terms); counted = true; }
                     const double acc = gb.with(x);
-                    QCNT(QRMSA_CNT_GN_EVALS, 1);
-                    if (qot_ok(t, m, acc, flags)) {
+                    // accept iff gsnr >= threshold (heuristics.py:957-958), decided on the linear value acc = 1/GSNR against
+                    // ACCT[m] = 10^(-thr/10); |gsnr - thr| < 1e-3 dB <=> ACCLO[m] < acc < ACCHI[m]
+                    const bool alive = (live >> lane) & 1u;
+                    const uint32_t okm = __ballot_sync(FULL, alive && acc <= t.ACCT(lane & 7));
+                    const uint32_t nearm = __ballot_sync(FULL, alive && acc > t.ACCLO(lane & 7) && acc < t.ACCHI(lane & 7));
+                    // checked: every live modulation down to the first that passes; pruned: the dead ones above it
+                    const uint32_t upto = okm ? ~((1u << (31 - __clz((int)okm))) - 1u) : 0xffffffffu;
+                    QCNT(QRMSA_CNT_GN_EVALS, __popc(live & upto));
+                    QCNT(QRMSA_CNT_GN_PRUNED, __popc(dead & upto));
+                    if (nearm & live & upto) flags |= QRMSA_FLAG_NEAR_THRESHOLD;
+                    if (okm) {
+                        const int m = 31 - __clz((int)okm);
                         found = true;
                         acc_ok = acc;
                         ase_ok = gb.ase;

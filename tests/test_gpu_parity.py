@@ -224,23 +224,24 @@ def test_highest_snr_policy_vs_reference(tag):
     eng.close()
 
 
-def test_highest_snr_policy_batched_vs_oracle():
-    """Several envs per launch (one CTA per env, two per SM) against the oracle on CPython-exact traces."""
+@pytest.mark.parametrize("topo,n_slots,load,n_envs,n", [("nobel-eu", 320, 450.0, 7, 60), ("germany50", 640, 800.0, 5, 40)])
+def test_highest_snr_policy_batched_vs_oracle(topo, n_slots, load, n_envs, n):
+    """Several envs per launch against the oracle on CPython-exact traces: the link-major kernel (spectra up to 320
+    slots, k_step_highest_snr_links) and the general one (640 slots, k_step_highest_snr)."""
     from optical_networking_gym_b200 import _lib
     from optical_networking_gym_b200.engine import Engine, unpack_bitmaps
     from optical_networking_gym_b200.tracegen import TraceGenerator
     from oracle import oracle as orc
 
-    tb = load_tables("nobel-eu", 320)
-    n_envs, n = 7, 60
-    tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, 450.0, base_seed=77).next(n + 1)
+    tb = load_tables(topo, n_slots)
+    tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, load, base_seed=77).next(n + 1)
     eng = Engine(tb, n_envs, n + 1)
     eng.reset(); eng.load_trace_host(*tr)
     eng.step_heuristic("highest_snr", n)
     words = eng.actions_host(0, n)
     actions = (words & _lib.ACTION_MASK).astype(np.int64).T
     flagged = ((words.view(np.uint32) & (_lib.FLAG_NEAR_THRESHOLD | _lib.FLAG_NEAR_TIE)) != 0).T
-    slots = unpack_bitmaps(eng.export_bitmaps(0, n_envs), 320)
+    slots = unpack_bitmaps(eng.export_bitmaps(0, n_envs), n_slots)
     ref = []
     for e in range(n_envs):
         o = orc.OracleEnv(tb, n + 1)
