@@ -4,7 +4,8 @@
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep TAG [--env-steps N] [--launches launches.csv]
 
 Writes: <tag>_metrics.csv (key raw metrics), <tag>_hot_lines.md (instruction counts per source line / region and
-SASS opcode mix of the top kernel), and updates profiles/traffic.json (dram bytes per launch, read by bench.py).
+SASS opcode mix of the top kernel), and updates profiles/traffic.json (dram bytes per launch, read by bench.py) when the
+capture is of the headline step kernel, <tag>_traffic.json otherwise.
 """
 import collections
 import csv
@@ -159,7 +160,9 @@ def main():
     per = env_steps or 1.0
     traffic.update(warp_instructions_per_launch_sass_page=tot, avg_threads_per_instruction=thr / max(tot, 1),
                    avg_predicated_on_threads_per_instruction=pon / max(tot, 1))
-    json.dump(traffic, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
+    # bench.py reads profiles/traffic.json for the HEADLINE step kernel only: captures of other kernels keep their own file
+    is_headline = "k_step_policy<320" in traffic["kernel"] or "k_step_policy<(int)320" in traffic["kernel"]
+    json.dump(traffic, open(os.path.join(out_dir, "traffic.json" if is_headline else f"{tag}_traffic.json"), "w"), indent=1)
     with open(os.path.join(out_dir, f"{tag}_hot_lines.md"), "w") as f:
         f.write(f"# {tag}: {m.get('Kernel Name', ('', ''))[0]}\n\n")
         f.write(f"warp-instructions per launch {tot:.4g}" + (f" = {tot / per:.1f} per env-step" if env_steps else "") +
