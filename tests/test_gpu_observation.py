@@ -69,15 +69,18 @@ def test_observation_vs_reference_recording(tag, topo):
     eng.close()
 
 
-def test_batched_observation_vs_oracle():
-    """Several envs at different fill levels, germany50/640 (two c2 passes per thread, non-prunable paths)."""
+@pytest.mark.parametrize("topo,n_slots,load", [("germany50", 640, 800.0), ("var_k3_nsfnet", 160, 150.0)])
+def test_batched_observation_vs_oracle(topo, n_slots, load):
+    """Several envs at different fill levels: germany50/640 (the general kernel: two c2 passes per thread, non-prunable
+    paths) and NSFNET with 160 slots and k = 3 (the link-major kernel away from its 320-slot / k = 5 shape: two live
+    centre groups at most, scratch sized by the staging area rather than by the start lists)."""
     import torch
     from optical_networking_gym_b200.engine import Engine
     from optical_networking_gym_b200.tracegen import TraceGenerator
 
-    tb = load_tables("germany50", 640)
+    tb = load_tables(topo, n_slots)
     n_envs, n_req = 5, 400
-    tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, 800.0, base_seed=321).next(n_req)
+    tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, load, base_seed=321).next(n_req)
     eng = Engine(tb, n_envs, n_req)
     eng.reset(); eng.load_trace_host(*tr)
     obs_dim, n_act = eng.observation_dims()

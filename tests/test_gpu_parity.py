@@ -224,7 +224,8 @@ def test_highest_snr_policy_vs_reference(tag):
     eng.close()
 
 
-@pytest.mark.parametrize("topo,n_slots,load,n_envs,n", [("nobel-eu", 320, 450.0, 7, 60), ("germany50", 640, 800.0, 5, 40)])
+@pytest.mark.parametrize("topo,n_slots,load,n_envs,n", [("nobel-eu", 320, 450.0, 7, 60), ("germany50", 640, 800.0, 5, 40),
+                                                       ("var_k3_nsfnet", 160, 150.0, 6, 120)])
 def test_highest_snr_policy_batched_vs_oracle(topo, n_slots, load, n_envs, n):
     """Several envs per launch against the oracle on CPython-exact traces: the link-major kernel (spectra up to 320
     slots, k_step_highest_snr_links) and the general one (640 slots, k_step_highest_snr)."""
