@@ -1886,10 +1886,14 @@ __device__ __forceinline__ uint32_t links_neighbour_sums(const KParams &p, const
         for (int l = 0; l < E && nj > 0; ++l) {
             const uint32_t pm = lmask[l];
             if (!pm) continue;      // no path of this request crosses the link
-            bool some = false;
+            // groups of centres with a taker in this warp for this link: all of them -> the nj-wide loop, some -> one
+            // single-group loop per taker (the staged records are read once per group then), none -> next link
+            uint32_t wmask = 0u;
 #pragma unroll
-            for (int j = 0; j < OBS2_NJ; ++j) some |= (myneed[j] & pm) != 0u;
-            if (!__any_sync(FULL, some)) continue;
+            for (int j = 0; j < OBS2_NJ; ++j)
+                if (__any_sync(FULL, (myneed[j] & pm) != 0u)) wmask |= 1u << j;
+            if (!wmask) continue;
+            const bool all_groups = wmask == (1u << nj) - 1u;
             const int cnt = (int)bm[(unsigned)(l * p.RW + p.RW - 1)];
             const uint32_t *lst = lists + (unsigned)(l * CAP);
             double s1[OBS2_NJ], s2[OBS2_NJ];
@@ -1907,7 +1911,7 @@ __device__ __forceinline__ uint32_t links_neighbour_sums(const KParams &p, const
                 }
                 __syncwarp();
                 const int nq = min(OBS2_STAGE, cnt - q0);
-                n_terms += (uint32_t)(nq * nj);
+                n_terms += (uint32_t)(nq * __popc(wmask));
                 auto sum_pass = [&](auto njc) {
                     constexpr int NJ = decltype(njc)::value;
 #pragma unroll 2
@@ -1927,8 +1931,31 @@ __device__ __forceinline__ uint32_t links_neighbour_sums(const KParams &p, const
                         }
                     }
                 };
-                if (nj >= 4) sum_pass(IntC<4>()); else if (nj == 3) sum_pass(IntC<3>());
-                else if (nj == 2) sum_pass(IntC<2>()); else sum_pass(IntC<1>());
+                auto sum_group = [&](auto jc) {
+                    constexpr int J = decltype(jc)::value;
+#pragma unroll 2
+                    for (int q = 0; q < nq; ++q) {
+                        uint32_t c2r8, gb, plo, phi;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c2r8), "=r"(gb), "=r"(plo), "=r"(phi)
+                                     : "r"(stage + 16u * (uint32_t)q));
+                        const double phin = __hiloint2double((int)phi, (int)plo);
+                        const uint32_t dd = (uint32_t)abs((int)c2r8 - c2j8[J]);
+                        double g, inv;
+                        asm("ld.shared.f64 %0, [%1+%2];" : "=d"(g) : "r"(gb + dd), "n"(lay::INV));
+                        asm("ld.shared.f64 %0, [%1+%2];" : "=d"(inv) : "r"(t.sb + dd), "n"(lay::INV));
+                        s1[J] += g;
+                        s2[J] = fma(phin, inv, s2[J]);
+                    }
+                };
+                if (all_groups) {
+                    if (nj >= 4) sum_pass(IntC<4>()); else if (nj == 3) sum_pass(IntC<3>());
+                    else if (nj == 2) sum_pass(IntC<2>()); else sum_pass(IntC<1>());
+                } else {
+                    if (wmask & 1u) sum_group(IntC<0>());
+                    if (wmask & 2u) sum_group(IntC<1>());
+                    if (wmask & 4u) sum_group(IntC<2>());
+                    if (wmask & 8u) sum_group(IntC<3>());
+                }
             }
             const double w1 = t.W1(l), w2 = t.W2(l);   // W2 is stored negated
 #pragma unroll
