@@ -69,7 +69,8 @@ def test_observation_vs_reference_recording(tag, topo):
     eng.close()
 
 
-@pytest.mark.parametrize("topo,n_slots,load", [("germany50", 640, 800.0), ("var_k3_nsfnet", 160, 150.0)])
+@pytest.mark.parametrize("topo,n_slots,load", [("germany50", 640, 800.0), ("var_k3_nsfnet", 160, 150.0), ("nsfnet", 100, 70.0),
+                                               ("nsfnet", 64, 40.0)])
 def test_batched_observation_vs_oracle(topo, n_slots, load):
     """Several envs at different fill levels: germany50/640 (the general kernel: two c2 passes per thread, non-prunable
     paths) and NSFNET with 160 slots and k = 3 (the link-major kernel away from its 320-slot / k = 5 shape: two live
@@ -78,7 +79,10 @@ def test_batched_observation_vs_oracle(topo, n_slots, load):
     from optical_networking_gym_b200.engine import Engine
     from optical_networking_gym_b200.tracegen import TraceGenerator
 
-    tb = load_tables(topo, n_slots)
+    # (100 and 64 slots: the 320-slot NSFNET tables re-dimensioned -- a spectrum that ends inside a bitmap word, and the
+    # smallest one, where the link-major kernel's scratch is sized by its record staging area)
+    tb = load_tables(topo, n_slots) if (topo, n_slots) != ("nsfnet", 100) and (topo, n_slots) != ("nsfnet", 64) \
+        else load_tables("nsfnet", 320).replace(n_slots=n_slots)
     n_envs, n_req = 5, 400
     tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, load, base_seed=321).next(n_req)
     eng = Engine(tb, n_envs, n_req)

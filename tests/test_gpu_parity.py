@@ -225,7 +225,7 @@ def test_highest_snr_policy_vs_reference(tag):
 
 
 @pytest.mark.parametrize("topo,n_slots,load,n_envs,n", [("nobel-eu", 320, 450.0, 7, 60), ("germany50", 640, 800.0, 5, 40),
-                                                       ("var_k3_nsfnet", 160, 150.0, 6, 120)])
+                                                       ("var_k3_nsfnet", 160, 150.0, 6, 120), ("nsfnet", 100, 70.0, 6, 120)])
 def test_highest_snr_policy_batched_vs_oracle(topo, n_slots, load, n_envs, n):
     """Several envs per launch against the oracle on CPython-exact traces: the link-major kernel (spectra up to 320
     slots, k_step_highest_snr_links) and the general one (640 slots, k_step_highest_snr)."""
@@ -234,7 +234,7 @@ def test_highest_snr_policy_batched_vs_oracle(topo, n_slots, load, n_envs, n):
     from optical_networking_gym_b200.tracegen import TraceGenerator
     from oracle import oracle as orc
 
-    tb = load_tables(topo, n_slots)
+    tb = load_tables(topo, n_slots) if (topo, n_slots) != ("nsfnet", 100) else load_tables("nsfnet", 320).replace(n_slots=100)
     tr = TraceGenerator(n_envs, tb.n_nodes, tb.n_rates, load, base_seed=77).next(n + 1)
     eng = Engine(tb, n_envs, n + 1)
     eng.reset(); eng.load_trace_host(*tr)
