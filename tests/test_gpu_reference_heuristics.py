@@ -39,6 +39,11 @@ def _same_request(cs, rs):
                                         ("best_modulation_load_balancing", 120),
                                         ("heuristic_load_balancing_first_fit", 80),
                                         ("heuristic_psr", 12),
+                                        ("heuristic_highest_snr", 25),
+                                        ("shortest_available_path_lowest_spectrum_best_modulation", 100),
+                                        ("load_balancing_best_modulation", 80),
+                                        # (heuristic_mscl itself takes minutes per request on the reference env: not run here)
+                                        ("heuristic_mscl_simplified", 40),
                                         # exact fit takes a free block of exactly n slots without a guard slot: step() then
                                         # answers "not free" and does not consume the request (qrmsa.pyx:886-897), so the
                                         # reference's own loop stops advancing -- the B200 env must stall the same way
